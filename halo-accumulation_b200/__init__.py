@@ -1,0 +1,152 @@
+"""halo-accumulation on B200: host-side mirror of the reference's hot-path interface.
+
+`Context` wraps the C ABI of libhalo_b200.so (include/halo_b200.h): hand-written sm_100a CUDA for the
+Pallas MSMs, IPA folds and h-expansion behind PCDL / ASDL.  The submodules `group`, `pedersen`, `pcdl`
+and `acc` mirror the reference's Rust modules of the same names (code/src/*.rs) on top of it.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _build
+from ._capi import HaloError, arr, load, p64, u8p
+
+__all__ = ["Context", "HaloError", "build"]
+
+
+def build(force=False):
+    return _build.build(force=force)
+
+
+class Context:
+    """One CUDA device + resident public parameters (replaces consts.rs:23-68)."""
+
+    def __init__(self, device=0, max_n=1 << 20):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.halo_ctx_create(int(device), C.c_uint64(max_n), C.byref(h))
+        if rc != 0:
+            raise HaloError(rc, "halo_ctx_create failed (no usable CUDA device? there is no CPU fallback)")
+        self._h = h
+        self.device = device
+        self.max_n = max_n
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.halo_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise HaloError(rc, self._lib.halo_last_error(self._h).decode())
+
+    # ---- parameters ----
+    def derive_generators(self, n):
+        self._chk(self._lib.halo_derive_generators(self._h, C.c_uint64(n)))
+
+    def load_generators(self, S, H, gs):
+        S, H, gs = arr(S, (12,)), arr(H, (12,)), arr(gs).reshape(-1, 8)
+        self._chk(self._lib.halo_load_generators(self._h, p64(S), p64(H), p64(gs), C.c_uint64(gs.shape[0])))
+
+    def get_generators(self, off, n):
+        out = np.zeros((n, 8), dtype=np.uint64)
+        self._chk(self._lib.halo_get_generators(self._h, C.c_uint64(off), C.c_uint64(n), p64(out)))
+        return out
+
+    def get_SH(self):
+        S, H = np.zeros(12, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
+        self._chk(self._lib.halo_get_SH(self._h, p64(S), p64(H)))
+        return S, H
+
+    def derive_points(self, start, count):
+        out = np.zeros((count, 8), dtype=np.uint64)
+        self._chk(self._lib.halo_derive_points(self._h, C.c_uint64(start), C.c_uint64(count), p64(out)))
+        return out
+
+    # ---- MSM ----
+    def msm_gens(self, scalars, off=0):
+        s = arr(scalars).reshape(-1, 4)
+        out = np.zeros(12, dtype=np.uint64)
+        self._chk(self._lib.halo_msm_gens(self._h, p64(s), C.c_uint64(off), C.c_uint64(s.shape[0]), p64(out)))
+        return out
+
+    def msm_gens_resident(self, d_ptr, n, off=0):
+        out = np.zeros(12, dtype=np.uint64)
+        self._chk(self._lib.halo_msm_gens_resident(self._h, C.c_void_p(d_ptr), C.c_uint64(off), C.c_uint64(n), p64(out)))
+        return out
+
+    def msm(self, bases_affine, scalars, inf_flags=None):
+        b, s = arr(bases_affine).reshape(-1, 8), arr(scalars).reshape(-1, 4)
+        n = min(b.shape[0], s.shape[0])  # msm_unchecked truncates to the shorter input
+        out = np.zeros(12, dtype=np.uint64)
+        infp = None
+        if inf_flags is not None:
+            inf_flags = np.ascontiguousarray(inf_flags, dtype=np.uint8)
+            infp = inf_flags.ctypes.data_as(u8p)
+        self._chk(self._lib.halo_msm(self._h, p64(b), infp, p64(s), C.c_uint64(n), p64(out)))
+        return out
+
+    def msm_jac(self, bases_jac, scalars):
+        b, s = arr(bases_jac).reshape(-1, 12), arr(scalars).reshape(-1, 4)
+        n = min(b.shape[0], s.shape[0])
+        out = np.zeros(12, dtype=np.uint64)
+        self._chk(self._lib.halo_msm_jac(self._h, p64(b), p64(s), C.c_uint64(n), p64(out)))
+        return out
+
+    # ---- tuning / accounting ----
+    def set_msm_window(self, c):
+        self._chk(self._lib.halo_set_msm_window(self._h, int(c)))
+
+    def set_profiling(self, on):
+        self._chk(self._lib.halo_set_profiling(self._h, int(bool(on))))
+
+    def last_msm_timings(self):
+        t = (C.c_float * 6)()
+        self._chk(self._lib.halo_last_msm_timings(self._h, t))
+        return dict(zip(["digits", "scan", "scatter", "accumulate", "reduce", "total"], list(t)))
+
+    def kernel_launches(self):
+        return int(self._lib.halo_kernel_launches(self._h))
+
+    # ---- test hooks (include/halo_b200_test.h) ----
+    def test_fp_op(self, which, op, a, b=None):
+        a = arr(a).reshape(-1, 4)
+        out = np.zeros_like(a)
+        bp = None
+        if b is not None:
+            b = arr(b).reshape(-1, 4)
+            bp = p64(b)
+        self._chk(self._lib.halo_test_fp_op(self._h, which, op, p64(a), bp, p64(out), C.c_uint64(a.shape[0])))
+        return out
+
+    def test_madd_chain(self, affine, neg=None):
+        a = arr(affine).reshape(-1, 8)
+        out = np.zeros(12, dtype=np.uint64)
+        negp = None
+        if neg is not None:
+            neg = np.ascontiguousarray(neg, dtype=np.uint8)
+            negp = neg.ctypes.data_as(u8p)
+        self._chk(self._lib.halo_test_madd_chain(self._h, p64(a), negp, C.c_uint64(a.shape[0]), p64(out)))
+        return out
+
+    def test_add_chain(self, jac, dbls=0):
+        a = arr(jac).reshape(-1, 12)
+        out = np.zeros(12, dtype=np.uint64)
+        self._chk(self._lib.halo_test_add_chain(self._h, p64(a), C.c_uint64(a.shape[0]), int(dbls), p64(out)))
+        return out
+
+    def test_fp_mul_throughput(self, blocks, threads, iters, ilp=1):
+        ms, ck = C.c_float(), C.c_uint64()
+        self._chk(self._lib.halo_test_fp_mul_throughput(self._h, blocks, threads, iters, ilp, C.byref(ms), C.byref(ck)))
+        return ms.value
+
+    def test_imad_throughput(self, kind, blocks, threads, iters):
+        ms, ck = C.c_float(), C.c_uint64()
+        self._chk(self._lib.halo_test_imad_throughput(self._h, kind, blocks, threads, iters, C.byref(ms), C.byref(ck)))
+        return ms.value

@@ -1,0 +1,269 @@
+// capi.cu -- extern "C" entry points of libhalo_b200.so (include/halo_b200.h).
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/halo_b200.h"
+#include "common.cuh"
+#include "msm.cuh"
+#include "params.cuh"
+
+using namespace halo;
+
+namespace halo {
+
+__global__ void __launch_bounds__(256) k_mark_infinity(affine_t* __restrict__ bases, const uint8_t* __restrict__ inf, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && inf[i]) affine_set_inf(bases[i]);
+}
+
+__global__ void __launch_bounds__(128) k_jac_to_affine(const jac_t* __restrict__ in, affine_t* __restrict__ out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    jac_t p = in[i];
+    xyzz_t q;
+    jac_to_xyzz(q, p);
+    affine_t a;
+    xyzz_to_affine(a, q);
+    out[i] = a;
+}
+
+int set_error(halo_ctx* ctx, int code, const char* fmt, const char* a, const char* b, int line) {
+    if (ctx) {
+        char buf[512];
+        snprintf(buf, sizeof buf, fmt, a, b, line);
+        ctx->last_error = buf;
+    }
+    return code;
+}
+
+}  // namespace halo
+
+#define HALO_TRY(ctx) \
+    try {             \
+        HALO_CUDA(cudaSetDevice((ctx)->device));
+#define HALO_CATCH(ctx)                                                                                        \
+    }                                                                                                          \
+    catch (const halo::CudaError& e) {                                                                         \
+        return halo::set_error(ctx, HALO_ECUDA, "CUDA error: %s at %s:%d", cudaGetErrorString(e.err), e.file, e.line); \
+    }                                                                                                          \
+    catch (const std::bad_alloc&) {                                                                            \
+        return halo::set_error(ctx, HALO_ENOMEM, "out of host memory%s%s%d", "", "", 0);                        \
+    }                                                                                                          \
+    return HALO_OK;
+
+static int fail(halo_ctx* ctx, int code, const char* msg) {
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+static void out_jac_from_xyzz(const xyzz_t& p, uint64_t out[12]) {
+    jac_t j;
+    xyzz_to_jac(j, p);
+    memcpy(out, &j, 96);
+}
+
+extern "C" {
+
+int halo_ctx_create(int device, uint64_t max_n, halo_ctx** out) {
+    if (!out) return HALO_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return HALO_ECUDA;
+    halo_ctx* ctx = new halo_ctx();
+    ctx->device = device;
+    ctx->max_n = max_n;
+    try {
+        HALO_CUDA(cudaSetDevice(device));
+        HALO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->ev) HALO_CUDA(cudaEventCreate(&e));
+    } catch (const halo::CudaError&) {
+        delete ctx;
+        return HALO_ECUDA;
+    }
+    *out = ctx;
+    return HALO_OK;
+}
+
+void halo_ctx_destroy(halo_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->gens.release();
+    ctx->fixed_table.release();
+    ctx->stage_scalars.release();
+    ctx->stage_bases.release();
+    ctx->stage_misc.release();
+    MsmWorkspace& ws = ctx->ws;
+    for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,
+                      &ws.task_bucket, &ws.task_partial})
+        b->release();
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* halo_last_error(halo_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+uint64_t halo_kernel_launches(halo_ctx* ctx) { return ctx ? ctx->kernel_launches : 0; }
+int halo_set_msm_window(halo_ctx* ctx, int c) {
+    if (!ctx || c < 0 || c > 20) return HALO_EINVAL;
+    ctx->force_c = c;
+    return HALO_OK;
+}
+int halo_set_profiling(halo_ctx* ctx, int on) {
+    if (!ctx) return HALO_EINVAL;
+    ctx->profile = on != 0;
+    return HALO_OK;
+}
+int halo_last_msm_timings(halo_ctx* ctx, float out_ms[6]) {
+    if (!ctx) return HALO_EINVAL;
+    const Timings& t = ctx->last;
+    out_ms[0] = t.digits_ms;
+    out_ms[1] = t.scan_ms;
+    out_ms[2] = t.scatter_ms;
+    out_ms[3] = t.accumulate_ms;
+    out_ms[4] = t.reduce_ms;
+    out_ms[5] = t.total_ms;
+    return HALO_OK;
+}
+
+int halo_derive_generators(halo_ctx* ctx, uint64_t n) {
+    if (!ctx) return HALO_EINVAL;
+    if (n == 0 || n > ctx->max_n) return fail(ctx, HALO_EINVAL, "halo_derive_generators: n exceeds max_n");
+    HALO_TRY(ctx)
+    // P_0 = S, P_1 = H land in a small staging buffer; G_i = P_{i+2} directly in the resident array
+    ctx->gens.reserve(n * sizeof(affine_t));
+    ctx->stage_misc.reserve(2 * sizeof(affine_t));
+    params_derive_points(ctx, 0, 2, ctx->stage_misc.as<affine_t>());
+    params_derive_points(ctx, 2, n, ctx->gens.as<affine_t>());
+    affine_t sh[2];
+    HALO_CUDA(cudaMemcpyAsync(sh, ctx->stage_misc.p, sizeof sh, cudaMemcpyDeviceToHost, ctx->stream));
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->S = sh[0];
+    ctx->H = sh[1];
+    ctx->have_SH = true;
+    ctx->n_gens = n;
+    HALO_CATCH(ctx)
+}
+
+int halo_load_generators(halo_ctx* ctx, const uint64_t S_jac[12], const uint64_t H_jac[12], const uint64_t* gs_affine,
+                         uint64_t n) {
+    if (!ctx || !gs_affine) return HALO_EINVAL;
+    if (n == 0 || n > ctx->max_n) return fail(ctx, HALO_EINVAL, "halo_load_generators: n exceeds max_n");
+    HALO_TRY(ctx)
+    ctx->gens.reserve(n * sizeof(affine_t));
+    HALO_CUDA(cudaMemcpyAsync(ctx->gens.p, gs_affine, n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (S_jac && H_jac) {
+        jac_t s, h;
+        memcpy(&s, S_jac, 96);
+        memcpy(&h, H_jac, 96);
+        xyzz_t t;
+        jac_to_xyzz(t, s);
+        xyzz_to_affine(ctx->S, t);
+        jac_to_xyzz(t, h);
+        xyzz_to_affine(ctx->H, t);
+        ctx->have_SH = true;
+    }
+    ctx->n_gens = n;
+    HALO_CATCH(ctx)
+}
+
+int halo_get_generators(halo_ctx* ctx, uint64_t off, uint64_t n, uint64_t* out_affine) {
+    if (!ctx || !out_affine) return HALO_EINVAL;
+    if (off + n > ctx->n_gens) return fail(ctx, HALO_EINVAL, "halo_get_generators: range exceeds resident generators");
+    HALO_TRY(ctx)
+    HALO_CUDA(cudaMemcpyAsync(out_affine, ctx->gens.as<affine_t>() + off, n * sizeof(affine_t), cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    HALO_CATCH(ctx)
+}
+
+int halo_get_SH(halo_ctx* ctx, uint64_t S_jac[12], uint64_t H_jac[12]) {
+    if (!ctx || !ctx->have_SH) return fail(ctx, HALO_ESTATE, "halo_get_SH: parameters not loaded");
+    xyzz_t t;
+    xyzz_from_affine(t, ctx->S);
+    out_jac_from_xyzz(t, S_jac);
+    xyzz_from_affine(t, ctx->H);
+    out_jac_from_xyzz(t, H_jac);
+    return HALO_OK;
+}
+
+int halo_derive_points(halo_ctx* ctx, uint64_t start, uint64_t count, uint64_t* out_affine) {
+    if (!ctx || !out_affine) return HALO_EINVAL;
+    HALO_TRY(ctx)
+    ctx->stage_bases.reserve(count * sizeof(affine_t));
+    params_derive_points(ctx, start, count, ctx->stage_bases.as<affine_t>());
+    HALO_CUDA(cudaMemcpyAsync(out_affine, ctx->stage_bases.p, count * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream));
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    HALO_CATCH(ctx)
+}
+
+int halo_msm_gens_resident(halo_ctx* ctx, const void* d_scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]) {
+    if (!ctx || !out_jac || (!d_scalars && n)) return HALO_EINVAL;
+    if (off + n > ctx->n_gens) return fail(ctx, HALO_ESTATE, "halo_msm_gens: range exceeds resident generators");
+    HALO_TRY(ctx)
+    xyzz_t r;
+    msm_device(ctx, ctx->gens.as<affine_t>() + off, reinterpret_cast<const fr_t*>(d_scalars), n, r);
+    out_jac_from_xyzz(r, out_jac);
+    HALO_CATCH(ctx)
+}
+
+int halo_msm_gens(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]) {
+    if (!ctx || !out_jac || (!scalars && n)) return HALO_EINVAL;
+    if (off + n > ctx->n_gens) return fail(ctx, HALO_ESTATE, "halo_msm_gens: range exceeds resident generators");
+    HALO_TRY(ctx)
+    ctx->stage_scalars.reserve((n ? n : 1) * sizeof(fr_t));
+    if (n) HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    xyzz_t r;
+    msm_device(ctx, ctx->gens.as<affine_t>() + off, ctx->stage_scalars.as<fr_t>(), n, r);
+    out_jac_from_xyzz(r, out_jac);
+    HALO_CATCH(ctx)
+}
+
+int halo_msm(halo_ctx* ctx, const uint64_t* bases_affine, const uint8_t* inf_flags, const uint64_t* scalars, uint64_t n,
+             uint64_t out_jac[12]) {
+    if (!ctx || !out_jac || ((!scalars || !bases_affine) && n)) return HALO_EINVAL;
+    if (n > ctx->max_n) return fail(ctx, HALO_EINVAL, "halo_msm: n exceeds max_n");
+    HALO_TRY(ctx)
+    ctx->stage_scalars.reserve((n ? n : 1) * sizeof(fr_t));
+    ctx->stage_bases.reserve((n ? n : 1) * sizeof(affine_t));
+    if (n) {
+        HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        HALO_CUDA(cudaMemcpyAsync(ctx->stage_bases.p, bases_affine, n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (inf_flags) {
+            ctx->stage_misc.reserve(n);
+            HALO_CUDA(cudaMemcpyAsync(ctx->stage_misc.p, inf_flags, n, cudaMemcpyHostToDevice, ctx->stream));
+            k_mark_infinity<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->stage_bases.as<affine_t>(),
+                                                                                 ctx->stage_misc.as<uint8_t>(), n);
+            ctx->kernel_launches++;
+        }
+    }
+    xyzz_t r;
+    msm_device(ctx, ctx->stage_bases.as<affine_t>(), ctx->stage_scalars.as<fr_t>(), n, r);
+    out_jac_from_xyzz(r, out_jac);
+    HALO_CATCH(ctx)
+}
+
+int halo_msm_jac(halo_ctx* ctx, const uint64_t* bases_jac, const uint64_t* scalars, uint64_t n, uint64_t out_jac[12]) {
+    if (!ctx || !out_jac || ((!scalars || !bases_jac) && n)) return HALO_EINVAL;
+    if (n > ctx->max_n) return fail(ctx, HALO_EINVAL, "halo_msm_jac: n exceeds max_n");
+    HALO_TRY(ctx)
+    ctx->stage_scalars.reserve((n ? n : 1) * sizeof(fr_t));
+    ctx->stage_bases.reserve((n ? n : 1) * sizeof(affine_t));
+    ctx->stage_misc.reserve((n ? n : 1) * sizeof(jac_t));
+    if (n) {
+        HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        HALO_CUDA(cudaMemcpyAsync(ctx->stage_misc.p, bases_jac, n * sizeof(jac_t), cudaMemcpyHostToDevice, ctx->stream));
+        k_jac_to_affine<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->stage_misc.as<jac_t>(),
+                                                                             ctx->stage_bases.as<affine_t>(), n);
+        ctx->kernel_launches++;
+    }
+    xyzz_t r;
+    msm_device(ctx, ctx->stage_bases.as<affine_t>(), ctx->stage_scalars.as<fr_t>(), n, r);
+    out_jac_from_xyzz(r, out_jac);
+    HALO_CATCH(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// common.cuh -- shared host-side declarations for libhalo_b200.so (context, workspaces, error plumbing).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "ec.cuh"
+
+namespace halo {
+
+// Error codes cross the C ABI as ints; see include/halo_b200.h.
+enum : int {
+    E_OK = 0,
+    E_INVAL = -1,
+    E_LEN = -2,
+    E_CUDA = -3,
+    E_NCCL = -4,
+    E_NOMEM = -5,
+    E_STATE = -6,
+};
+
+struct CudaError {
+    cudaError_t err;
+    const char* what;
+    const char* file;
+    int line;
+};
+
+#define HALO_CUDA(expr)                                                      \
+    do {                                                                     \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) throw halo::CudaError{_e, #expr, __FILE__, __LINE__}; \
+    } while (0)
+
+// Device buffer that only grows; owned by a context, never handed across the ABI.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) HALO_CUDA(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        HALO_CUDA(cudaMalloc(&p, bytes));
+        cap = bytes;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+// MSM plan: window width c, W windows, M = 2^(c-1) buckets per window (signed digits).
+struct MsmPlan {
+    int c = 0;
+    int W = 0;
+    uint32_t M = 0;
+    uint32_t NB = 0;  // W * M
+};
+MsmPlan msm_make_plan(uint64_t n, int force_c);
+
+struct MsmWorkspace {
+    DevBuf counts, offsets, cursor, entries, buckets, wsums, scan_tmp;
+    DevBuf task_bucket, task_partial;  // bucket splitting for skewed inputs
+};
+
+struct Timings {
+    float digits_ms = 0, scan_ms = 0, scatter_ms = 0, accumulate_ms = 0, reduce_ms = 0, total_ms = 0;
+};
+
+}  // namespace halo
+
+// The opaque handle behind `halo_ctx*` (include/halo_b200.h).
+struct halo_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t max_n = 0;
+    // public parameters (consts.rs:23-68): G_0..G_{n_gens-1} resident in HBM as Montgomery affine, S and H on host
+    halo::DevBuf gens;
+    uint64_t n_gens = 0;
+    halo::affine_t S, H;
+    bool have_SH = false;
+    halo::DevBuf fixed_table;  // fixed-base table for generator derivation (K6)
+    // scratch
+    halo::MsmWorkspace ws;
+    halo::DevBuf stage_scalars, stage_bases, stage_misc;
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+    int force_c = 0;
+    uint64_t kernel_launches = 0;
+    halo::Timings last;
+    bool profile = false;
+    cudaEvent_t ev[8] = {};
+    std::string last_error;
+};

@@ -1,0 +1,323 @@
+// fp.cuh -- 255-bit Montgomery field core for the two Pasta moduli (K1 in SURVEY.md section 2b).
+//
+// Replaces, for the hot path, arkworks' `Fp<MontBackend<_, 4>>` arithmetic beneath every call site
+// listed in SURVEY.md section 8a (group.rs:13-37, pcdl.rs:195-227, pcdl.rs:56-77).  Elements use the
+// reference's in-memory layout bit for bit: 256-bit little-endian Montgomery residues with
+// R = 2^256 (consts.rs:4-21, main.rs:47-53), here viewed as 8 x u32 limbs so every product is a
+// 32-bit IMAD / IMAD.WIDE on the sm_100a integer pipe.
+//
+// Both moduli have the shape  p = 2^254 + t  with  t < 2^126  and  p = 1 (mod 2^32):
+//   limbs(p) = [1, P1, P2, P3, 0, 0, 0, 0x40000000]   and   -p^-1 mod 2^32 = 0xffffffff,
+// so one Montgomery reduction step is  m = -T[i]  (no multiply), three real 32x32 products
+// (m*P1, m*P2, m*P3) and a shift (m * 2^30).  See DESIGN.md section "K1".
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HALO_HD __host__ __device__ __forceinline__
+#else
+#define HALO_HD inline
+#endif
+
+namespace halo {
+
+struct FqParams {  // Pallas base field (point coordinates)
+    static constexpr uint32_t P1 = 0x992d30edu, P2 = 0x094cf91bu, P3 = 0x224698fcu;
+    HALO_HD static constexpr uint32_t one(int i) {
+        constexpr uint32_t v[8] = {0xfffffffdu, 0x34786d38u, 0xe41914adu, 0x992c350bu,
+                                   0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu};
+        return v[i];
+    }
+    HALO_HD static constexpr uint32_t r2(int i) {
+        constexpr uint32_t v[8] = {0x0000000fu, 0x8c78ecb3u, 0x8b0de0e7u, 0xd7d30dbdu,
+                                   0xc3c95d18u, 0x7797a99bu, 0x7b9cb714u, 0x096d41afu};
+        return v[i];
+    }
+};
+struct FrParams {  // Pallas scalar field (= Vesta base field)
+    static constexpr uint32_t P1 = 0x8c46eb21u, P2 = 0x0994a8ddu, P3 = 0x224698fcu;
+    HALO_HD static constexpr uint32_t one(int i) {
+        constexpr uint32_t v[8] = {0xfffffffdu, 0x5b2b3e9cu, 0xe3420567u, 0x992c350bu,
+                                   0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu};
+        return v[i];
+    }
+    HALO_HD static constexpr uint32_t r2(int i) {
+        constexpr uint32_t v[8] = {0x0000000fu, 0xfc9678ffu, 0x891a16e3u, 0x67bb433du,
+                                   0x04ccf590u, 0x7fae2310u, 0x7ccfdaa9u, 0x096d41afu};
+        return v[i];
+    }
+};
+
+template <class P>
+HALO_HD constexpr uint32_t fp_mod(int i) {
+    return i == 0 ? 1u : i == 1 ? P::P1 : i == 2 ? P::P2 : i == 3 ? P::P3 : i == 7 ? 0x40000000u : 0u;
+}
+
+template <class P>
+struct alignas(16) fp_t {
+    uint32_t v[8];
+};
+using fq_t = fp_t<FqParams>;
+using fr_t = fp_t<FrParams>;
+
+template <class P>
+HALO_HD void fp_zero(fp_t<P>& r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+}
+template <class P>
+HALO_HD void fp_one(fp_t<P>& r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+}
+template <class P>
+HALO_HD bool fp_is_zero(const fp_t<P>& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= a.v[i];
+    return o == 0;
+}
+template <class P>
+HALO_HD bool fp_eq(const fp_t<P>& a, const fp_t<P>& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i];
+    return o == 0;
+}
+
+// ---- raw 256-bit helpers ---------------------------------------------------------------------
+// r = a + b, returns carry out
+HALO_HD uint32_t add8(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
+#if defined(__CUDA_ARCH__)
+    uint32_t c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return (uint32_t)c;
+#endif
+}
+// r = a - b, returns borrow out (1 if a < b)
+HALO_HD uint32_t sub8(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
+#if defined(__CUDA_ARCH__)
+    uint32_t c;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c & 1u;  // subc.u32 0,0 with borrow gives 0xffffffff
+#else
+    uint64_t br = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a[i] - b[i] - br;
+        r[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    return (uint32_t)br;
+#endif
+}
+
+template <class P>
+HALO_HD void fp_mod_limbs(uint32_t m[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = fp_mod<P>(i);
+}
+
+// if (x >= p) x -= p      (x < 2p)
+template <class P>
+HALO_HD void fp_reduce_once(uint32_t x[8]) {
+    uint32_t m[8], t[8];
+    fp_mod_limbs<P>(m);
+    uint32_t borrow = sub8(t, x, m);
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = borrow ? x[i] : t[i];
+}
+
+template <class P>
+HALO_HD void fp_add(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
+    uint32_t s[8];
+    add8(s, a.v, b.v);  // a, b < p < 2^255: no carry out
+    fp_reduce_once<P>(s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = s[i];
+}
+template <class P>
+HALO_HD void fp_sub(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
+    uint32_t d[8], m[8], t[8];
+    uint32_t borrow = sub8(d, a.v, b.v);
+    fp_mod_limbs<P>(m);
+    add8(t, d, m);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = borrow ? t[i] : d[i];
+}
+template <class P>
+HALO_HD void fp_dbl(fp_t<P>& r, const fp_t<P>& a) {
+    fp_add(r, a, a);
+}
+template <class P>
+HALO_HD void fp_neg(fp_t<P>& r, const fp_t<P>& a) {
+    uint32_t m[8], t[8];
+    fp_mod_limbs<P>(m);
+    sub8(t, m, a.v);
+    bool z = fp_is_zero(a);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = z ? 0u : t[i];
+}
+// r = neg ? -a : a   (branch-free select used by the signed-digit bucket accumulation)
+template <class P>
+HALO_HD void fp_cneg(fp_t<P>& r, const fp_t<P>& a, bool neg) {
+    fp_t<P> n;
+    fp_neg(n, a);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = neg ? n.v[i] : a.v[i];
+}
+
+// ---- Montgomery multiplication -----------------------------------------------------------------
+// Montgomery reduction of a 16-limb value T < p * 2^256: returns T * 2^-256 mod p in r (fully reduced).
+// Per step i: m = -T[i] (because -p^-1 = -1 mod 2^32); T += m * p * 2^(32 i).  With
+// p = 1 + 2^32 * (P1 + 2^32 P2 + 2^64 P3) + 2^254 the limb T[i] cancels to zero with carry
+// (T[i] != 0), the three products land on limbs i+1..i+4 and m * 2^30 on limbs i+7, i+8.
+template <class P>
+HALO_HD void fp_mont_reduce(uint32_t r[8], uint32_t T[16]) {
+    uint32_t top = 0;  // carry out of limb 15 (T + sum m_i p 2^(32i) < 2p * 2^256 fits 16 limbs + 1 bit)
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t m = 0u - T[i];
+        uint64_t c = (T[i] != 0) ? 1u : 0u;
+        c += (uint64_t)m * P::P1 + T[i + 1];
+        T[i + 1] = (uint32_t)c;
+        c >>= 32;
+        c += (uint64_t)m * P::P2 + T[i + 2];
+        T[i + 2] = (uint32_t)c;
+        c >>= 32;
+        c += (uint64_t)m * P::P3 + T[i + 3];
+        T[i + 3] = (uint32_t)c;
+        c >>= 32;
+#pragma unroll
+        for (int j = 4; j < 7; j++) {
+            c += T[i + j];
+            T[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += ((uint64_t)m << 30) + T[i + 7];
+        T[i + 7] = (uint32_t)c;
+        c >>= 32;
+#pragma unroll
+        for (int j = i + 8; j < 16; j++) {
+            c += T[j];
+            T[j] = (uint32_t)c;
+            c >>= 32;
+        }
+        top += (uint32_t)c;
+    }
+    // result = T[8..16) (+ top * 2^256) < 2p
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = T[8 + i];
+    if (top) {
+        uint32_t m[8], t[8];
+        fp_mod_limbs<P>(m);
+        sub8(t, x, m);
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = t[i];
+    } else {
+        fp_reduce_once<P>(x);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = x[i];
+}
+
+// 8x8 schoolbook product into 16 limbs
+HALO_HD void mul8x8(uint32_t T[16], const uint32_t a[8], const uint32_t b[8]) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) T[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            c += (uint64_t)a[j] * b[i] + T[i + j];
+            T[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        T[i + 8] = (uint32_t)c;
+    }
+}
+
+template <class P>
+HALO_HD void fp_mul(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
+    uint32_t T[16];
+    mul8x8(T, a.v, b.v);
+    fp_mont_reduce<P>(r.v, T);
+}
+template <class P>
+HALO_HD void fp_sqr(fp_t<P>& r, const fp_t<P>& a) {
+    fp_mul(r, a, a);
+}
+
+// Montgomery form <-> canonical integer
+template <class P>
+HALO_HD void fp_to_canon(uint32_t out[8], const fp_t<P>& a) {
+    uint32_t T[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        T[i] = a.v[i];
+        T[8 + i] = 0;
+    }
+    fp_mont_reduce<P>(out, T);
+}
+template <class P>
+HALO_HD void fp_from_canon(fp_t<P>& r, const uint32_t in[8]) {
+    fp_t<P> t, r2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        t.v[i] = in[i];
+        r2.v[i] = P::r2(i);
+    }
+    fp_mul(r, t, r2);
+}
+template <class P>
+HALO_HD void fp_from_u32(fp_t<P>& r, uint32_t x) {
+    uint32_t t[8] = {x, 0, 0, 0, 0, 0, 0, 0};
+    fp_from_canon(r, t);
+}
+
+// a^(p-2) (Fermat).  Used once per normalised point / per IPA round, never in an inner loop.
+template <class P>
+HALO_HD void fp_inv(fp_t<P>& r, const fp_t<P>& a) {
+    // exponent p - 2: limbs(p) with limb0 = 1 - 2 -> borrow: p - 2 = [0xffffffff, P1-1, P2, P3, 0,0,0,0x40000000]
+    uint32_t e[8] = {0xffffffffu, P::P1 - 1u, P::P2, P::P3, 0u, 0u, 0u, 0x40000000u};
+    fp_t<P> acc;
+    fp_one(acc);
+    for (int i = 254; i >= 0; i--) {
+        fp_sqr(acc, acc);
+        if ((e[i >> 5] >> (i & 31)) & 1u) fp_mul(acc, acc, a);
+    }
+    r = acc;
+}
+
+}  // namespace halo

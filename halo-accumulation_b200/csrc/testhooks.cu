@@ -1,0 +1,238 @@
+// testhooks.cu -- device test hooks and integer-pipe microbenchmarks (include/halo_b200_test.h).
+#include <cstring>
+
+#include "../../include/halo_b200_test.h"
+#include "common.cuh"
+
+using namespace halo;
+
+namespace halo {
+
+template <class P>
+__global__ void __launch_bounds__(128) k_fp_op(int op, const fp_t<P>* a, const fp_t<P>* b, fp_t<P>* out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp_t<P> x = a[i], y = b ? b[i] : a[i], r;
+    switch (op) {
+        case 0: fp_mul(r, x, y); break;
+        case 1: fp_add(r, x, y); break;
+        case 2: fp_sub(r, x, y); break;
+        case 3: fp_sqr(r, x); break;
+        case 4: fp_inv(r, x); break;
+        case 5: fp_neg(r, x); break;
+        case 6: fp_to_canon(r.v, x); break;
+        default: fp_from_canon(r, x.v); break;
+    }
+    out[i] = r;
+}
+
+__global__ void k_madd_chain(const affine_t* pts, const uint8_t* neg, uint64_t n, jac_t* out) {
+    if (threadIdx.x || blockIdx.x) return;
+    xyzz_t acc;
+    xyzz_set_inf(acc);
+    for (uint64_t i = 0; i < n; i++) xyzz_madd(acc, pts[i], neg && neg[i]);
+    jac_t j;
+    xyzz_to_jac(j, acc);
+    *out = j;
+}
+__global__ void k_add_chain(const jac_t* pts, uint64_t n, int dbls, jac_t* out) {
+    if (threadIdx.x || blockIdx.x) return;
+    xyzz_t acc;
+    xyzz_set_inf(acc);
+    for (uint64_t i = 0; i < n; i++) {
+        xyzz_t q;
+        jac_to_xyzz(q, pts[i]);
+        xyzz_add(acc, q);
+    }
+    for (int i = 0; i < dbls; i++) xyzz_dbl(acc, acc);
+    jac_t j;
+    xyzz_to_jac(j, acc);
+    *out = j;
+}
+
+template <int ILP>
+__global__ void __launch_bounds__(512) k_fp_mul_tp(int iters, uint32_t* sink) {
+    fq_t x[ILP], y;
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+        fp_one(x[k]);
+        x[k].v[0] ^= tid + k;
+        x[k].v[7] &= 0x0fffffffu;
+    }
+    fp_one(y);
+    y.v[1] ^= tid * 2654435761u;
+    y.v[7] &= 0x0fffffffu;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) fp_mul(x[k], x[k], y);
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc ^= x[k].v[j];
+    if (acc == 0x12345678u) sink[0] = acc;  // keep the chain alive without a store per thread
+    if (tid == 0) sink[1] = acc;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(1024) k_imad_tp(int iters, uint32_t* sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a = tid * 2654435761u + 12345u, b = tid ^ 0x9e3779b9u;
+    uint32_t r[16];
+    uint64_t w[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        r[k] = tid + k;
+        w[k] = tid + 7 * k;
+    }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (KIND == 0) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r[k]) : "r"(a), "r"(b));
+            if (KIND == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"(a), "r"(b));
+            if (KIND == 2) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(r[k]) : "r"(a), "r"(b));
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc ^= r[k] ^ (uint32_t)w[k] ^ (uint32_t)(w[k] >> 32);
+    if (acc == 0x12345678u) sink[0] = acc;
+    if (tid == 0) sink[1] = acc;
+}
+
+}  // namespace halo
+
+#define T_TRY(ctx) try { HALO_CUDA(cudaSetDevice((ctx)->device));
+#define T_CATCH(ctx)                                        \
+    }                                                       \
+    catch (const halo::CudaError& e) {                      \
+        (ctx)->last_error = cudaGetErrorString(e.err);      \
+        return HALO_ECUDA;                                  \
+    }                                                       \
+    return HALO_OK;
+
+extern "C" {
+
+int halo_test_fp_op(halo_ctx* ctx, int which, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
+    if (!ctx || !a || !out) return HALO_EINVAL;
+    T_TRY(ctx)
+    DevBuf da, db, dout;
+    da.reserve(n * 32);
+    dout.reserve(n * 32);
+    HALO_CUDA(cudaMemcpy(da.p, a, n * 32, cudaMemcpyHostToDevice));
+    if (b) {
+        db.reserve(n * 32);
+        HALO_CUDA(cudaMemcpy(db.p, b, n * 32, cudaMemcpyHostToDevice));
+    }
+    unsigned grid = (unsigned)((n + 127) / 128);
+    if (which)
+        k_fp_op<FrParams><<<grid, 128, 0, ctx->stream>>>(op, da.as<fr_t>(), b ? db.as<fr_t>() : nullptr, dout.as<fr_t>(), n);
+    else
+        k_fp_op<FqParams><<<grid, 128, 0, ctx->stream>>>(op, da.as<fq_t>(), b ? db.as<fq_t>() : nullptr, dout.as<fq_t>(), n);
+    ctx->kernel_launches++;
+    HALO_CUDA(cudaGetLastError());
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    HALO_CUDA(cudaMemcpy(out, dout.p, n * 32, cudaMemcpyDeviceToHost));
+    da.release();
+    db.release();
+    dout.release();
+    T_CATCH(ctx)
+}
+
+int halo_test_madd_chain(halo_ctx* ctx, const uint64_t* affine, const uint8_t* neg, uint64_t n, uint64_t out_jac[12]) {
+    if (!ctx || !out_jac) return HALO_EINVAL;
+    T_TRY(ctx)
+    DevBuf dp, dn, dout;
+    dp.reserve((n ? n : 1) * 64);
+    dout.reserve(96);
+    if (n) HALO_CUDA(cudaMemcpy(dp.p, affine, n * 64, cudaMemcpyHostToDevice));
+    if (neg && n) {
+        dn.reserve(n);
+        HALO_CUDA(cudaMemcpy(dn.p, neg, n, cudaMemcpyHostToDevice));
+    }
+    k_madd_chain<<<1, 32, 0, ctx->stream>>>(dp.as<affine_t>(), neg ? dn.as<uint8_t>() : nullptr, n, dout.as<jac_t>());
+    ctx->kernel_launches++;
+    HALO_CUDA(cudaGetLastError());
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    HALO_CUDA(cudaMemcpy(out_jac, dout.p, 96, cudaMemcpyDeviceToHost));
+    dp.release();
+    dn.release();
+    dout.release();
+    T_CATCH(ctx)
+}
+
+int halo_test_add_chain(halo_ctx* ctx, const uint64_t* jac, uint64_t n, int dbls, uint64_t out_jac[12]) {
+    if (!ctx || !out_jac) return HALO_EINVAL;
+    T_TRY(ctx)
+    DevBuf dp, dout;
+    dp.reserve((n ? n : 1) * 96);
+    dout.reserve(96);
+    if (n) HALO_CUDA(cudaMemcpy(dp.p, jac, n * 96, cudaMemcpyHostToDevice));
+    k_add_chain<<<1, 32, 0, ctx->stream>>>(dp.as<jac_t>(), n, dbls, dout.as<jac_t>());
+    ctx->kernel_launches++;
+    HALO_CUDA(cudaGetLastError());
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    HALO_CUDA(cudaMemcpy(out_jac, dout.p, 96, cudaMemcpyDeviceToHost));
+    dp.release();
+    dout.release();
+    T_CATCH(ctx)
+}
+
+int halo_test_fp_mul_throughput(halo_ctx* ctx, int blocks, int threads, int iters, int ilp, float* ms, uint64_t* checksum) {
+    if (!ctx || !ms) return HALO_EINVAL;
+    T_TRY(ctx)
+    DevBuf sink;
+    sink.reserve(16);
+    cudaEvent_t e0, e1;
+    HALO_CUDA(cudaEventCreate(&e0));
+    HALO_CUDA(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {
+        HALO_CUDA(cudaEventRecord(e0, ctx->stream));
+        if (ilp == 1) k_fp_mul_tp<1><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else if (ilp == 2) k_fp_mul_tp<2><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else k_fp_mul_tp<4><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        HALO_CUDA(cudaEventRecord(e1, ctx->stream));
+        HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->kernel_launches += 2;
+    HALO_CUDA(cudaGetLastError());
+    HALO_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    uint32_t h[4] = {0, 0, 0, 0};
+    HALO_CUDA(cudaMemcpy(h, sink.p, 8, cudaMemcpyDeviceToHost));
+    if (checksum) *checksum = h[1];
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    sink.release();
+    T_CATCH(ctx)
+}
+
+int halo_test_imad_throughput(halo_ctx* ctx, int kind, int blocks, int threads, int iters, float* ms, uint64_t* checksum) {
+    if (!ctx || !ms) return HALO_EINVAL;
+    T_TRY(ctx)
+    DevBuf sink;
+    sink.reserve(16);
+    cudaEvent_t e0, e1;
+    HALO_CUDA(cudaEventCreate(&e0));
+    HALO_CUDA(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {
+        HALO_CUDA(cudaEventRecord(e0, ctx->stream));
+        if (kind == 0) k_imad_tp<0><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else if (kind == 1) k_imad_tp<1><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else k_imad_tp<2><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        HALO_CUDA(cudaEventRecord(e1, ctx->stream));
+        HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->kernel_launches += 2;
+    HALO_CUDA(cudaGetLastError());
+    HALO_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    uint32_t h[4] = {0, 0, 0, 0};
+    HALO_CUDA(cudaMemcpy(h, sink.p, 8, cudaMemcpyDeviceToHost));
+    if (checksum) *checksum = h[1];
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    sink.release();
+    T_CATCH(ctx)
+}
+}

@@ -1,0 +1,91 @@
+/*
+ * halo_b200.h -- C ABI of libhalo_b200.so: the B200 (sm_100a) implementation of the data-parallel hot
+ * path of rasmus-kirk/halo-accumulation (PCDL commit / open / succinct check / check, ASDL decider).
+ *
+ * This is the drop-in boundary: exactly the entry points a Rust FFI shim inside the reference crate
+ * would bind to replace the bodies of group.rs:13-37 and the loops of pcdl.rs:195-227 / pcdl.rs:56-77,338
+ * (see INTEGRATION.md for the `extern "C"` block and the marshalling code).  Plain pointers and sizes
+ * only; no C++ or torch types.  Paths below are relative to the reference tree (code/src/...).
+ *
+ * Data layout (identical to arkworks' in-memory representation, consts.rs:4-21, main.rs:47-53,91-100):
+ *   scalar  (PallasScalar, Fr)  : uint64_t[4], little-endian limbs, Montgomery form, R = 2^256
+ *   base-field element (Fq)     : uint64_t[4], same
+ *   affine point (PallasAffine) : uint64_t[8] = x[4] | y[4]; infinity via a separate flag byte
+ *   Jacobian point (PallasPoint): uint64_t[12] = x[4] | y[4] | z[4]; infinity <=> z == 0
+ * Points returned by the library are valid Jacobian representatives of the same group element the
+ * reference computes; compare with `==` on `Projective` (cross-multiplied) or after `into_affine()`.
+ *
+ * Conventions: every function returns 0 (HALO_OK) or a negative error code; nothing unwinds across
+ * the ABI; `halo_last_error(ctx)` returns a human-readable message for the last failure on that
+ * context.  Verifier-style rejections are NOT errors at this level: the library returns points and
+ * scalars, the host layer above (pcdl / acc) raises the reference's `ensure!` failures.
+ * A context is bound to one CUDA device and one stream; it is not thread-safe (the reference is
+ * single-threaded); calls are synchronous unless the name ends in `_async`.  All host buffers are
+ * owned by the caller; all device memory is owned by the context.  There is no CPU fallback: if
+ * no CUDA device is usable, halo_ctx_create fails with HALO_ECUDA.
+ */
+#ifndef HALO_B200_H
+#define HALO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HALO_OK 0
+#define HALO_EINVAL (-1) /* n not a power of two / exceeds the context's max_n (pcdl.rs:102-104, :261-262) */
+#define HALO_ELEN (-2)   /* length mismatch (pedersen.rs:7-12) */
+#define HALO_ECUDA (-3)  /* CUDA runtime failure; see halo_last_error */
+#define HALO_ENCCL (-4)
+#define HALO_ENOMEM (-5)
+#define HALO_ESTATE (-6) /* call out of order (e.g. generators not loaded) */
+
+typedef struct halo_ctx halo_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device` able to handle vectors up to `max_n` elements. */
+int halo_ctx_create(int device, uint64_t max_n, halo_ctx **out);
+void halo_ctx_destroy(halo_ctx *ctx);
+const char *halo_last_error(halo_ctx *ctx);
+/* Count of this library's kernel launches on the context since creation (bench accounting). */
+uint64_t halo_kernel_launches(halo_ctx *ctx);
+/* Tuning / diagnostics: force the Pippenger window width (0 = automatic). */
+int halo_set_msm_window(halo_ctx *ctx, int c);
+/* Enable per-phase CUDA-event timing of the MSM; read back with halo_last_msm_timings (ms):
+ * [digits, scan, scatter, accumulate, bucket_reduce, total]. */
+int halo_set_profiling(halo_ctx *ctx, int on);
+int halo_last_msm_timings(halo_ctx *ctx, float out_ms[6]);
+
+/* ---- public parameters: replaces consts.rs:23-68 (N, S, H, GS) ----------------------------------- */
+/* K6. Derives S = P_0, H = P_1, G_i = P_{i+2}, i < n, on the device by the rule of main.rs:18-45
+ * (P_k = [SHA3-256(genesis || k as u64 LE) mod r] * (-1, 2)) and keeps them resident. */
+int halo_derive_generators(halo_ctx *ctx, uint64_t n);
+/* Alternative: take the reference's own constants (consts::S, consts::H as Jacobian, consts::GS affine). */
+int halo_load_generators(halo_ctx *ctx, const uint64_t S_jac[12], const uint64_t H_jac[12],
+                         const uint64_t *gs_affine /*[n][8]*/, uint64_t n);
+/* Reads generators back (tests / caching): out_affine[i] = G_{off+i}. */
+int halo_get_generators(halo_ctx *ctx, uint64_t off, uint64_t n, uint64_t *out_affine /*[n][8]*/);
+int halo_get_SH(halo_ctx *ctx, uint64_t S_jac[12], uint64_t H_jac[12]);
+/* Raw derivation without installing: out_affine[i] = P_{start+i}. */
+int halo_derive_points(halo_ctx *ctx, uint64_t start, uint64_t count, uint64_t *out_affine /*[count][8]*/);
+
+/* ---- K2: multi-scalar multiplication ------------------------------------------------------------- */
+/* sum_i scalars[i] * G_{off+i}, i < n.   Replaces group.rs:24-26 `point_dot_affine` as called by
+ * pedersen.rs:14 over GS[0..n] (pcdl.rs:109, :338; acc.rs:153, :195). */
+int halo_msm_gens(halo_ctx *ctx, const uint64_t *scalars /*[n][4]*/, uint64_t off, uint64_t n, uint64_t out_jac[12]);
+/* sum_i scalars[i] * bases[i] for caller-supplied affine bases; inf_flags may be NULL.
+ * Replaces group.rs:24-26 for arbitrary bases and, after the caller's normalisation, group.rs:18-21. */
+int halo_msm(halo_ctx *ctx, const uint64_t *bases_affine /*[n][8]*/, const uint8_t *inf_flags /*[n] or NULL*/,
+             const uint64_t *scalars /*[n][4]*/, uint64_t n, uint64_t out_jac[12]);
+/* Same as group.rs:18-21 `point_dot`: Jacobian bases, normalised on the device (batched inversion). */
+int halo_msm_jac(halo_ctx *ctx, const uint64_t *bases_jac /*[n][12]*/, const uint64_t *scalars /*[n][4]*/, uint64_t n,
+                 uint64_t out_jac[12]);
+/* Device-resident variant for throughput measurement: d_scalars is a CUDA device pointer to n scalars. */
+int halo_msm_gens_resident(halo_ctx *ctx, const void *d_scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALO_B200_H */

@@ -1,0 +1,29 @@
+/*
+ * halo_b200_test.h -- test hooks exported by libhalo_b200.so so the parity suite can exercise the
+ * device field core (K1) and group law in isolation against the oracle.  Not part of the drop-in
+ * boundary; a Rust shim never binds these.
+ */
+#ifndef HALO_B200_TEST_H
+#define HALO_B200_TEST_H
+#include "halo_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* Element-wise field op on the device: which = 0 (Fq) / 1 (Fr); op = 0 mul, 1 add, 2 sub, 3 sqr, 4 inv,
+ * 5 neg, 6 to_canonical, 7 from_canonical.  a, b, out: host arrays of n elements (uint64_t[4] each). */
+int halo_test_fp_op(halo_ctx *ctx, int which, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n);
+/* Single device thread: sum_i (neg[i] ? -P_i : P_i) over affine points via mixed adds -> Jacobian. */
+int halo_test_madd_chain(halo_ctx *ctx, const uint64_t *affine /*[n][8]*/, const uint8_t *neg, uint64_t n,
+                         uint64_t out_jac[12]);
+/* Single device thread: sum of Jacobian points via full XYZZ adds followed by `dbls` doublings. */
+int halo_test_add_chain(halo_ctx *ctx, const uint64_t *jac /*[n][12]*/, uint64_t n, int dbls, uint64_t out_jac[12]);
+/* Modular-multiplication throughput microbenchmark (K1): `iters` dependent Fq multiplications per thread
+ * on blocks x threads threads; returns elapsed ms and a checksum limb. */
+int halo_test_fp_mul_throughput(halo_ctx *ctx, int blocks, int threads, int iters, int ilp, float *ms, uint64_t *checksum);
+/* Integer-pipe peak microbenchmark: independent IMAD chains; kind 0 = mad.lo.u32, 1 = mad.wide.u32,
+ * 2 = mad.hi.u32.  Returns elapsed ms; ops = blocks * threads * iters * 16. */
+int halo_test_imad_throughput(halo_ctx *ctx, int kind, int blocks, int threads, int iters, float *ms, uint64_t *checksum);
+#ifdef __cplusplus
+}
+#endif
+#endif

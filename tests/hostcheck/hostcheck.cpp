@@ -1,0 +1,44 @@
+// tests/hostcheck/hostcheck.cpp -- compiles the product's __host__ __device__ field / curve headers as
+// plain C++ (g++) so their logic can be checked against the oracle on a machine without a GPU.
+// Test-only; never shipped, never linked into libhalo_b200.so.
+#include <cstring>
+#include "../../halo-accumulation_b200/csrc/ec.cuh"
+using namespace halo;
+extern "C" {
+void hc_fp_mul(int which, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    if (which) { fr_t x, y, z; memcpy(&x, a, 32); memcpy(&y, b, 32); fp_mul(z, x, y); memcpy(r, &z, 32); }
+    else { fq_t x, y, z; memcpy(&x, a, 32); memcpy(&y, b, 32); fp_mul(z, x, y); memcpy(r, &z, 32); }
+}
+void hc_fp_addsub(int which, int sub, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    if (which) { fr_t x, y, z; memcpy(&x, a, 32); memcpy(&y, b, 32); if (sub) fp_sub(z, x, y); else fp_add(z, x, y); memcpy(r, &z, 32); }
+    else { fq_t x, y, z; memcpy(&x, a, 32); memcpy(&y, b, 32); if (sub) fp_sub(z, x, y); else fp_add(z, x, y); memcpy(r, &z, 32); }
+}
+void hc_fp_inv(int which, const uint32_t* a, uint32_t* r) {
+    if (which) { fr_t x, z; memcpy(&x, a, 32); fp_inv(z, x); memcpy(r, &z, 32); }
+    else { fq_t x, z; memcpy(&x, a, 32); fp_inv(z, x); memcpy(r, &z, 32); }
+}
+void hc_fp_canon(int which, int to, const uint32_t* a, uint32_t* r) {
+    if (which) { fr_t x; if (to) { memcpy(&x, a, 32); fp_to_canon(r, x); } else { fp_from_canon(x, a); memcpy(r, &x, 32); } }
+    else { fq_t x; if (to) { memcpy(&x, a, 32); fp_to_canon(r, x); } else { fp_from_canon(x, a); memcpy(r, &x, 32); } }
+}
+// sum_i (neg_i ? -P_i : P_i) with madd, returned as Jacobian
+void hc_madd_chain(const uint32_t* aff, const uint8_t* neg, uint64_t n, uint32_t* out_jac) {
+    xyzz_t acc; xyzz_set_inf(acc);
+    for (uint64_t i = 0; i < n; i++) { affine_t p; memcpy(&p, aff + 16 * i, 64); xyzz_madd(acc, p, neg && neg[i]); }
+    jac_t j; xyzz_to_jac(j, acc); memcpy(out_jac, &j, 96);
+}
+// sum of Jacobian inputs via xyzz_add (+ optional doublings of the total)
+void hc_add_chain(const uint32_t* jac, uint64_t n, int dbls, uint32_t* out_jac) {
+    xyzz_t acc; xyzz_set_inf(acc);
+    for (uint64_t i = 0; i < n; i++) { jac_t p; memcpy(&p, jac + 24 * i, 96); xyzz_t q; jac_to_xyzz(q, p); xyzz_add(acc, q); }
+    for (int i = 0; i < dbls; i++) xyzz_dbl(acc, acc);
+    jac_t j; xyzz_to_jac(j, acc); memcpy(out_jac, &j, 96);
+}
+void hc_to_affine(const uint32_t* jac, uint32_t* aff) {
+    jac_t p; memcpy(&p, jac, 96); xyzz_t q; jac_to_xyzz(q, p); affine_t a; xyzz_to_affine(a, q); memcpy(aff, &a, 64);
+}
+void hc_mul(const uint32_t* jac, const uint32_t* k_canon, uint32_t* out_jac) {
+    jac_t p; memcpy(&p, jac, 96); xyzz_t q, r; jac_to_xyzz(q, p); xyzz_mul_canon(r, q, k_canon);
+    jac_t j; xyzz_to_jac(j, r); memcpy(out_jac, &j, 96);
+}
+}

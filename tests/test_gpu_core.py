@@ -1,0 +1,201 @@
+"""GPU parity tests for the field core (K1), group law, generator derivation (K6) and MSM (K2),
+all through the C ABI of libhalo_b200.so, checked against the CPU oracle and the golden fixture."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+P_MOD = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001
+R_MOD = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
+
+
+def _limbs(vals):
+    return np.array([[(v >> (64 * i)) & (2**64 - 1) for i in range(4)] for v in vals], dtype=np.uint64)
+
+
+def _ints(a):
+    return [sum(int(x) << (64 * i) for i, x in enumerate(row)) for row in np.asarray(a).reshape(-1, 4)]
+
+
+@pytest.mark.parametrize("which,mod", [(0, P_MOD), (1, R_MOD)])
+def test_field_ops_bit_exact(ctx, which, mod):
+    rnd = random.Random(1234 + which)
+    edge = [0, 1, 2, mod - 1, mod - 2, (1 << 256) % mod, (1 << 255) % mod, 0xFFFFFFFF, 1 << 32, (1 << 254) % mod,
+            mod >> 1, (mod >> 1) + 1, (1 << 64) - 1, 1 << 64, (1 << 128) - 1, (1 << 224)]
+    a = edge * len(edge) + [rnd.randrange(mod) for _ in range(20000)]
+    b = [e for e in edge for _ in edge] + [rnd.randrange(mod) for _ in range(20000)]
+    A, B = _limbs(a), _limbs(b)
+    rinv = pow(1 << 256, -1, mod)
+    assert _ints(ctx.test_fp_op(which, 0, A, B)) == [x * y * rinv % mod for x, y in zip(a, b)]
+    assert _ints(ctx.test_fp_op(which, 1, A, B)) == [(x + y) % mod for x, y in zip(a, b)]
+    assert _ints(ctx.test_fp_op(which, 2, A, B)) == [(x - y) % mod for x, y in zip(a, b)]
+    assert _ints(ctx.test_fp_op(which, 3, A)) == [x * x * rinv % mod for x in a]
+    assert _ints(ctx.test_fp_op(which, 5, A)) == [(-x) % mod for x in a]
+    assert _ints(ctx.test_fp_op(which, 6, A)) == [x * rinv % mod for x in a]
+    assert _ints(ctx.test_fp_op(which, 7, A)) == [x * (1 << 256) % mod for x in a]
+    sub = [x for x in a[:600] if x]
+    r2 = pow(1 << 256, 2, mod)
+    assert _ints(ctx.test_fp_op(which, 4, _limbs(sub))) == [pow(x, -1, mod) * r2 % mod for x in sub]
+
+
+def test_group_law_edge_cases(ctx, oracle):
+    O = oracle
+    GS = O.derive_points(2, 32)
+    aff = np.concatenate([GS[:10], GS[3:4], GS[3:4], GS[5:6], np.zeros((1, 8), dtype=np.uint64), GS[:10]])
+    neg = np.zeros(len(aff), dtype=np.uint8)
+    neg[12] = 1
+    neg[-10:] = 1
+    exp = np.zeros(12, dtype=np.uint64)
+    exp[:] = O.pt_from_affine_ints(None)
+    for a, ng in zip(aff, neg):
+        if not a.any():
+            continue
+        j = O.affine_to_jac(a)[0]
+        if ng:
+            j = O.pt_mul(j, O.to_mont([R_MOD - 1])[0])
+        exp = O.pt_add(exp, j)
+    assert O.pt_eq(ctx.test_madd_chain(aff, neg), exp)
+    # P + P (doubling branch), then -P, -P: back to infinity
+    quad = np.concatenate([GS[:1]] * 4)
+    assert O.pt_to_affine(ctx.test_madd_chain(quad, np.array([0, 0, 1, 1], dtype=np.uint8)))[1]
+    two = O.pt_add(O.affine_to_jac(GS[0])[0], O.affine_to_jac(GS[0])[0])
+    assert O.pt_eq(ctx.test_madd_chain(quad[:2]), two)
+    # full adds on non-trivial Jacobian representatives, equal operands, then doublings
+    jacs = np.array([O.pt_mul(O.affine_to_jac(GS[i])[0], O.random_scalars(1, i)[0]) for i in range(8)])
+    jacs2 = np.concatenate([jacs, jacs[:1], jacs[2:3]])
+    exp = O.pt_from_affine_ints(None)
+    for j in jacs2:
+        exp = O.pt_add(exp, j)
+    for _ in range(3):
+        exp = O.pt_add(exp, exp)
+    assert O.pt_eq(ctx.test_add_chain(jacs2, 3), exp)
+    assert O.pt_eq(ctx.test_add_chain(np.concatenate([jacs[:1], jacs[:1]])), O.pt_add(jacs[0], jacs[0]))
+
+
+def test_generator_derivation_matches_consts_rs(ctx, golden):
+    """K6 against the reference's golden data: all 16 386 points of consts.rs, bit for bit."""
+    pts = ctx.derive_points(0, 16386)
+    gs = pts[2:]
+    assert hashlib.sha256(gs.astype("<u8").tobytes()).hexdigest() == str(golden["gs_full_sha256"])
+    assert np.array_equal(gs[golden["gs_idx"]], golden["gs"])
+    assert np.array_equal(ctx.get_generators(0, 16384), gs)
+
+
+def test_SH_match_consts_rs(ctx, golden, oracle):
+    S, H = ctx.get_SH()
+    assert oracle.pt_eq(S, golden["S"]) and oracle.pt_eq(H, golden["H"])
+
+
+def test_generators_beyond_reference_limit(ctx, oracle):
+    """n > 16384 (the reference's literal cap, consts.rs:23): device derivation == oracle derivation."""
+    for start in (16384 + 2, 65000, (1 << 24) + 1, (1 << 32) + 12345):
+        assert np.array_equal(ctx.derive_points(start, 64), oracle.derive_points(start, 64))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 255, 1000, 4096, 5000])
+def test_msm_gens_small(ctx, oracle, n):
+    sc = oracle.random_scalars(n, 100 + n)
+    gs = ctx.get_generators(0, n)
+    got = ctx.msm_gens(sc)
+    assert oracle.pt_eq(got, oracle.msm_affine(gs, sc))
+    if n <= 33:
+        assert oracle.pt_eq(got, oracle.msm_naive(gs, sc))
+
+
+@pytest.mark.parametrize("c", [4, 7, 11, 13, 16])
+def test_msm_window_widths(ctx, oracle, c):
+    n = 3000
+    sc = oracle.random_scalars(n, 7)
+    exp = oracle.msm_affine(ctx.get_generators(0, n), sc)
+    ctx.set_msm_window(c)
+    try:
+        assert oracle.pt_eq(ctx.msm_gens(sc), exp)
+    finally:
+        ctx.set_msm_window(0)
+
+
+def test_msm_2_16_bit_exact(ctx, oracle):
+    """BASELINE config 2: single Pallas MSM n = 2^16, normalised affine output equal byte for byte."""
+    n = 1 << 16
+    sc = oracle.random_scalars(n, 1)
+    gs = ctx.get_generators(0, n)
+    got = ctx.msm_gens(sc)
+    exp = oracle.msm_affine(gs, sc, threads=oracle.lib().orc_num_threads())
+    ga, ginf = oracle.pt_to_affine(got)
+    ea, einf = oracle.pt_to_affine(exp)
+    assert not ginf and not einf
+    assert ga.tobytes() == ea.tobytes()
+
+
+def test_msm_edge_scalars(ctx, oracle):
+    O = oracle
+    n = 512
+    gs = ctx.get_generators(0, n)
+    cases = {
+        "zeros": np.zeros((n, 4), dtype=np.uint64),
+        "ones": np.tile(O.to_mont([1])[0], (n, 1)),
+        "r_minus_1": np.tile(O.to_mont([R_MOD - 1])[0], (n, 1)),
+        "same_big": np.tile(O.random_scalars(1, 5)[0], (n, 1)),
+        "sparse": np.zeros((n, 4), dtype=np.uint64),
+        "small": O.to_mont([i % 7 for i in range(n)]),
+        "half": O.to_mont([(1 << 254) + i for i in range(n)]),
+    }
+    cases["sparse"][3] = O.random_scalars(1, 9)[0]
+    cases["sparse"][400] = O.to_mont([2])[0]
+    for name, sc in cases.items():
+        assert O.pt_eq(ctx.msm_gens(sc), O.msm_affine(gs, sc)), name
+    assert O.pt_to_affine(ctx.msm_gens(cases["zeros"]))[1]
+    assert O.pt_to_affine(ctx.msm_gens(np.zeros((0, 4), dtype=np.uint64)))[1]
+
+
+def test_msm_arbitrary_bases_duplicates_and_infinity(ctx, oracle):
+    O = oracle
+    n = 700
+    gs = ctx.get_generators(100, n).copy()
+    gs[10:20] = gs[0]            # duplicate bases
+    gs[50] = gs[51]
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[[5, 77, 699]] = 1
+    sc = O.random_scalars(n, 33)
+    sc[10:20] = sc[0]            # identical (base, scalar) pairs land in the same buckets
+    assert O.pt_eq(ctx.msm(gs, sc, inf), O.msm_affine(gs, sc, inf=inf))
+    # offset slice of resident generators
+    assert O.pt_eq(ctx.msm_gens(sc, off=100), O.msm_affine(ctx.get_generators(100, n), sc))
+    # truncation to the shorter input (msm_unchecked semantics)
+    assert O.pt_eq(ctx.msm(gs[:300], sc), O.msm_affine(gs[:300], sc[:300]))
+
+
+def test_msm_jacobian_bases(ctx, oracle):
+    """group.rs:18-21 point_dot: non-normalised bases."""
+    O = oracle
+    n = 200
+    aff = ctx.get_generators(0, n)
+    jac = np.array([O.pt_mul(O.affine_to_jac(aff[i])[0], O.to_mont([i + 2])[0]) for i in range(n)])
+    jac[7] = O.pt_from_affine_ints(None)
+    sc = O.random_scalars(n, 44)
+    assert O.pt_eq(ctx.msm_jac(jac, sc), O.point_dot(sc, jac))
+
+
+def test_msm_linearity_2_20(ctx, oracle):
+    """Size-independent property at a size the oracle cannot reach quickly: <a+b, G> == <a, G> + <b, G>."""
+    O = oracle
+    n = 1 << 20
+    ctx.derive_generators(n)
+    try:
+        a, b = O.random_scalars(n, 11), O.random_scalars(n, 12)
+        ai, bi = None, None
+        s = np.zeros_like(a)
+        # limb-wise modular addition on the host via the oracle's field add, vectorised through Python ints is slow;
+        # use the device field op (already parity-checked above)
+        s = ctx.test_fp_op(1, 1, a, b)
+        lhs = ctx.msm_gens(s)
+        rhs = O.pt_add(ctx.msm_gens(a), ctx.msm_gens(b))
+        assert O.pt_eq(lhs, rhs)
+        # and one slice checked directly against the oracle
+        m = 1 << 14
+        assert O.pt_eq(ctx.msm_gens(a[:m], off=n - m), O.msm_affine(ctx.get_generators(n - m, m), a[:m], threads=8))
+    finally:
+        ctx.derive_generators(1 << 16)
