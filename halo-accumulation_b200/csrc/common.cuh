@@ -58,11 +58,19 @@ struct DevBuf {
 };
 
 // MSM plan: window width c, W windows, M = 2^(c-1) buckets per window (signed digits).
+// The 255 scalar bits are split into W windows of near-equal width (<= c, top window <= c - 1) so that
+// for uniform scalars every window fills its buckets evenly; a short top window would otherwise pile
+// n / 2^t entries into a handful of buckets and serialise their accumulation.
+constexpr int MSM_MAX_WINDOWS = 64;
+struct MsmWidths {
+    uint8_t w[MSM_MAX_WINDOWS];
+};
 struct MsmPlan {
     int c = 0;
     int W = 0;
     uint32_t M = 0;
     uint32_t NB = 0;  // W * M
+    MsmWidths widths;
 };
 MsmPlan msm_make_plan(uint64_t n, int force_c);
 

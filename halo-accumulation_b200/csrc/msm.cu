@@ -22,7 +22,7 @@ MsmPlan msm_make_plan(uint64_t n, int force_c) {
     double best = 1e300;
     for (int c = 4; c <= 17; c++) {
         int W = 255 / c + 1;
-        double M = (double)(1u << (c - 1));
+        double M = (double)(1u << (c - 1)) * (255.0 / (W * c) > 0.97 ? 1.0 : 0.75);  // narrower windows use half their slots
         // bucket accumulation (10 modmul per mixed add) + bucket reduction (2 full adds per bucket, poorly
         // parallel -> weighted) ; tuned on B200, see profiles/
         double cost = (double)W * ((double)n * 10.0 + M * 28.0 * 6.0);
@@ -32,13 +32,16 @@ MsmPlan msm_make_plan(uint64_t n, int force_c) {
         }
     }
     int c = force_c ? force_c : best_c;
-    if (c < 2) c = 2;
+    if (c < 4) c = 4;  // W = 255 / c + 1 <= MSM_MAX_WINDOWS
     if (c > 20) c = 20;
     MsmPlan p;
     p.c = c;
     p.W = 255 / c + 1;  // c * W >= 256 > 255: the top window absorbs the final carry
     p.M = 1u << (c - 1);
     p.NB = (uint32_t)p.W * p.M;
+    // near-equal widths summing to 255; the low windows take the remainder so the top window is the narrow one
+    int base = 255 / p.W, rem = 255 - base * p.W;
+    for (int w = 0; w < MSM_MAX_WINDOWS; w++) p.widths.w[w] = w < p.W ? (uint8_t)(base + (w < rem ? 1 : 0)) : 0;
     return p;
 }
 
@@ -46,7 +49,7 @@ MsmPlan msm_make_plan(uint64_t n, int force_c) {
 // 1/3. digit extraction: count or scatter
 // ------------------------------------------------------------------------------------------------
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars, uint32_t n, int c, int W, uint32_t M,
+__global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars, uint32_t n, const MsmWidths widths, int W, uint32_t M,
                                                 uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                                                 uint32_t* __restrict__ entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,16 +57,16 @@ __global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars
     fr_t s = scalars[i];
     uint32_t k[8];
     fp_to_canon(k, s);  // arkworks `into_bigint`
-    const uint32_t mask = (1u << c) - 1u;
     uint32_t carry = 0;
     for (int w = 0; w < W; w++) {
-        uint32_t d = (k[0] & mask) + carry;
+        const uint32_t c = widths.w[w];
+        uint32_t d = (k[0] & ((1u << c) - 1u)) + carry;
 #pragma unroll
         for (int j = 0; j < 7; j++) k[j] = __funnelshift_r(k[j], k[j + 1], c);
         k[7] >>= c;
         carry = 0;
         uint32_t neg = 0;
-        if (d > M) {  // digit in (-2^(c-1), 2^(c-1)]
+        if (d > (1u << (c - 1))) {  // digit in (-2^(c-1), 2^(c-1)]; never taken in the top window (scalar < 2^255)
             d = (1u << c) - d;
             neg = 1;
             carry = 1;
@@ -285,12 +288,12 @@ void msm_window_sums(halo_ctx* ctx, const affine_t* d_bases, const fr_t* d_scala
     HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, st));
     const int TPB = 256;
     uint32_t grid = (n + TPB - 1) / TPB;
-    k_digits<false><<<grid, TPB, 0, st>>>(d_scalars, n, plan.c, plan.W, plan.M, counts, nullptr, nullptr);
+    k_digits<false><<<grid, TPB, 0, st>>>(d_scalars, n, plan.widths, plan.W, plan.M, counts, nullptr, nullptr);
     mark(1);
     exclusive_scan(counts, offsets, NB, ws.scan_tmp.as<uint32_t>(), st, &ctx->kernel_launches);
     HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, st));
     mark(2);
-    k_digits<true><<<grid, TPB, 0, st>>>(d_scalars, n, plan.c, plan.W, plan.M, counts, offsets, entries);
+    k_digits<true><<<grid, TPB, 0, st>>>(d_scalars, n, plan.widths, plan.W, plan.M, counts, offsets, entries);
     mark(3);
     k_accumulate<<<(NB + 127) / 128, 128, 0, st>>>(d_bases, offsets, entries, NB, buckets);
     mark(4);
@@ -315,9 +318,9 @@ void msm_finish_host(const xyzz_t* wsums, const MsmPlan& plan, xyzz_t& out) {
     xyzz_t total;
     xyzz_set_inf(total);
     for (int w = plan.W - 1; w >= 0; w--) {
-        if (w != plan.W - 1)
-            for (int k = 0; k < plan.c; k++) xyzz_dbl(total, total);
         xyzz_add(total, wsums[w]);
+        if (w > 0)
+            for (int k = 0; k < plan.widths.w[w - 1]; k++) xyzz_dbl(total, total);
     }
     out = total;
 }

@@ -34,13 +34,13 @@ for ilp in (1, 2, 4):
         emit(bench="fp_mul", ilp=ilp, threads=threads, blocks_per_sm=bps, ms=ms, gmodmul_s=n / ms / 1e6)
 
 ctx.set_profiling(True)
-for lg in (10, 12, 14, 16, 18, 20, 22):
+for lg in (10, 12, 14, 16, 18, 20, 22, 24):
     n = 1 << lg
     t = time.time()
     ctx.derive_generators(n)
     t_der = time.time() - t
     sc = O.random_scalars(n, lg)
-    for c in (0,) if lg < 16 else (0, 12, 14, 16):
+    for c in (0, 6, 8, 10) if lg < 16 else (0, 11, 12, 13, 14, 15, 16, 17):
         ctx.set_msm_window(c)
         ctx.msm_gens(sc)
         t = time.time()
