@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "msm.cuh"
 #include "params.cuh"
+#include "vec.cuh"
 
 using namespace halo;
 
@@ -106,6 +107,7 @@ void halo_ctx_destroy(halo_ctx* ctx) {
 
 const char* halo_last_error(halo_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 uint64_t halo_kernel_launches(halo_ctx* ctx) { return ctx ? ctx->kernel_launches : 0; }
+uint64_t halo_num_generators(halo_ctx* ctx) { return ctx ? ctx->n_gens : 0; }
 int halo_set_msm_window(halo_ctx* ctx, int c) {
     if (!ctx || c < 0 || c > 20) return HALO_EINVAL;
     ctx->force_c = c;
@@ -263,6 +265,94 @@ int halo_msm_jac(halo_ctx* ctx, const uint64_t* bases_jac, const uint64_t* scala
     xyzz_t r;
     msm_device(ctx, ctx->stage_bases.as<affine_t>(), ctx->stage_scalars.as<fr_t>(), n, r);
     out_jac_from_xyzz(r, out_jac);
+    HALO_CATCH(ctx)
+}
+
+
+// ---- scalar vectors (group.rs:13-15, :29-37) ----------------------------------------------------------
+int halo_scalar_dot(halo_ctx* ctx, const uint64_t* xs, const uint64_t* ys, uint64_t n, uint64_t out[4]) {
+    if (!ctx || !out || ((!xs || !ys) && n)) return HALO_EINVAL;
+    HALO_TRY(ctx)
+    ctx->stage_scalars.reserve((2 * (n ? n : 1) + 1 + VEC_DOT_MAX_BLOCKS) * sizeof(fr_t));
+    fr_t* a = ctx->stage_scalars.as<fr_t>();
+    fr_t* b = a + n;
+    fr_t* res = b + n;
+    if (n) {
+        HALO_CUDA(cudaMemcpyAsync(a, xs, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        HALO_CUDA(cudaMemcpyAsync(b, ys, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    vec_dot(ctx, a, b, n, res + 1, res);
+    HALO_CUDA(cudaMemcpyAsync(out, res, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    HALO_CATCH(ctx)
+}
+
+int halo_construct_powers(halo_ctx* ctx, const uint64_t z[4], uint64_t n, uint64_t* out) {
+    if (!ctx || !z || (!out && n)) return HALO_EINVAL;
+    HALO_TRY(ctx)
+    if (n) {
+        ctx->stage_scalars.reserve(n * sizeof(fr_t));
+        fr_t zz;
+        memcpy(&zz, z, 32);
+        vec_powers(ctx, zz, n, ctx->stage_scalars.as<fr_t>());
+        HALO_CUDA(cudaMemcpyAsync(out, ctx->stage_scalars.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+        HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    HALO_CATCH(ctx)
+}
+
+// ---- K5: h(X) (pcdl.rs:56-77, :338; acc.rs:85-94) --------------------------------------------------------
+static int check_lg(halo_ctx* ctx, uint32_t lg_n, bool need_gens) {
+    if (lg_n > 30 || ((uint64_t)1 << lg_n) > ctx->max_n) return fail(ctx, HALO_EINVAL, "h: 2^lg_n exceeds max_n");
+    if (need_gens && ((uint64_t)1 << lg_n) > ctx->n_gens) return fail(ctx, HALO_ESTATE, "h: 2^lg_n exceeds resident generators");
+    return HALO_OK;
+}
+
+int halo_h_expand(halo_ctx* ctx, const uint64_t* xis, uint32_t lg_n, uint64_t* out) {
+    if (!ctx || !xis || !out) return HALO_EINVAL;
+    if (int rc = check_lg(ctx, lg_n, false)) return rc;
+    HALO_TRY(ctx)
+    uint64_t n = (uint64_t)1 << lg_n;
+    ctx->stage_scalars.reserve(n * sizeof(fr_t));
+    fr_t one;
+    fp_one(one);
+    vec_h_expand(ctx, reinterpret_cast<const fr_t*>(xis), (int)lg_n, one, false, ctx->stage_scalars.as<fr_t>());
+    HALO_CUDA(cudaMemcpyAsync(out, ctx->stage_scalars.p, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    HALO_CATCH(ctx)
+}
+
+int halo_h_msm(halo_ctx* ctx, const uint64_t* xis, uint32_t lg_n, uint64_t out_jac[12]) {
+    if (!ctx || !xis || !out_jac) return HALO_EINVAL;
+    if (int rc = check_lg(ctx, lg_n, true)) return rc;
+    HALO_TRY(ctx)
+    uint64_t n = (uint64_t)1 << lg_n;
+    ctx->stage_scalars.reserve(n * sizeof(fr_t));
+    fr_t one;
+    fp_one(one);
+    vec_h_expand(ctx, reinterpret_cast<const fr_t*>(xis), (int)lg_n, one, false, ctx->stage_scalars.as<fr_t>());
+    xyzz_t r;
+    msm_device(ctx, ctx->gens.as<affine_t>(), ctx->stage_scalars.as<fr_t>(), n, r);
+    out_jac_from_xyzz(r, out_jac);
+    HALO_CATCH(ctx)
+}
+
+int halo_h_lincomb(halo_ctx* ctx, const uint64_t* h0, uint64_t n_h0, const uint64_t* alphas, const uint64_t* xis, uint64_t m,
+                   uint32_t lg_n, uint64_t* out) {
+    if (!ctx || !out || (!h0 && n_h0) || ((!alphas || !xis) && m)) return HALO_EINVAL;
+    if (int rc = check_lg(ctx, lg_n, false)) return rc;
+    uint64_t n = (uint64_t)1 << lg_n;
+    if (n_h0 > n) return fail(ctx, HALO_EINVAL, "halo_h_lincomb: h_0 longer than n");
+    HALO_TRY(ctx)
+    ctx->stage_scalars.reserve(n * sizeof(fr_t));
+    fr_t* d = ctx->stage_scalars.as<fr_t>();
+    HALO_CUDA(cudaMemsetAsync(d, 0, n * sizeof(fr_t), ctx->stream));
+    if (n_h0) HALO_CUDA(cudaMemcpyAsync(d, h0, n_h0 * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    const fr_t* al = reinterpret_cast<const fr_t*>(alphas);
+    const fr_t* xs = reinterpret_cast<const fr_t*>(xis);
+    for (uint64_t i = 0; i < m; i++) vec_h_expand(ctx, xs + i * (lg_n + 1), (int)lg_n, al[i + 1], true, d);  // acc.rs:90-92
+    HALO_CUDA(cudaMemcpyAsync(out, d, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
     HALO_CATCH(ctx)
 }
 

@@ -23,6 +23,7 @@ namespace halo {
 
 struct FqParams {  // Pallas base field (point coordinates)
     static constexpr uint32_t P1 = 0x992d30edu, P2 = 0x094cf91bu, P3 = 0x224698fcu;
+    static constexpr uint64_t INV64 = 0x992d30ecffffffffull;  // -p^-1 mod 2^64 (host path)
     HALO_HD static constexpr uint32_t one(int i) {
         constexpr uint32_t v[8] = {0xfffffffdu, 0x34786d38u, 0xe41914adu, 0x992c350bu,
                                    0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu};
@@ -36,6 +37,7 @@ struct FqParams {  // Pallas base field (point coordinates)
 };
 struct FrParams {  // Pallas scalar field (= Vesta base field)
     static constexpr uint32_t P1 = 0x8c46eb21u, P2 = 0x0994a8ddu, P3 = 0x224698fcu;
+    static constexpr uint64_t INV64 = 0x8c46eb20ffffffffull;
     HALO_HD static constexpr uint32_t one(int i) {
         constexpr uint32_t v[8] = {0xfffffffdu, 0x5b2b3e9cu, 0xe3420567u, 0x992c350bu,
                                    0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu};
@@ -268,11 +270,65 @@ HALO_HD void mul8x8(uint32_t T[16], const uint32_t a[8], const uint32_t b[8]) {
     }
 }
 
+#if !defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+// Host path (transcript glue, the O(255)-doubling Horner finish of an MSM): 4 x u64 CIOS on the same bytes.
+template <class P>
+inline void fp_mul_host64(uint32_t r32[8], const uint32_t a32[8], const uint32_t b32[8]) {
+    typedef unsigned __int128 u128;
+    uint64_t a[4], b[4], p[4], t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        a[i] = (uint64_t)a32[2 * i] | ((uint64_t)a32[2 * i + 1] << 32);
+        b[i] = (uint64_t)b32[2 * i] | ((uint64_t)b32[2 * i + 1] << 32);
+        p[i] = (uint64_t)fp_mod<P>(2 * i) | ((uint64_t)fp_mod<P>(2 * i + 1) << 32);
+    }
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)a[j] * b[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * P::INV64;
+        c = (u128)m * p[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128)m * p[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    // conditional subtraction
+    uint64_t d[4];
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 x = (u128)t[i] - p[i] - br;
+        d[i] = (uint64_t)x;
+        br = (x >> 64) & 1;
+    }
+    bool ge = t[4] != 0 || br == 0;
+    for (int i = 0; i < 4; i++) {
+        uint64_t o = ge ? d[i] : t[i];
+        r32[2 * i] = (uint32_t)o;
+        r32[2 * i + 1] = (uint32_t)(o >> 32);
+    }
+}
+#endif
+
 template <class P>
 HALO_HD void fp_mul(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
+#if !defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+    fp_mul_host64<P>(r.v, a.v, b.v);
+#else
     uint32_t T[16];
     mul8x8(T, a.v, b.v);
     fp_mont_reduce<P>(r.v, T);
+#endif
 }
 template <class P>
 HALO_HD void fp_sqr(fp_t<P>& r, const fp_t<P>& a) {

@@ -1,0 +1,18 @@
+// ipa.cuh -- device state of one PCDL opening (pcdl.rs:183-231).
+#pragma once
+#include "common.cuh"
+
+struct halo_ipa {
+    halo_ctx* ctx = nullptr;
+    uint64_t n = 0;    // d + 1
+    uint64_t cur = 0;  // current vector length (n, n/2, ..., 1)
+    uint32_t lg_n = 0;
+    uint32_t round = 0;
+    bool have_hprime = false;
+    bool lr_done = false;
+    halo::fr_t z;
+    halo::DevBuf G;        // affine working copy of GS[0..n)  (pcdl.rs:185)
+    halo::DevBuf cs, zs;   // coefficient and z-power vectors (pcdl.rs:183-186)
+    halo::DevBuf pbar;     // hiding polynomial (pcdl.rs:140-142)
+    halo::DevBuf tail;     // [affine H'] then [fr dot_l, fr dot_r] and dot partials
+};

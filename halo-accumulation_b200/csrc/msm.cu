@@ -49,12 +49,13 @@ MsmPlan msm_make_plan(uint64_t n, int force_c) {
 // 1/3. digit extraction: count or scatter
 // ------------------------------------------------------------------------------------------------
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars, uint32_t n, const MsmWidths widths, int W, uint32_t M,
-                                                uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                                                uint32_t* __restrict__ entries) {
+__global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars, uint32_t n,
+                                                const fr_t* __restrict__ tail_scalars, uint32_t n_tail, const MsmWidths widths,
+                                                int W, uint32_t M, uint32_t* __restrict__ counts,
+                                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    fr_t s = scalars[i];
+    if (i >= n + n_tail) return;
+    fr_t s = i < n ? scalars[i] : tail_scalars[i - n];
     uint32_t k[8];
     fp_to_canon(k, s);  // arkworks `into_bigint`
     uint32_t carry = 0;
@@ -173,7 +174,9 @@ static void exclusive_scan(const uint32_t* counts, uint32_t* offsets, uint32_t n
 // ------------------------------------------------------------------------------------------------
 // 4. bucket accumulation: one thread per bucket, accumulator in registers
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__ bases, const uint32_t* __restrict__ offsets,
+__global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__ bases, uint32_t n,
+                                                    const affine_t* __restrict__ tail_bases,
+                                                    const uint32_t* __restrict__ offsets,
                                                     const uint32_t* __restrict__ entries, uint32_t NB,
                                                     xyzz_t* __restrict__ buckets) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,7 +186,8 @@ __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__
     xyzz_set_inf(acc);
     for (uint32_t e = beg; e < end; e++) {
         uint32_t ent = entries[e];
-        affine_t p = bases[ent & 0x7fffffffu];
+        uint32_t idx = ent & 0x7fffffffu;
+        affine_t p = idx < n ? bases[idx] : tail_bases[idx - n];
         xyzz_madd(acc, p, (ent >> 31) != 0);
     }
     buckets[b] = acc;
@@ -263,14 +267,17 @@ __global__ void __launch_bounds__(REDUCE_THREADS) k_bucket_reduce(const xyzz_t* 
 // ------------------------------------------------------------------------------------------------
 static inline bool is_pow2_u32(uint32_t x) { return x && !(x & (x - 1)); }
 
-void msm_window_sums(halo_ctx* ctx, const affine_t* d_bases, const fr_t* d_scalars, uint32_t n, const MsmPlan& plan,
-                     xyzz_t* d_wsums_out) {
+void msm_window_sums(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_wsums_out) {
+    const affine_t* d_bases = in.bases;
+    const fr_t* d_scalars = in.scalars;
+    const uint32_t n = in.n;
+    const uint32_t ntot = in.n + in.n_tail;
     MsmWorkspace& ws = ctx->ws;
     cudaStream_t st = ctx->stream;
     const uint32_t NB = plan.NB;
     ws.counts.reserve((size_t)(NB + 1) * 4);
     ws.offsets.reserve((size_t)(NB + 1) * 4);
-    ws.entries.reserve((size_t)n * plan.W * 4);
+    ws.entries.reserve((size_t)ntot * plan.W * 4);
     ws.buckets.reserve((size_t)NB * sizeof(xyzz_t));
     ws.scan_tmp.reserve(4096 * 4);
     if ((NB + SCAN_TILE - 1) / SCAN_TILE > 2048) throw CudaError{cudaErrorInvalidValue, "bucket count too large for scan", __FILE__, __LINE__};
@@ -287,26 +294,22 @@ void msm_window_sums(halo_ctx* ctx, const affine_t* d_bases, const fr_t* d_scala
     mark(0);
     HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, st));
     const int TPB = 256;
-    uint32_t grid = (n + TPB - 1) / TPB;
-    k_digits<false><<<grid, TPB, 0, st>>>(d_scalars, n, plan.widths, plan.W, plan.M, counts, nullptr, nullptr);
+    uint32_t grid = (ntot + TPB - 1) / TPB;
+    k_digits<false><<<grid, TPB, 0, st>>>(d_scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, counts, nullptr, nullptr);
     mark(1);
     exclusive_scan(counts, offsets, NB, ws.scan_tmp.as<uint32_t>(), st, &ctx->kernel_launches);
     HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, st));
     mark(2);
-    k_digits<true><<<grid, TPB, 0, st>>>(d_scalars, n, plan.widths, plan.W, plan.M, counts, offsets, entries);
+    k_digits<true><<<grid, TPB, 0, st>>>(d_scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, counts, offsets, entries);
     mark(3);
-    k_accumulate<<<(NB + 127) / 128, 128, 0, st>>>(d_bases, offsets, entries, NB, buckets);
+    k_accumulate<<<(NB + 127) / 128, 128, 0, st>>>(d_bases, n, in.tail_bases, offsets, entries, NB, buckets);
     mark(4);
     int T = plan.M < (uint32_t)REDUCE_THREADS ? (int)plan.M : REDUCE_THREADS;
     int log_s = 0;
     while (((uint32_t)T << log_s) < plan.M) log_s++;
     size_t smem = (size_t)T * sizeof(xyzz_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        HALO_CUDA(cudaFuncSetAttribute(k_bucket_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       REDUCE_THREADS * (int)sizeof(xyzz_t)));
-        attr_set = true;
-    }
+    HALO_CUDA(cudaFuncSetAttribute(k_bucket_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   REDUCE_THREADS * (int)sizeof(xyzz_t)));
     k_bucket_reduce<<<plan.W, T, smem, st>>>(buckets, plan.M, T, log_s, d_wsums_out);
     mark(5);
     ctx->kernel_launches += 4;
@@ -325,19 +328,29 @@ void msm_finish_host(const xyzz_t* wsums, const MsmPlan& plan, xyzz_t& out) {
     out = total;
 }
 
-void msm_device(halo_ctx* ctx, const affine_t* d_bases, const fr_t* d_scalars, uint64_t n, xyzz_t& out) {
-    if (n == 0) {
-        xyzz_set_inf(out);
-        return;
-    }
-    MsmPlan plan = msm_make_plan(n, ctx->force_c);
-    ctx->ws.wsums.reserve(64 * sizeof(xyzz_t) * 2);
+// Enqueue `count` MSMs back to back on the context stream (they share the workspace, so they serialise on the
+// stream), then one D2H of all window sums, one synchronisation, and the host Horner per MSM.
+void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs) {
+    if (count > 4) throw CudaError{cudaErrorInvalidValue, "msm_batch: count > 4", __FILE__, __LINE__};
+    MsmPlan plans[4];
+    ctx->ws.wsums.reserve(4 * MSM_MAX_WINDOWS * sizeof(xyzz_t));
     xyzz_t* d_wsums = ctx->ws.wsums.as<xyzz_t>();
-    msm_window_sums(ctx, d_bases, d_scalars, (uint32_t)n, plan, d_wsums);
-    xyzz_t h_wsums[128];
-    HALO_CUDA(cudaMemcpyAsync(h_wsums, d_wsums, plan.W * sizeof(xyzz_t), cudaMemcpyDeviceToHost, ctx->stream));
-    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->profile) {
+    if (!ctx->pinned) {
+        HALO_CUDA(cudaMallocHost(&ctx->pinned, 4 * MSM_MAX_WINDOWS * sizeof(xyzz_t)));
+        ctx->pinned_cap = 4 * MSM_MAX_WINDOWS * sizeof(xyzz_t);
+    }
+    xyzz_t* h_wsums = reinterpret_cast<xyzz_t*>(ctx->pinned);
+    bool any = false;
+    for (int k = 0; k < count; k++) {
+        if (ins[k].n + ins[k].n_tail == 0) continue;
+        plans[k] = msm_make_plan(ins[k].n + ins[k].n_tail, ctx->force_c);
+        msm_window_sums(ctx, ins[k], plans[k], d_wsums + k * MSM_MAX_WINDOWS);
+        HALO_CUDA(cudaMemcpyAsync(h_wsums + k * MSM_MAX_WINDOWS, d_wsums + k * MSM_MAX_WINDOWS, plans[k].W * sizeof(xyzz_t),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        any = true;
+    }
+    if (any) HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (any && ctx->profile) {
         float t[5];
         for (int i = 0; i < 5; i++) HALO_CUDA(cudaEventElapsedTime(&t[i], ctx->ev[i], ctx->ev[i + 1]));
         ctx->last.digits_ms = t[0];
@@ -347,7 +360,20 @@ void msm_device(halo_ctx* ctx, const affine_t* d_bases, const fr_t* d_scalars, u
         ctx->last.reduce_ms = t[4];
         HALO_CUDA(cudaEventElapsedTime(&ctx->last.total_ms, ctx->ev[0], ctx->ev[5]));
     }
-    msm_finish_host(h_wsums, plan, out);
+    for (int k = 0; k < count; k++) {
+        if (ins[k].n + ins[k].n_tail == 0)
+            xyzz_set_inf(outs[k]);
+        else
+            msm_finish_host(h_wsums + k * MSM_MAX_WINDOWS, plans[k], outs[k]);
+    }
+}
+
+void msm_device(halo_ctx* ctx, const affine_t* d_bases, const fr_t* d_scalars, uint64_t n, xyzz_t& out) {
+    MsmInput in;
+    in.bases = d_bases;
+    in.scalars = d_scalars;
+    in.n = (uint32_t)n;
+    msm_batch(ctx, &in, 1, &out);
 }
 
 }  // namespace halo

@@ -1,0 +1,130 @@
+// host/capi_host.cpp -- C view (include/halo_pcdl.h) of the C++ host layer, for ctypes / C callers.
+#include "../../include/halo_pcdl.h"
+
+#include "acc.hpp"
+#include "pcdl.hpp"
+#include "pedersen.hpp"
+
+using namespace halo;
+
+namespace {
+thread_local std::string g_host_error;
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return HALO_OK;
+    } catch (const HaloFailure& e) {
+        g_host_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_host_error = "out of host memory";
+        return HALO_ENOMEM;
+    } catch (const std::exception& e) {
+        g_host_error = e.what();
+        return HALO_EINVAL;
+    }
+}
+PallasPoly poly_from(const uint64_t* c, uint64_t n) {
+    PallasPoly p(n);
+    if (n) std::memcpy(p.data(), c, n * 32);
+    return p;
+}
+}  // namespace
+
+extern "C" {
+
+const char* halo_host_last_error(void) { return g_host_error.c_str(); }
+
+int halo_pedersen_commit(halo_ctx* ctx, const uint64_t* w, const uint64_t* gs_affine, uint64_t n_gs, const uint64_t* ms,
+                         uint64_t n_ms, uint64_t out_jac[12]) {
+    return guarded([&] {
+        PallasScalar ws;
+        if (w) ws = scalar_load(w);
+        PallasPoint r = pedersen::commit(ctx, w ? &ws : nullptr, gs_affine, n_gs, reinterpret_cast<const PallasScalar*>(ms), n_ms);
+        point_store(out_jac, r);
+    });
+}
+
+int halo_pcdl_commit(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, uint64_t d, const uint64_t* w, uint64_t out_jac[12]) {
+    return guarded([&] {
+        PallasScalar ws;
+        if (w) ws = scalar_load(w);
+        point_store(out_jac, pcdl::commit(ctx, poly_from(coeffs, n_coeffs), d, w ? &ws : nullptr));
+    });
+}
+
+int halo_pcdl_open(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, const uint64_t C_jac[12], uint64_t d,
+                   const uint64_t z[4], const uint64_t* w, const uint64_t* q, uint64_t n_q, const uint64_t* w_bar,
+                   halo_eval_proof* pi) {
+    return guarded([&] {
+        PallasScalar ws, wbs;
+        PallasPoly qp;
+        if (w) {
+            ensure(q && w_bar, HALO_EINVAL, "hiding open needs q and w_bar");
+            ws = scalar_load(w);
+            wbs = scalar_load(w_bar);
+            qp = poly_from(q, n_q);
+        }
+        pcdl::EvalProof p = pcdl::open(ctx, poly_from(coeffs, n_coeffs), point_load(C_jac), d, scalar_load(z), w ? &ws : nullptr,
+                                       w ? &qp : nullptr, w ? &wbs : nullptr);
+        pcdl::proof_to_c(p, *pi);
+    });
+}
+
+int halo_pcdl_succinct_check(halo_ctx* ctx, const uint64_t C_jac[12], uint64_t d, const uint64_t z[4], const uint64_t v[4],
+                             const halo_eval_proof* pi, uint64_t* xis_out, uint64_t U_out[12]) {
+    return guarded([&] {
+        auto hu = pcdl::succinct_check(ctx, point_load(C_jac), d, scalar_load(z), scalar_load(v), pcdl::proof_from_c(*pi));
+        if (xis_out) std::memcpy(xis_out, hu.first.xis.data(), hu.first.xis.size() * 32);
+        if (U_out) point_store(U_out, hu.second);
+    });
+}
+
+int halo_pcdl_check(halo_ctx* ctx, const uint64_t C_jac[12], uint64_t d, const uint64_t z[4], const uint64_t v[4],
+                    const halo_eval_proof* pi) {
+    return guarded([&] { pcdl::check(ctx, point_load(C_jac), d, scalar_load(z), scalar_load(v), pcdl::proof_from_c(*pi)); });
+}
+
+int halo_h_eval(const uint64_t* xis, uint32_t lg_n, const uint64_t z[4], uint64_t out[4]) {
+    return guarded([&] {
+        std::vector<PallasScalar> x(lg_n + 1);
+        std::memcpy(x.data(), xis, (lg_n + 1) * 32);
+        scalar_store(out, pcdl::HPoly(x).eval(scalar_load(z)));
+    });
+}
+
+int halo_acc_prover(halo_ctx* ctx, uint64_t d, const halo_instance* qs, uint64_t m, const uint64_t h0[2][4], const uint64_t w[4],
+                    const uint64_t* q, uint64_t n_q, const uint64_t w_bar[4], halo_accumulator* acc) {
+    return guarded([&] {
+        std::vector<acc::Instance> v;
+        for (uint64_t i = 0; i < m; i++) v.push_back(acc::instance_from_c(qs[i]));
+        acc::Accumulator a = acc::prover(ctx, d, v, PallasPoly{scalar_load(h0[0]), scalar_load(h0[1])}, scalar_load(w),
+                                         poly_from(q, n_q), scalar_load(w_bar));
+        acc::accumulator_to_c(a, *acc);
+    });
+}
+
+int halo_acc_verifier(halo_ctx* ctx, uint64_t d, const halo_instance* qs, uint64_t m, const halo_accumulator* acc) {
+    return guarded([&] {
+        std::vector<acc::Instance> v;
+        for (uint64_t i = 0; i < m; i++) v.push_back(acc::instance_from_c(qs[i]));
+        acc::verifier(ctx, d, v, acc::accumulator_from_c(*acc));
+    });
+}
+
+int halo_acc_decider(halo_ctx* ctx, const halo_accumulator* acc) {
+    return guarded([&] { acc::decider(ctx, acc::accumulator_from_c(*acc)); });
+}
+
+void halo_acc_to_instance(const halo_accumulator* acc, halo_instance* q) {
+    std::memcpy(q->C, acc->C_bar, 96);
+    q->d = acc->d;
+    std::memcpy(q->z, acc->z, 32);
+    std::memcpy(q->v, acc->v, 32);
+    q->pi = acc->pi;
+}
+
+void halo_point_serialize_compressed(const uint64_t p_jac[12], uint8_t out[33]) { serialize_compressed(point_load(p_jac), out); }
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// host/group.hpp -- host mirror of code/src/group.rs: type aliases, the dot products (dispatched to the
+// device through the C ABI), and the Fiat-Shamir macros rho_0! / rho_1! (host side, group.rs:41-89).
+//
+// Host arithmetic here is O(lg n) glue (challenges, inversions, a handful of point operations); the
+// O(n) work is behind halo_b200.h.  Field / curve code is shared with the device (csrc/fp.cuh, ec.cuh,
+// sha3.cuh compile as plain C++).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/halo_b200.h"
+#include "../csrc/ec.cuh"
+#include "../csrc/sha3.cuh"
+
+namespace halo {
+
+// group.rs:7-10
+using PallasScalar = fr_t;
+struct PallasPoint {  // Projective; kept as XYZZ on the host, Jacobian on the wire
+    xyzz_t p;
+};
+using PallasPoly = std::vector<PallasScalar>;  // DensePolynomial coefficients, low degree first
+
+struct HaloFailure : std::runtime_error {  // carries a HALO_E* / HALO_REJECT_* code; the analogue of panic / Err
+    int code;
+    HaloFailure(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void ensure(bool ok, int code, const char* msg) {
+    if (!ok) throw HaloFailure(code, msg);
+}
+inline void check_rc(halo_ctx* ctx, int rc) {
+    if (rc != HALO_OK) throw HaloFailure(rc, halo_last_error(ctx));
+}
+
+// ---- scalars -----------------------------------------------------------------------------------
+inline PallasScalar scalar_zero() { PallasScalar s; fp_zero(s); return s; }
+inline PallasScalar scalar_one() { PallasScalar s; fp_one(s); return s; }
+inline PallasScalar scalar_load(const uint64_t* p) { PallasScalar s; std::memcpy(&s, p, 32); return s; }
+inline void scalar_store(uint64_t* p, const PallasScalar& s) { std::memcpy(p, &s, 32); }
+inline PallasScalar operator*(const PallasScalar& a, const PallasScalar& b) { PallasScalar r; fp_mul(r, a, b); return r; }
+inline PallasScalar operator+(const PallasScalar& a, const PallasScalar& b) { PallasScalar r; fp_add(r, a, b); return r; }
+inline PallasScalar operator-(const PallasScalar& a, const PallasScalar& b) { PallasScalar r; fp_sub(r, a, b); return r; }
+inline PallasScalar operator-(const PallasScalar& a) { PallasScalar r; fp_neg(r, a); return r; }
+inline bool operator==(const PallasScalar& a, const PallasScalar& b) { return fp_eq(a, b); }
+inline PallasScalar scalar_inverse(const PallasScalar& a) { PallasScalar r; fp_inv(r, a); return r; }
+
+// ---- points --------------------------------------------------------------------------------------
+inline PallasPoint point_load(const uint64_t* jac12) {
+    jac_t j;
+    std::memcpy(&j, jac12, 96);
+    PallasPoint r;
+    jac_to_xyzz(r.p, j);
+    return r;
+}
+inline void point_store(uint64_t* jac12, const PallasPoint& a) {
+    jac_t j;
+    xyzz_to_jac(j, a.p);
+    std::memcpy(jac12, &j, 96);
+}
+inline PallasPoint point_zero() { PallasPoint r; xyzz_set_inf(r.p); return r; }
+inline PallasPoint operator+(const PallasPoint& a, const PallasPoint& b) { PallasPoint r = a; xyzz_add(r.p, b.p); return r; }
+inline PallasPoint operator-(const PallasPoint& a) { PallasPoint r = a; if (!xyzz_is_inf(r.p)) xyzz_neg(r.p); return r; }
+inline PallasPoint operator-(const PallasPoint& a, const PallasPoint& b) { return a + (-b); }
+// `Projective * Fr`
+inline PallasPoint operator*(const PallasPoint& a, const PallasScalar& k) {
+    uint32_t kc[8];
+    fp_to_canon(kc, k);
+    PallasPoint r;
+    xyzz_mul_canon(r.p, a.p, kc);
+    return r;
+}
+// Projective equality (representation independent)
+inline bool operator==(const PallasPoint& a, const PallasPoint& b) {
+    bool ia = xyzz_is_inf(a.p), ib = xyzz_is_inf(b.p);
+    if (ia || ib) return ia && ib;
+    fq_t l, r;
+    fp_mul(l, a.p.x, b.p.zz);
+    fp_mul(r, b.p.x, a.p.zz);
+    if (!fp_eq(l, r)) return false;
+    fp_mul(l, a.p.y, b.p.zzz);
+    fp_mul(r, b.p.y, a.p.zzz);
+    return fp_eq(l, r);
+}
+
+// ark-serialize `serialize_compressed` of a short-Weierstrass point for Pallas (ark-ec 0.5): normalise,
+// then Fp::serialize_with_flags(x, SWFlags) -> ceil((255 + 2) / 8) = 33 bytes: 32 bytes little-endian canonical x
+// and a final byte holding only the flags: 0x80 if y > -y (as canonical integers), 0x40 for infinity (x = 0).
+// [arkworks is not in the reference tree; restated from the published crate, see DESIGN.md "parity unpinned".]
+inline void serialize_compressed(const PallasPoint& a, uint8_t out[33]) {
+    std::memset(out, 0, 33);
+    affine_t aff;
+    xyzz_to_affine(aff, a.p);
+    if (xyzz_is_inf(a.p)) {
+        out[32] = 0x40;
+        return;
+    }
+    uint32_t x[8], y[8], ny[8];
+    fq_t negy;
+    fp_to_canon(x, aff.x);
+    fp_to_canon(y, aff.y);
+    fp_neg(negy, aff.y);
+    fp_to_canon(ny, negy);
+    for (int i = 0; i < 8; i++)
+        for (int b = 0; b < 4; b++) out[4 * i + b] = (uint8_t)(x[i] >> (8 * b));
+    bool gt = false;
+    for (int i = 7; i >= 0; i--) {
+        if (y[i] != ny[i]) {
+            gt = y[i] > ny[i];
+            break;
+        }
+    }
+    if (gt) out[32] = 0x80;
+}
+
+// ---- Fiat-Shamir transcript: group.rs:41-64 (rho_0!, tag 0) and :66-89 (rho_1!, tag 1) -----------------
+class Transcript {
+    std::vector<uint8_t> data_;
+
+public:
+    Transcript& point(const PallasPoint& p) {
+        uint8_t b[33];
+        serialize_compressed(p, b);
+        data_.insert(data_.end(), b, b + 33);
+        return *this;
+    }
+    Transcript& scalar(const PallasScalar& s) {  // Fr::serialize_compressed: 32 bytes little-endian canonical
+        uint32_t c[8];
+        fp_to_canon(c, s);
+        for (int i = 0; i < 8; i++)
+            for (int b = 0; b < 4; b++) data_.push_back((uint8_t)(c[i] >> (8 * b)));
+        return *this;
+    }
+    Transcript& u64(uint64_t v) {  // Vec length prefix / usize
+        for (int b = 0; b < 8; b++) data_.push_back((uint8_t)(v >> (8 * b)));
+        return *this;
+    }
+    Transcript& u8(uint8_t v) {  // Option discriminant
+        data_.push_back(v);
+        return *this;
+    }
+    // SHA3-256(data || u32_le(tag)) -> from_le_bytes_mod_order (group.rs:52-60)
+    PallasScalar finish(uint32_t tag) {
+        for (int b = 0; b < 4; b++) data_.push_back((uint8_t)(tag >> (8 * b)));
+        uint64_t dg[4];
+        sha3_256(data_.data(), data_.size(), dg);
+        uint32_t s[8], m[8], t[8];
+        for (int j = 0; j < 4; j++) {
+            s[2 * j] = (uint32_t)dg[j];
+            s[2 * j + 1] = (uint32_t)(dg[j] >> 32);
+        }
+        fp_mod_limbs<FrParams>(m);
+        for (int it = 0; it < 3; it++) {  // r > 2^254: at most three subtractions
+            uint32_t borrow = sub8(t, s, m);
+            for (int j = 0; j < 8; j++) s[j] = borrow ? s[j] : t[j];
+        }
+        PallasScalar r;
+        fp_from_canon(r, s);
+        return r;
+    }
+};
+
+// ---- group.rs functions ----------------------------------------------------------------------------------
+// group.rs:13-15
+inline PallasScalar scalar_dot(halo_ctx* ctx, const PallasScalar* xs, const PallasScalar* ys, uint64_t n) {
+    uint64_t out[4];
+    check_rc(ctx, halo_scalar_dot(ctx, reinterpret_cast<const uint64_t*>(xs), reinterpret_cast<const uint64_t*>(ys), n, out));
+    return scalar_load(out);
+}
+// group.rs:18-21 (Jacobian bases on the wire)
+inline PallasPoint point_dot(halo_ctx* ctx, const PallasScalar* xs, const std::vector<PallasPoint>& Gs, uint64_t n) {
+    if (n <= 4) {  // a handful of terms (acc.rs:178 has m + 1 <= 3): host double-and-add, no device round trip
+        PallasPoint acc = point_zero();
+        for (uint64_t i = 0; i < n; i++) acc = acc + Gs[i] * xs[i];
+        return acc;
+    }
+    std::vector<uint64_t> jac(12 * n);
+    for (uint64_t i = 0; i < n; i++) point_store(&jac[12 * i], Gs[i]);
+    uint64_t out[12];
+    check_rc(ctx, halo_msm_jac(ctx, jac.data(), reinterpret_cast<const uint64_t*>(xs), n, out));
+    return point_load(out);
+}
+// group.rs:29-37
+inline std::vector<PallasScalar> construct_powers(const PallasScalar& z, uint64_t n) {
+    std::vector<PallasScalar> zs(n);
+    PallasScalar cur = scalar_one();
+    for (uint64_t i = 0; i < n; i++) {
+        zs[i] = cur;
+        cur = cur * z;
+    }
+    return zs;
+}
+
+// consts.rs S, H of the context
+inline void params_SH(halo_ctx* ctx, PallasPoint& S, PallasPoint& H) {
+    uint64_t s[12], h[12];
+    check_rc(ctx, halo_get_SH(ctx, s, h));
+    S = point_load(s);
+    H = point_load(h);
+}
+
+}  // namespace halo

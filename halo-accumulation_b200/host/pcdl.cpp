@@ -1,0 +1,215 @@
+// host/pcdl.cpp -- see pcdl.hpp.  Control flow follows code/src/pcdl.rs step by step; every O(n) step is a
+// call into libhalo_b200.so.
+#include "pcdl.hpp"
+
+#include "pedersen.hpp"
+
+namespace halo {
+namespace pcdl {
+
+static bool is_pow2(uint64_t n) { return n && !(n & (n - 1)); }
+static uint32_t ilog2(uint64_t n) {
+    uint32_t l = 0;
+    while (((uint64_t)1 << (l + 1)) <= n) l++;
+    return l;
+}
+static uint64_t degree(const PallasPoly& p) {  // DensePolynomial::degree (trailing zeros trimmed)
+    uint64_t n = p.size();
+    while (n > 0 && fp_is_zero(p[n - 1])) n--;
+    return n ? n - 1 : 0;
+}
+
+PallasPoly HPoly::get_poly(halo_ctx* ctx) const {
+    uint32_t lg_n = (uint32_t)xis.size() - 1;
+    PallasPoly out((size_t)1 << lg_n);
+    check_rc(ctx, halo_h_expand(ctx, reinterpret_cast<const uint64_t*>(xis.data()), lg_n, reinterpret_cast<uint64_t*>(out.data())));
+    return out;
+}
+
+PallasScalar HPoly::eval(const PallasScalar& z) const {
+    size_t lg_n = xis.size() - 1;
+    PallasScalar one = scalar_one();
+    PallasScalar v = one + xis[lg_n] * z;
+    PallasScalar z_i = z;
+    for (size_t i = 1; i < lg_n; i++) {
+        z_i = z_i * z_i;
+        v = v * (one + xis[lg_n - i] * z_i);
+    }
+    return v;
+}
+
+PallasPoint commit(halo_ctx* ctx, const PallasPoly& p, uint64_t d, const PallasScalar* w) {
+    uint64_t n = d + 1;
+    ensure(is_pow2(n), HALO_EINVAL, "d+1 is not a power of 2");  // pcdl.rs:102
+    ensure(degree(p) <= d, HALO_EINVAL, "p.degree() > d");       // pcdl.rs:103
+    ensure(n <= halo_num_generators(ctx), HALO_EINVAL, "d > D");  // pcdl.rs:104
+    uint64_t n_coeffs = p.size() < n ? p.size() : n;
+    // coeffs.resize(n, ZERO) (pcdl.rs:106-107): the zero tail is implied, not uploaded
+    return pedersen::commit(ctx, w, nullptr, n, p.data(), n_coeffs, true);
+}
+
+EvalProof open(halo_ctx* ctx, const PallasPoly& p, const PallasPoint& C, uint64_t d, const PallasScalar& z,
+               const PallasScalar* w, const PallasPoly* q, const PallasScalar* w_bar) {
+    uint64_t n = d + 1;
+    ensure(is_pow2(n), HALO_EINVAL, "d+1 is not a power of 2");  // pcdl.rs:130
+    uint64_t deg = degree(p);
+    ensure(deg <= d, HALO_EINVAL, "p.degree() > d");             // pcdl.rs:131
+    ensure(n <= halo_num_generators(ctx), HALO_EINVAL, "d > D");  // pcdl.rs:132
+    uint32_t lg_n = ilog2(n);
+    PallasPoint S, H;
+    params_SH(ctx, S, H);
+
+    // device state: c (zero padded), G, z-powers; v = p(z) (pcdl.rs:135, :183-186)
+    halo_ipa* st = nullptr;
+    uint64_t vbuf[4];
+    uint64_t n_coeffs = p.size() < n ? p.size() : n;
+    check_rc(ctx, halo_ipa_begin(ctx, reinterpret_cast<const uint64_t*>(p.data()), n_coeffs, n,
+                                 reinterpret_cast<const uint64_t*>(&z), &st, vbuf));
+    struct Guard {
+        halo_ipa* s;
+        ~Guard() { halo_ipa_destroy(s); }
+    } guard{st};
+    PallasScalar v = scalar_load(vbuf);
+
+    EvalProof pi;
+    PallasPoint C_prime = C;
+    if (w) {  // pcdl.rs:137-164
+        ensure(q && w_bar, HALO_EINVAL, "hiding open needs the random polynomial q and w_bar");
+        ensure(deg >= 1 && q->size() == deg, HALO_ELEN, "q must have deg(p) coefficients (PallasPoly::rand(p.degree() - 1))");
+        // p_bar = q (X - z); C_bar = commit(p_bar, d, w_bar)  (:140-149)
+        uint64_t cb[12];
+        check_rc(ctx, halo_ipa_blind_commit(st, reinterpret_cast<const uint64_t*>(q->data()), q->size(), cb));
+        PallasPoint C_bar = S * (*w_bar) + point_load(cb);
+        // alpha = rho_0(C, z, v, C_bar)  (:153)
+        PallasScalar a = Transcript().point(C).scalar(z).scalar(v).point(C_bar).finish(0);
+        // p' = p + alpha p_bar  (:156)
+        check_rc(ctx, halo_ipa_blind_apply(st, reinterpret_cast<const uint64_t*>(&a)));
+        // w' = w_bar alpha + w ; C' = C + alpha C_bar - w' S  (:159-162)
+        PallasScalar w_prime = (*w_bar) * a + (*w);
+        C_prime = C + C_bar * a - S * w_prime;
+        pi.hiding = true;
+        pi.C_bar = C_bar;
+        pi.w_prime = w_prime;
+    }
+
+    // xi_0 = rho_0(C', z, v); H' = xi_0 H  (:180-181)
+    PallasScalar xi_i = Transcript().point(C_prime).scalar(z).scalar(v).finish(0);
+    PallasPoint H_prime = H * xi_i;
+    uint64_t hp[12];
+    point_store(hp, H_prime);
+    check_rc(ctx, halo_ipa_set_hprime(st, hp));
+
+    pi.Ls.reserve(lg_n);
+    pi.Rs.reserve(lg_n);
+    for (uint32_t round = 0; round < lg_n; round++) {  // :195-227
+        uint64_t Lb[12], Rb[12];
+        check_rc(ctx, halo_ipa_round_lr(st, Lb, Rb));  // :199-209
+        PallasPoint L = point_load(Lb), R = point_load(Rb);
+        pi.Ls.push_back(L);
+        pi.Rs.push_back(R);
+        PallasScalar xi_next = Transcript().scalar(xi_i).point(L).point(R).finish(0);  // :212
+        ensure(!fp_is_zero(xi_next), HALO_EINVAL, "challenge is zero (inverse().unwrap())");  // :213
+        PallasScalar xi_next_inv = scalar_inverse(xi_next);
+        xi_i = xi_next;
+        check_rc(ctx, halo_ipa_round_fold(st, reinterpret_cast<const uint64_t*>(&xi_next),
+                                          reinterpret_cast<const uint64_t*>(&xi_next_inv)));  // :216-224
+    }
+    uint64_t Ub[12], cb[4];
+    check_rc(ctx, halo_ipa_finish(st, Ub, cb));  // :230-231
+    pi.U = point_load(Ub);
+    pi.c = scalar_load(cb);
+    return pi;
+}
+
+std::pair<HPoly, PallasPoint> succinct_check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z,
+                                             const PallasScalar& v, const EvalProof& pi) {
+    uint64_t n = d + 1;
+    ensure(is_pow2(n), HALO_EINVAL, "d+1 is not a power of 2!");           // :261
+    ensure(n <= halo_num_generators(ctx), HALO_EINVAL, "d was larger than D!");  // :262
+    uint32_t lg_n = ilog2(n);
+    ensure(pi.Ls.size() == lg_n && pi.Rs.size() == lg_n, HALO_EINVAL, "proof has the wrong number of rounds");
+    PallasPoint S, H;
+    params_SH(ctx, S, H);
+
+    // C' = C + alpha C_bar - w' S  (:272-279)
+    PallasPoint C_prime = C;
+    if (pi.hiding) {
+        PallasScalar a = Transcript().point(C).scalar(z).scalar(v).point(pi.C_bar).finish(0);
+        C_prime = C + pi.C_bar * a - S * pi.w_prime;
+    }
+    // xi_0, challenges (:282-293); the group arithmetic of :285-298 and :307-310 is one small MSM:
+    //   C_lg == c U + v' H'   <=>   C' + (xi_0 v - xi_0 v') H + sum_i (xi_{i+1}^-1 L_i + xi_{i+1} R_i) - c U == 0
+    std::vector<PallasScalar> xis;
+    xis.reserve(lg_n + 1);
+    xis.push_back(Transcript().point(C_prime).scalar(z).scalar(v).finish(0));
+    std::vector<PallasScalar> scalars;
+    std::vector<uint64_t> bases;
+    scalars.reserve(2 * lg_n + 2);
+    bases.resize(12 * (2 * (size_t)lg_n + 2));
+    size_t k = 0;
+    for (uint32_t i = 0; i < lg_n; i++) {
+        PallasScalar xi_next = Transcript().scalar(xis[i]).point(pi.Ls[i]).point(pi.Rs[i]).finish(0);  // :293
+        ensure(!fp_is_zero(xi_next), HALO_EINVAL, "challenge is zero (inverse().unwrap())");            // :297
+        xis.push_back(xi_next);
+        point_store(&bases[12 * k++], pi.Ls[i]);
+        scalars.push_back(scalar_inverse(xi_next));
+        point_store(&bases[12 * k++], pi.Rs[i]);
+        scalars.push_back(xi_next);
+    }
+    HPoly h(xis);                                   // :301
+    PallasScalar v_prime = pi.c * h.eval(z);        // :304
+    point_store(&bases[12 * k++], H);
+    scalars.push_back(xis[0] * v - xis[0] * v_prime);  // v H' - v' H' with H' = xi_0 H  (:285, :288, :308)
+    point_store(&bases[12 * k++], pi.U);
+    scalars.push_back(-pi.c);
+    uint64_t out[12];
+    check_rc(ctx, halo_msm_jac(ctx, bases.data(), reinterpret_cast<const uint64_t*>(scalars.data()), k, out));
+    PallasPoint lhs = C_prime + point_load(out);
+    ensure(xyzz_is_inf(lhs.p), HALO_REJECT_SUCCINCT, "C_(log_n) != CM.Commit_Sigma(c || v')");  // :307-310
+    return {h, pi.U};                                                                           // :313
+}
+
+void check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z, const PallasScalar& v,
+           const EvalProof& pi) {
+    auto hu = succinct_check(ctx, C, d, z, v, pi);  // :332
+    const HPoly& h = hu.first;
+    // comm = pedersen::commit(None, GS[0..d+1], h.get_poly().coeffs) (:338): expansion + MSM fused on the device
+    uint64_t out[12];
+    check_rc(ctx, halo_h_msm(ctx, reinterpret_cast<const uint64_t*>(h.xis.data()), (uint32_t)h.xis.size() - 1, out));
+    ensure(hu.second == point_load(out), HALO_REJECT_U, "U != CM.Commit(ck, h_vec)");  // :339
+}
+
+EvalProof proof_from_c(const halo_eval_proof& p) {
+    EvalProof r;
+    ensure(p.lg_n <= HALO_MAX_LG, HALO_EINVAL, "lg_n too large");
+    for (uint32_t i = 0; i < p.lg_n; i++) {
+        r.Ls.push_back(point_load(p.Ls[i]));
+        r.Rs.push_back(point_load(p.Rs[i]));
+    }
+    r.U = point_load(p.U);
+    r.c = scalar_load(p.c);
+    r.hiding = p.hiding != 0;
+    if (r.hiding) {
+        r.C_bar = point_load(p.C_bar);
+        r.w_prime = scalar_load(p.w_prime);
+    }
+    return r;
+}
+void proof_to_c(const EvalProof& p, halo_eval_proof& out) {
+    std::memset(&out, 0, sizeof out);
+    out.lg_n = (uint32_t)p.Ls.size();
+    out.hiding = p.hiding ? 1 : 0;
+    for (size_t i = 0; i < p.Ls.size(); i++) {
+        point_store(out.Ls[i], p.Ls[i]);
+        point_store(out.Rs[i], p.Rs[i]);
+    }
+    point_store(out.U, p.U);
+    scalar_store(out.c, p.c);
+    if (p.hiding) {
+        point_store(out.C_bar, p.C_bar);
+        scalar_store(out.w_prime, p.w_prime);
+    }
+}
+
+}  // namespace pcdl
+}  // namespace halo

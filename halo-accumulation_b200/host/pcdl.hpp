@@ -1,0 +1,46 @@
+// host/pcdl.hpp -- host mirror of code/src/pcdl.rs (Bulletproofs-style polynomial commitment, DL based).
+#pragma once
+#include "../../include/halo_pcdl.h"
+#include "group.hpp"
+
+namespace halo {
+namespace pcdl {
+
+// pcdl.rs:22-30
+struct EvalProof {
+    std::vector<PallasPoint> Ls, Rs;
+    PallasPoint U;
+    PallasScalar c;
+    bool hiding = false;  // C_bar / w_prime are Some(..)
+    PallasPoint C_bar;
+    PallasScalar w_prime;
+};
+
+// pcdl.rs:44-92
+struct HPoly {
+    std::vector<PallasScalar> xis;
+    explicit HPoly(std::vector<PallasScalar> x) : xis(std::move(x)) {}
+    // pcdl.rs:56-77: coefficient vector (n = 2^lg n elements), expanded on the device
+    PallasPoly get_poly(halo_ctx* ctx) const;
+    // pcdl.rs:79-91
+    PallasScalar eval(const PallasScalar& z) const;
+};
+
+// pcdl.rs:99-110
+PallasPoint commit(halo_ctx* ctx, const PallasPoly& p, uint64_t d, const PallasScalar* w);
+// pcdl.rs:120-242; rng draws made explicit: q (deg p coefficients), w_bar
+EvalProof open(halo_ctx* ctx, const PallasPoly& p, const PallasPoint& C, uint64_t d, const PallasScalar& z,
+               const PallasScalar* w, const PallasPoly* q, const PallasScalar* w_bar);
+// pcdl.rs:252-314; throws HaloFailure(HALO_REJECT_SUCCINCT) on reject
+std::pair<HPoly, PallasPoint> succinct_check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z,
+                                             const PallasScalar& v, const EvalProof& pi);
+// pcdl.rs:323-342
+void check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z, const PallasScalar& v,
+           const EvalProof& pi);
+
+// wire conversion
+EvalProof proof_from_c(const halo_eval_proof& p);
+void proof_to_c(const EvalProof& p, halo_eval_proof& out);
+
+}  // namespace pcdl
+}  // namespace halo

@@ -68,6 +68,8 @@ int halo_load_generators(halo_ctx *ctx, const uint64_t S_jac[12], const uint64_t
 /* Reads generators back (tests / caching): out_affine[i] = G_{off+i}. */
 int halo_get_generators(halo_ctx *ctx, uint64_t off, uint64_t n, uint64_t *out_affine /*[n][8]*/);
 int halo_get_SH(halo_ctx *ctx, uint64_t S_jac[12], uint64_t H_jac[12]);
+/* Number of resident generators: the reference's N (consts.rs:23); D = N - 1. */
+uint64_t halo_num_generators(halo_ctx *ctx);
 /* Raw derivation without installing: out_affine[i] = P_{start+i}. */
 int halo_derive_points(halo_ctx *ctx, uint64_t start, uint64_t count, uint64_t *out_affine /*[count][8]*/);
 
@@ -84,6 +86,44 @@ int halo_msm_jac(halo_ctx *ctx, const uint64_t *bases_jac /*[n][12]*/, const uin
                  uint64_t out_jac[12]);
 /* Device-resident variant for throughput measurement: d_scalars is a CUDA device pointer to n scalars. */
 int halo_msm_gens_resident(halo_ctx *ctx, const void *d_scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]);
+
+/* ---- scalar vectors -------------------------------------------------------------------------------- */
+/* sum_i xs[i] * ys[i] in Fr.  Replaces group.rs:13-15 `scalar_dot`. */
+int halo_scalar_dot(halo_ctx *ctx, const uint64_t *xs, const uint64_t *ys, uint64_t n, uint64_t out[4]);
+/* out[j] = z^j, j < n.  Replaces group.rs:29-37 `construct_powers`. */
+int halo_construct_powers(halo_ctx *ctx, const uint64_t z[4], uint64_t n, uint64_t *out /*[n][4]*/);
+
+/* ---- K5: the polynomial h(X) = prod_{i<lg n} (1 + xi_{lg n - i} X^{2^i}) ---------------------------- */
+/* Coefficient vector of h.  xis = [xi_0 .. xi_{lg n}] (xi_0 is carried but unused, as in the reference).
+ * Replaces HPoly::get_poly, pcdl.rs:56-77. */
+int halo_h_expand(halo_ctx *ctx, const uint64_t *xis /*[lg_n+1][4]*/, uint32_t lg_n, uint64_t *out /*[2^lg_n][4]*/);
+/* U' = <GS[0..n), coeffs(h)>: expansion and MSM without the coefficients ever leaving the device.
+ * Replaces pcdl.rs:338 (`pedersen::commit(None, &GS[0..n], &h.get_poly().coeffs)`), the decider's MSM. */
+int halo_h_msm(halo_ctx *ctx, const uint64_t *xis /*[lg_n+1][4]*/, uint32_t lg_n, uint64_t out_jac[12]);
+/* out = h_0 + sum_{i<m} alphas[i+1] * coeffs(h_i), zero-padded to n = 2^lg_n.
+ * Replaces AccumulatedHPolys::get_poly, acc.rs:85-94. */
+int halo_h_lincomb(halo_ctx *ctx, const uint64_t *h0 /*[n_h0][4]*/, uint64_t n_h0, const uint64_t *alphas /*[m+1][4]*/,
+                   const uint64_t *xis /*[m][lg_n+1][4]*/, uint64_t m, uint32_t lg_n, uint64_t *out /*[2^lg_n][4]*/);
+
+/* ---- K3 / K4 / K7: the rounds of PCDL.open (pcdl.rs:183-231) ----------------------------------------- */
+typedef struct halo_ipa halo_ipa;
+/* Uploads the coefficients of p (zero-padded to n, pcdl.rs:183-184), copies GS[0..n) (pcdl.rs:185), builds
+ * (1, z, .., z^{n-1}) on the device (pcdl.rs:186) and returns v = p(z) (pcdl.rs:135). */
+int halo_ipa_begin(halo_ctx *ctx, const uint64_t *coeffs /*[n_coeffs][4]*/, uint64_t n_coeffs, uint64_t n,
+                   const uint64_t z[4], halo_ipa **out, uint64_t v_out[4]);
+void halo_ipa_destroy(halo_ipa *st);
+/* Hiding (pcdl.rs:137-164): p_bar = q (X - z) on the device, returns <GS, p_bar> (the caller adds w_bar * S). */
+int halo_ipa_blind_commit(halo_ipa *st, const uint64_t *q /*[n_q][4]*/, uint64_t n_q, uint64_t out_jac[12]);
+/* p' = p + alpha p_bar (pcdl.rs:156). */
+int halo_ipa_blind_apply(halo_ipa *st, const uint64_t alpha[4]);
+/* H' = xi_0 * H (pcdl.rs:181), computed by the caller. */
+int halo_ipa_set_hprime(halo_ipa *st, const uint64_t Hprime_jac[12]);
+/* L = <c_hi, G_lo> + <c_hi, z_lo> H', R = <c_lo, G_hi> + <c_lo, z_hi> H' for the current round (pcdl.rs:199-209). */
+int halo_ipa_round_lr(halo_ipa *st, uint64_t L_jac[12], uint64_t R_jac[12]);
+/* G <- G_lo + xi G_hi, c <- c_lo + xi^-1 c_hi, z <- z_lo + xi z_hi (pcdl.rs:216-224). */
+int halo_ipa_round_fold(halo_ipa *st, const uint64_t xi[4], const uint64_t xi_inv[4]);
+/* U = G[0], c = c[0] after lg n rounds (pcdl.rs:230-231). */
+int halo_ipa_finish(halo_ipa *st, uint64_t U_jac[12], uint64_t c[4]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,268 @@
+"""GPU parity tests for the PCDL / ASDL path through the host layer (mirror of pcdl.rs / acc.rs) and the C ABI:
+identical commitments, L/R values, accumulators and accept/reject decisions as the CPU oracle on the same inputs.
+Shapes follow the reference's own tests (pcdl.rs:440-483 test_check*, acc.rs:298-315 test_acc_scheme,
+pcdl.rs:381-438 test_u_check, pcdl.rs:485-509 test_construct_h_with_degree_7, pedersen.rs:54-63)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+R_MOD = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
+
+
+@pytest.fixture(scope="module")
+def env(ctx, oracle):
+    """Context with 2^16 generators and the oracle holding the very same parameters."""
+    from halo_accumulation_b200 import acc, group, pcdl, pedersen
+
+    ctx.derive_generators(1 << 16)
+    S, H = ctx.get_SH()
+    oracle.set_params(S, H, ctx.get_generators(0, 1 << 16))
+    return dict(ctx=ctx, O=oracle, pcdl=pcdl, acc=acc, pedersen=pedersen, group=group)
+
+
+def _same_proof(O, a, b):
+    """a: halo EvalProof, b: oracle EvalProof -- equal group elements and identical scalars."""
+    assert a.lg_n == b.lg_n and a.hiding == b.hiding
+    for i in range(a.lg_n):
+        assert O.pt_eq(np.array(a.Ls[i]), np.array(b.Ls[i])), f"L[{i}]"
+        assert O.pt_eq(np.array(a.Rs[i]), np.array(b.Rs[i])), f"R[{i}]"
+    assert O.pt_eq(np.array(a.U), np.array(b.U))
+    assert list(a.c) == list(b.c)
+    if a.hiding:
+        assert O.pt_eq(np.array(a.C_bar), np.array(b.C_bar))
+        assert list(a.w_prime) == list(b.w_prime)
+
+
+def _as_oracle_proof(O, pi):
+    return O.EvalProof.from_buffer_copy(bytes(pi))
+
+
+def test_struct_layouts_match(env):
+    from halo_accumulation_b200 import _host
+
+    O = env["O"]
+    assert C.sizeof(_host.EvalProof) == C.sizeof(O.EvalProof)
+    assert C.sizeof(_host.Instance) == C.sizeof(O.Instance)
+    assert C.sizeof(_host.Accumulator) == C.sizeof(O.Accumulator)
+
+
+def test_vector_helpers(env):
+    ctx, O, group = env["ctx"], env["O"], env["group"]
+    for n in (1, 2, 31, 1000, 70000):
+        a, b = O.random_scalars(n, n), O.random_scalars(n, n + 1)
+        assert group.scalar_dot(ctx, a, b).tolist() == O.scalar_dot(a, b).tolist()
+        z = O.random_scalars(1, 3 * n)[0]
+        assert np.array_equal(group.construct_powers(ctx, z, n), O.construct_powers(z, n))
+
+
+@pytest.mark.parametrize("lg_n", [1, 2, 3, 4, 7, 10, 16])
+def test_h_poly(env, lg_n):
+    """HPoly::get_poly / eval (pcdl.rs:56-91), incl. the index convention pinned by pcdl.rs:485-509."""
+    ctx, O, pcdl = env["ctx"], env["O"], env["pcdl"]
+    xis = O.random_scalars(lg_n + 1, 40 + lg_n)
+    h = pcdl.HPoly(xis)
+    got = h.get_poly(ctx)
+    assert np.array_equal(got, O.h_get_poly(xis))
+    z = O.random_scalars(1, 9)[0]
+    assert h.eval(z).tolist() == O.h_eval(xis, z).tolist()
+    if lg_n == 3:  # test_construct_h_with_degree_7
+        x = O.from_mont(xis)
+        exp = [1, x[3], x[2], x[2] * x[3], x[1], x[1] * x[3], x[1] * x[2], x[1] * x[2] * x[3]]
+        assert O.from_mont(got) == [e % R_MOD for e in exp]
+
+
+def test_u_check_kat(env):
+    """pcdl.rs:381-438 with the reference's fixed inputs GS[0..8], xi = (0,1,2,3); expected value from SURVEY A.6."""
+    ctx, O, pcdl, pedersen = env["ctx"], env["O"], env["pcdl"], env["pedersen"]
+    xis = O.to_mont([0, 1, 2, 3])
+    h = pcdl.HPoly(xis).get_poly(ctx)
+    assert O.from_mont(h) == [1, 3, 2, 6, 1, 3, 2, 6]
+    U = pedersen.commit(ctx, None, ctx.get_generators(0, 8), h)
+    assert O.pt_to_affine_ints(U) == (0x18CEF7A91C998EAB6266EAA5C7523A520B6F9B56AEFE02B7CB48B226B9C0530C,
+                                      0x2CC9CEE89D461087F1312759EFB678EC548F5CDA04F99A56429AE889CC2D7DA3)
+    assert O.pt_eq(ctx._h and U, O.pedersen_commit(None, ctx.get_generators(0, 8), h))
+
+
+def test_pedersen_homomorphism(env):
+    """pedersen.rs:54-63"""
+    ctx, O, pedersen = env["ctx"], env["O"], env["pedersen"]
+    l = 64
+    Gs = ctx.get_generators(0, l)
+    for rep in range(3):
+        m1, m2 = O.random_scalars(l, 10 * rep), O.random_scalars(l, 10 * rep + 1)
+        w1, w2 = O.random_scalars(2, 10 * rep + 2)
+        msum = ctx.test_fp_op(1, 1, m1, m2)
+        wsum = ctx.test_fp_op(1, 1, w1.reshape(1, 4), w2.reshape(1, 4))[0]
+        inner = pedersen.commit(ctx, wsum, Gs, msum)
+        outer = O.pt_add(pedersen.commit(ctx, w1, Gs, m1), pedersen.commit(ctx, w2, Gs, m2))
+        assert O.pt_eq(inner, outer)
+        assert O.pt_eq(inner, O.pedersen_commit(wsum, Gs, msum))
+    with pytest.raises(Exception):
+        pedersen.commit(ctx, None, Gs, m1[:10])  # length mismatch asserts (pedersen.rs:7-12)
+
+
+def test_serialize_compressed_matches_oracle(env):
+    from halo_accumulation_b200 import _host
+
+    ctx, O = env["ctx"], env["O"]
+    pts = [O.affine_to_jac(g)[0] for g in ctx.get_generators(0, 16)]
+    pts += [O.pt_mul(pts[0], O.to_mont([R_MOD - 1])[0]), O.pt_from_affine_ints(None), O.pt_add(pts[1], pts[2])]
+    for p in pts:
+        out = (C.c_uint8 * 33)()
+        _host.lib().halo_point_serialize_compressed(p.ctypes.data_as(C.POINTER(C.c_uint64)), out)
+        assert bytes(out) == O.pt_serialize_compressed(p)
+
+
+@pytest.mark.parametrize("n,hiding", [(2, 0), (2, 1), (4, 1), (8, 0), (64, 1), (512, 0), (512, 1), (4096, 1), (1 << 14, 0)])
+def test_pcdl_commit_open_check(env, n, hiding):
+    """test_check / test_check_no_hiding (pcdl.rs:440-483) with ragged degree d' < d, against the oracle."""
+    ctx, O, pcdl = env["ctx"], env["O"], env["pcdl"]
+    d = n - 1
+    dp = max(1, (2 * n) // 3 - 1) if n > 2 else 1
+    p = O.random_scalars(dp + 1, 1000 + n)
+    w = O.random_scalars(1, 7)[0] if hiding else None
+    q = O.random_scalars(dp, 8) if hiding else None
+    wb = O.random_scalars(1, 9)[0] if hiding else None
+    Cm = pcdl.commit(ctx, p, d, w)
+    assert O.pt_eq(Cm, O.pcdl_commit(p, d, w, threads=8))
+    z = O.random_scalars(1, 10)[0]
+    v = O.scalar_dot(p, O.construct_powers(z, dp + 1))
+    pi = pcdl.open(ctx, p, Cm, d, z, w, q, wb)
+    _same_proof(O, pi, O.pcdl_open(p, Cm, d, z, w, q, wb, threads=8))
+    pcdl.check(ctx, Cm, d, z, v, pi)                                   # accepts
+    assert O.pcdl_check(Cm, d, z, v, _as_oracle_proof(O, pi), threads=8) == 0  # the oracle accepts the GPU proof
+    h, U = pcdl.succinct_check(ctx, Cm, d, z, v, pi)
+    rc, xis, Uo = O.pcdl_succinct_check(Cm, d, z, v, _as_oracle_proof(O, pi))
+    assert rc == 0 and np.array_equal(h.xis, xis) and O.pt_eq(U, Uo)
+    # reject paths: same decision and same failing check as the oracle
+    bad = type(pi).from_buffer_copy(bytes(pi))
+    bad.c[0] ^= 1
+    with pytest.raises(pcdl.Rejected) as e:
+        pcdl.check(ctx, Cm, d, z, v, bad)
+    assert e.value.code == O.pcdl_check(Cm, d, z, v, _as_oracle_proof(O, bad)) == -10
+    if n > 2:
+        bad = type(pi).from_buffer_copy(bytes(pi))
+        C.memmove(bad.Ls[1], bytes(pi.Rs[0]), 96)
+        with pytest.raises(pcdl.Rejected) as e:
+            pcdl.check(ctx, Cm, d, z, v, bad)
+        assert e.value.code == O.pcdl_check(Cm, d, z, v, _as_oracle_proof(O, bad)) == -10
+    v_bad = O.random_scalars(1, 77)[0]
+    with pytest.raises(pcdl.Rejected):
+        pcdl.check(ctx, Cm, d, v_bad, v, pi)
+
+
+def test_pcdl_full_check_rejects_wrong_U(env):
+    """pcdl.rs:339: a proof that passes the succinct check but whose U is not <G, h> must fail step 5.  Built by
+    running the honest prover against a context whose generator G_5 was replaced (so its U is consistent with its
+    own L/R but not with the verifier's key)."""
+    ctx, O, pcdl = env["ctx"], env["O"], env["pcdl"]
+    import halo_accumulation_b200 as H
+
+    n, d = 64, 63
+    S, Hh = ctx.get_SH()
+    gs = ctx.get_generators(0, n).copy()
+    gs[5] = ctx.get_generators(1000, 1)[0]
+    other = H.Context(0, 1 << 10)
+    try:
+        other.load_generators(S, Hh, gs)
+        p, z = O.random_scalars(n, 1), O.random_scalars(1, 2)[0]
+        p[5] = 0  # coefficient 5 is zero, so C is the same under both keys ...
+        Cm = pcdl.commit(other, p, d)
+        assert O.pt_eq(Cm, pcdl.commit(ctx, p, d))
+        v = O.scalar_dot(p, O.construct_powers(z, n))
+        pi = pcdl.open(other, p, Cm, d, z)
+        pcdl.check(other, Cm, d, z, v, pi)
+    finally:
+        other.close()
+    # ... but L/R/U were folded with the foreign G_5: whichever check trips, GPU and oracle must agree
+    rc = O.pcdl_check(Cm, d, z, v, _as_oracle_proof(O, pi))
+    assert rc in (-10, -11)
+    with pytest.raises(pcdl.Rejected) as e:
+        pcdl.check(ctx, Cm, d, z, v, pi)
+    assert e.value.code == rc
+
+
+def test_pcdl_argument_errors(env):
+    import halo_accumulation_b200 as H
+
+    ctx, O, pcdl = env["ctx"], env["O"], env["pcdl"]
+    p = O.random_scalars(8, 1)
+    with pytest.raises(H.HaloError):
+        pcdl.commit(ctx, p, 6)            # d + 1 not a power of two (pcdl.rs:102)
+    with pytest.raises(H.HaloError):
+        pcdl.commit(ctx, p, 3)            # degree exceeds d (pcdl.rs:103)
+    with pytest.raises(H.HaloError):
+        pcdl.commit(ctx, p, (1 << 17) - 1)  # d > D (pcdl.rs:104)
+
+
+def _random_instance(env, d, seed):
+    """benches/acc.rs:15-29 / acc.rs:264-278 with explicit draws."""
+    ctx, O, pcdl, acc = env["ctx"], env["O"], env["pcdl"], env["acc"]
+    n = d + 1
+    dp = max(1, n // 2)
+    p = O.random_scalars(dp + 1, seed)
+    w, z, wb = O.random_scalars(3, seed + 1)
+    q = O.random_scalars(dp, seed + 2)
+    Cm = pcdl.commit(ctx, p, d, w)
+    v = O.scalar_dot(p, O.construct_powers(z, dp + 1))
+    pi = pcdl.open(ctx, p, Cm, d, z, w, q, wb)
+    pio = O.pcdl_open(p, O.pcdl_commit(p, d, w), d, z, w, q, wb, threads=8)
+    _same_proof(O, pi, pio)
+    return acc.new_instance(Cm, d, z, v, pi), O.make_instance(Cm, d, z, v, pio)
+
+
+@pytest.mark.parametrize("n,steps", [(4, 3), (16, 4), (1024, 3)])
+def test_acc_chain_matches_oracle(env, n, steps):
+    """test_acc_scheme (acc.rs:298-315): prover + verifier per step, decider at the end; every accumulator field
+    equals the oracle's."""
+    ctx, O, acc = env["ctx"], env["O"], env["acc"]
+    d = n - 1
+    a, ao = None, None
+    for s in range(steps):
+        q, qo = _random_instance(env, d, 500 + 10 * s + n)
+        qs = [acc.to_instance(a), q] if a is not None else [q]
+        qso = [O.acc_to_instance(ao), qo] if ao is not None else [qo]
+        h0, (w, wb), qq = O.random_scalars(2, 900 + s), O.random_scalars(2, 910 + s), O.random_scalars(n - 1, 920 + s)
+        a = acc.prover(ctx, d, qs, h0, w, qq, wb)
+        ao = O.acc_prover(d, qso, h0, w, qq, wb, threads=8)
+        assert O.pt_eq(np.array(a.C_bar), np.array(ao.C_bar))
+        assert (a.d, list(a.z), list(a.v), list(a.w)) == (ao.d, list(ao.z), list(ao.v), list(ao.w))
+        assert O.pt_eq(np.array(a.U0), np.array(ao.U0)) and bytes(a.h0) == bytes(ao.h0)
+        _same_proof(O, a.pi, ao.pi)
+        acc.verifier(ctx, d, qs, a)
+        assert O.acc_verifier(d, qso, ao) == 0
+        # the oracle accepts the GPU accumulator and vice versa
+        assert O.acc_verifier(d, qso, O.Accumulator.from_buffer_copy(bytes(a))) == 0
+        # reject paths agree
+        bad = type(a).from_buffer_copy(bytes(a))
+        bad.v[0] ^= 1
+        with pytest.raises(acc.Rejected) as e:
+            acc.verifier(ctx, d, qs, bad)
+        assert e.value.code == O.acc_verifier(d, qso, O.Accumulator.from_buffer_copy(bytes(bad))) == -17
+        bad = type(a).from_buffer_copy(bytes(a))
+        bad.h0[1][0] ^= 1
+        with pytest.raises(acc.Rejected) as e:
+            acc.verifier(ctx, d, qs, bad)
+        assert e.value.code == O.acc_verifier(d, qso, O.Accumulator.from_buffer_copy(bytes(bad))) == -12
+    acc.decider(ctx, a)
+    assert O.acc_decider(ao, threads=8) == 0
+    bad = type(a).from_buffer_copy(bytes(a))
+    bad.z[0] ^= 1
+    with pytest.raises(acc.Rejected):
+        acc.decider(ctx, bad)
+
+
+def test_open_check_2_16_full_parity(env):
+    ctx, O, pcdl = env["ctx"], env["O"], env["pcdl"]
+    n = 1 << 16
+    d = n - 1
+    p = O.random_scalars(n, 2)
+    z = O.random_scalars(1, 3)[0]
+    Cm = pcdl.commit(ctx, p, d)
+    pi = pcdl.open(ctx, p, Cm, d, z)
+    _same_proof(O, pi, O.pcdl_open(p, Cm, d, z, threads=8))
+    v = O.scalar_dot(p, O.construct_powers(z, n))
+    pcdl.check(ctx, Cm, d, z, v, pi)
