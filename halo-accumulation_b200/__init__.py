@@ -11,11 +11,27 @@ import numpy as np
 from . import _build
 from ._capi import HaloError, arr, load, p64, u8p
 
-__all__ = ["Context", "HaloError", "build"]
+__all__ = ["Context", "HaloError", "build", "points_sum", "points_equal"]
+
+
+def points_sum(points_jac):
+    """Sum of Jacobian points in index order (combining per-GPU partial MSM results)."""
+    pts = arr(points_jac).reshape(-1, 12)
+    out = np.zeros(12, dtype=np.uint64)
+    rc = load().halo_points_sum(p64(pts), C.c_uint64(pts.shape[0]), p64(out))
+    if rc != 0:
+        raise HaloError(rc, "halo_points_sum")
+    return out
 
 
 def build(force=False):
     return _build.build(force=force)
+
+
+def points_equal(a, b):
+    """`==` on Projective: same group element regardless of representation."""
+    a, b = arr(a, (12,)), arr(b, (12,))
+    return bool(load().halo_points_equal(p64(a), p64(b)))
 
 
 class Context:
@@ -49,6 +65,18 @@ class Context:
     # ---- parameters ----
     def derive_generators(self, n):
         self._chk(self._lib.halo_derive_generators(self._h, C.c_uint64(n)))
+
+    def derive_generators_range(self, first, n):
+        """Resident generators become G_first .. G_{first+n-1} (point slice of the sharded MSM)."""
+        self._chk(self._lib.halo_derive_generators_range(self._h, C.c_uint64(first), C.c_uint64(n)))
+
+    def timer_start(self):
+        self._chk(self._lib.halo_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._chk(self._lib.halo_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def load_generators(self, S, H, gs):
         S, H, gs = arr(S, (12,)), arr(H, (12,)), arr(gs).reshape(-1, 8)

@@ -130,7 +130,58 @@ int halo_last_msm_timings(halo_ctx* ctx, float out_ms[6]) {
     return HALO_OK;
 }
 
-int halo_derive_generators(halo_ctx* ctx, uint64_t n) {
+int halo_derive_generators(halo_ctx* ctx, uint64_t n) { return halo_derive_generators_range(ctx, 0, n); }
+
+int halo_points_sum(const uint64_t* points_jac, uint64_t g, uint64_t out_jac[12]) {
+    if (!out_jac || (!points_jac && g)) return HALO_EINVAL;
+    xyzz_t acc;
+    xyzz_set_inf(acc);
+    for (uint64_t i = 0; i < g; i++) {
+        jac_t j;
+        memcpy(&j, points_jac + 12 * i, 96);
+        xyzz_t q;
+        jac_to_xyzz(q, j);
+        xyzz_add(acc, q);
+    }
+    out_jac_from_xyzz(acc, out_jac);
+    return HALO_OK;
+}
+
+int halo_points_equal(const uint64_t a_jac[12], const uint64_t b_jac[12]) {
+    jac_t a, b;
+    memcpy(&a, a_jac, 96);
+    memcpy(&b, b_jac, 96);
+    bool ia = fp_is_zero(a.z), ib = fp_is_zero(b.z);
+    if (ia || ib) return ia && ib;
+    fq_t za2, zb2, l, r;
+    fp_sqr(za2, a.z);
+    fp_sqr(zb2, b.z);
+    fp_mul(l, a.x, zb2);
+    fp_mul(r, b.x, za2);
+    if (!fp_eq(l, r)) return 0;
+    fp_mul(l, a.y, zb2);
+    fp_mul(l, l, b.z);
+    fp_mul(r, b.y, za2);
+    fp_mul(r, r, a.z);
+    return fp_eq(l, r) ? 1 : 0;
+}
+
+int halo_timer_start(halo_ctx* ctx) {
+    if (!ctx) return HALO_EINVAL;
+    HALO_TRY(ctx)
+    HALO_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    HALO_CATCH(ctx)
+}
+int halo_timer_stop(halo_ctx* ctx, float* elapsed_ms) {
+    if (!ctx || !elapsed_ms) return HALO_EINVAL;
+    HALO_TRY(ctx)
+    HALO_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+    HALO_CUDA(cudaEventSynchronize(ctx->ev[7]));
+    HALO_CUDA(cudaEventElapsedTime(elapsed_ms, ctx->ev[6], ctx->ev[7]));
+    HALO_CATCH(ctx)
+}
+
+int halo_derive_generators_range(halo_ctx* ctx, uint64_t first, uint64_t n) {
     if (!ctx) return HALO_EINVAL;
     if (n == 0 || n > ctx->max_n) return fail(ctx, HALO_EINVAL, "halo_derive_generators: n exceeds max_n");
     HALO_TRY(ctx)
@@ -138,7 +189,7 @@ int halo_derive_generators(halo_ctx* ctx, uint64_t n) {
     ctx->gens.reserve(n * sizeof(affine_t));
     ctx->stage_misc.reserve(2 * sizeof(affine_t));
     params_derive_points(ctx, 0, 2, ctx->stage_misc.as<affine_t>());
-    params_derive_points(ctx, 2, n, ctx->gens.as<affine_t>());
+    params_derive_points(ctx, 2 + first, n, ctx->gens.as<affine_t>());
     affine_t sh[2];
     HALO_CUDA(cudaMemcpyAsync(sh, ctx->stage_misc.p, sizeof sh, cudaMemcpyDeviceToHost, ctx->stream));
     HALO_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -62,6 +62,9 @@ int halo_last_msm_timings(halo_ctx *ctx, float out_ms[6]);
 /* K6. Derives S = P_0, H = P_1, G_i = P_{i+2}, i < n, on the device by the rule of main.rs:18-45
  * (P_k = [SHA3-256(genesis || k as u64 LE) mod r] * (-1, 2)) and keeps them resident. */
 int halo_derive_generators(halo_ctx *ctx, uint64_t n);
+/* Point-slice variant for the sharded MSM: S, H as above, resident generators are G_first .. G_{first+n-1}
+ * (rank r of g holds the slice [r n/g, (r+1) n/g); halo_msm_gens offsets are relative to `first`). */
+int halo_derive_generators_range(halo_ctx *ctx, uint64_t first, uint64_t n);
 /* Alternative: take the reference's own constants (consts::S, consts::H as Jacobian, consts::GS affine). */
 int halo_load_generators(halo_ctx *ctx, const uint64_t S_jac[12], const uint64_t H_jac[12],
                          const uint64_t *gs_affine /*[n][8]*/, uint64_t n);
@@ -86,6 +89,15 @@ int halo_msm_jac(halo_ctx *ctx, const uint64_t *bases_jac /*[n][12]*/, const uin
                  uint64_t out_jac[12]);
 /* Device-resident variant for throughput measurement: d_scalars is a CUDA device pointer to n scalars. */
 int halo_msm_gens_resident(halo_ctx *ctx, const void *d_scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]);
+
+/* Sum of g Jacobian points on the host, in index order: combines the per-GPU partial MSM results after the
+ * single all-gather of the sharded MSM. */
+int halo_points_sum(const uint64_t *points_jac /*[g][12]*/, uint64_t g, uint64_t out_jac[12]);
+/* Projective equality of two Jacobian points (cross-multiplied, as `==` on arkworks' Projective): 1 / 0. */
+int halo_points_equal(const uint64_t a_jac[12], const uint64_t b_jac[12]);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of this library is launched on). */
+int halo_timer_start(halo_ctx *ctx);
+int halo_timer_stop(halo_ctx *ctx, float *elapsed_ms);
 
 /* ---- scalar vectors -------------------------------------------------------------------------------- */
 /* sum_i xs[i] * ys[i] in Fr.  Replaces group.rs:13-15 `scalar_dot`. */

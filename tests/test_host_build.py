@@ -1,0 +1,165 @@
+"""CPU tests of the product without a GPU: the shared libraries load, export every symbol the headers declare,
+fail loudly without a device, and the shared field / curve / hash code (compiled as plain C++) agrees with the oracle."""
+import ctypes as C
+import os
+import random
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyref as PR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libs():
+    import halo_accumulation_b200 as H
+
+    H.build()
+    from halo_accumulation_b200 import _capi, _host
+
+    return _capi.load(), _host.lib()
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(halo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_cuda_library_exports_declared_symbols(libs):
+    cuda, host = libs
+    for name in _declared("halo_b200.h") + _declared("halo_b200_test.h"):
+        assert hasattr(cuda, name), f"libhalo_b200.so does not export {name}"
+    for name in _declared("halo_pcdl.h"):
+        assert hasattr(host, name), f"libhalo_host.so does not export {name}"
+
+
+def test_library_contains_sm100a_code():
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "halo-accumulation_b200", "lib", "libhalo_b200.so")],
+                         capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_device(libs):
+    """The product path must fail loudly when no CUDA device is usable."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import halo_accumulation_b200 as H
+
+    with pytest.raises(H.HaloError):
+        H.Context(0, 1024)
+
+
+def test_product_sources_do_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "halo-accumulation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath or "__pycache__" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f in (), f"{f} mentions the oracle"
+
+
+@pytest.fixture(scope="module")
+def hostcheck():
+    """The product's __host__ __device__ headers compiled by g++ (portable 32-bit limb path = the algorithm the
+    device runs; and the 64-bit host path used by the transcript glue)."""
+    d = os.path.join(ROOT, "tests", "hostcheck")
+    libs = {}
+    for tag, flags in (("portable", ["-DHALO_FP_FORCE_PORTABLE"]), ("host64", [])):
+        so = os.path.join(d, f"libhostcheck_{tag}.so")
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", *flags, "-o", so,
+                               os.path.join(d, "hostcheck.cpp")])
+        libs[tag] = C.CDLL(so)
+    return libs
+
+
+def _p32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+@pytest.mark.parametrize("tag", ["portable", "host64"])
+def test_shared_field_core_vs_python(hostcheck, oracle, tag):
+    hc = hostcheck[tag]
+    rnd = random.Random(3)
+    for which, mod in ((0, PR.P), (1, PR.R)):
+        edge = [0, 1, 2, mod - 1, mod - 2, (1 << 256) % mod, (1 << 255) % mod, 0xFFFFFFFF, 1 << 32, (1 << 254) % mod, mod >> 1]
+        vals = edge + [rnd.randrange(mod) for _ in range(150)]
+        rinv = pow(1 << 256, -1, mod)
+        for i, a in enumerate(vals):
+            for b in edge + [vals[(7 * i + 3) % len(vals)]]:
+                A = np.array(oracle.int_to_limbs(a), dtype=np.uint64)
+                B = np.array(oracle.int_to_limbs(b), dtype=np.uint64)
+                r = np.zeros(4, dtype=np.uint64)
+                hc.hc_fp_mul(which, _p32(A), _p32(B), _p32(r))
+                assert oracle.limbs_to_int(r) == a * b * rinv % mod
+                hc.hc_fp_addsub(which, 0, _p32(A), _p32(B), _p32(r))
+                assert oracle.limbs_to_int(r) == (a + b) % mod
+                hc.hc_fp_addsub(which, 1, _p32(A), _p32(B), _p32(r))
+                assert oracle.limbs_to_int(r) == (a - b) % mod
+        for a in vals[1:30]:
+            A = np.array(oracle.int_to_limbs(a), dtype=np.uint64)
+            r = np.zeros(4, dtype=np.uint64)
+            hc.hc_fp_inv(which, _p32(A), _p32(r))
+            assert oracle.limbs_to_int(r) == pow(a, -1, mod) * pow(1 << 256, 2, mod) % mod
+            hc.hc_fp_canon(which, 1, _p32(A), _p32(r))
+            assert oracle.limbs_to_int(r) == a * rinv % mod
+
+
+@pytest.mark.parametrize("tag", ["portable", "host64"])
+def test_shared_group_law_vs_oracle(hostcheck, oracle, tag):
+    hc, O = hostcheck[tag], oracle
+    GS = O.derive_points(2, 32)
+    aff = np.concatenate([GS[:10], GS[3:4], GS[3:4], GS[5:6], np.zeros((1, 8), dtype=np.uint64), GS[:10]])
+    neg = np.zeros(len(aff), dtype=np.uint8)
+    neg[12] = 1
+    neg[-10:] = 1
+    out = np.zeros(12, dtype=np.uint64)
+    hc.hc_madd_chain(_p32(aff), neg.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(len(aff)), _p32(out))
+    exp = None
+    for a, ng in zip(aff, neg):
+        if a.any():
+            x, y = O.from_mont(a.reshape(2, 4), 0)
+            exp = PR.pt_add(exp, (x, (-y) % PR.P if ng else y))
+    assert O.pt_to_affine_ints(out) == exp
+    quad = np.concatenate([GS[:1]] * 4)
+    n4 = np.array([0, 0, 1, 1], dtype=np.uint8)
+    hc.hc_madd_chain(_p32(quad), n4.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(4), _p32(out))
+    assert O.pt_to_affine_ints(out) is None
+    jacs = np.array([O.pt_mul(O.affine_to_jac(GS[i])[0], O.random_scalars(1, i)[0]) for i in range(8)])
+    jacs2 = np.concatenate([jacs, jacs[:1], jacs[2:3]])
+    hc.hc_add_chain(_p32(jacs2), C.c_uint64(len(jacs2)), 3, _p32(out))
+    exp = None
+    for j in jacs2:
+        exp = PR.pt_add(exp, O.pt_to_affine_ints(j))
+    assert O.pt_to_affine_ints(out) == PR.pt_mul(exp, 8)
+    k = O.random_scalars(1, 77)[0]
+    kc = np.zeros(4, dtype=np.uint64)
+    O.lib().orc_fp_to_canon(1, O._p(k), O._p(kc))
+    hc.hc_mul(_p32(jacs[2]), _p32(kc), _p32(out))
+    assert O.pt_eq(out, O.pt_mul(jacs[2], k))
+
+
+def test_host_transcript_serialisation_vs_oracle(libs, oracle):
+    """Host layer's compressed point encoding == oracle's (both restate arkworks' 33-byte form)."""
+    _, host = libs
+    O = oracle
+    GS = O.derive_points(2, 12)
+    pts = [O.affine_to_jac(g)[0] for g in GS] + [O.pt_from_affine_ints(None)]
+    pts.append(O.pt_mul(pts[0], O.random_scalars(1, 1)[0]))
+    for p in pts:
+        out = (C.c_uint8 * 33)()
+        host.halo_point_serialize_compressed(p.ctypes.data_as(C.POINTER(C.c_uint64)), out)
+        assert bytes(out) == O.pt_serialize_compressed(p)
+    # HPoly::eval on the host layer
+    xs, z = O.random_scalars(8, 5), O.random_scalars(1, 6)[0]
+    out = np.zeros(4, dtype=np.uint64)
+    assert host.halo_h_eval(O._p(xs), 7, O._p(z), O._p(out)) == 0
+    assert out.tolist() == O.h_eval(xs, z).tolist()
