@@ -210,8 +210,8 @@ def run_ours(args):
         # integer-pipe peak, measured here: independent IMAD chains on every SM
         sms = torch.cuda.get_device_properties(local).multi_processor_count
         blocks, threads, iters = sms * 8, 256, 4096
-        imad_ms = min(ctx.test_imad_throughput(1, blocks, threads, iters) for _ in range(3))
-        imad_peak = blocks * threads * iters * 16 / imad_ms / 1e9  # T IMAD/s (mad.wide.u32; mad.lo.u32 is the same rate)
+        imad_ms = min(ctx.test_imad_throughput(0, blocks, threads, iters) for _ in range(3))
+        imad_peak = blocks * threads * iters * 16 / imad_ms / 1e9  # T IMAD32/s: dependent-multiplicand mad.lo.u32 chains
         alg_imad = n * CANON_W * 10 * IMAD_PER_MODMUL  # algorithmic IMAD32 of one k_accumulate launch (canonical c = 16)
         achieved = alg_imad / (phases["accumulate"] * 1e-3) / 1e12
         cpu = None
@@ -240,7 +240,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD32/s",
                          "frac": achieved / imad_peak, "traffic": None,
-                         "peak_source": "measured in this run (libhalo_b200 mad.wide.u32 microbenchmark); MEASURED_PEAKS.json has no integer-pipe figure",
+                         "peak_source": "measured in this run (libhalo_b200 mad.lo.u32 microbenchmark, 16 independent chains per thread, all SMs); MEASURED_PEAKS.json has no integer-pipe figure. IMAD.WIDE / IMAD.HI issue at half this rate (profiles/r01_imad_pipe_rates.jsonl)",
                          "algorithmic": f"{n} pts x {CANON_W} windows x 10 modmul x {IMAD_PER_MODMUL} IMAD32 per launch",
                          "launch_ms": phases["accumulate"], "phases_ms": phases,
                          "whole_msm_frac": (n * 160 + 14.68e6) * IMAD_PER_MODMUL / (ms_step * 1e-3) / 1e12 / imad_peak},

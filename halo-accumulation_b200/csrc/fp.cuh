@@ -15,6 +15,7 @@
 
 #if defined(__CUDACC__)
 #define HALO_HD __host__ __device__ __forceinline__
+#include "fp_mul_asm.cuh"
 #else
 #define HALO_HD inline
 #endif
@@ -320,19 +321,41 @@ inline void fp_mul_host64(uint32_t r32[8], const uint32_t a32[8], const uint32_t
 }
 #endif
 
+// Portable 32-bit-limb version (reference semantics of the device algorithm; also what the host check compiles).
 template <class P>
-HALO_HD void fp_mul(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
-#if !defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
-    fp_mul_host64<P>(r.v, a.v, b.v);
-#else
+HALO_HD void fp_mul_portable(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
     uint32_t T[16];
     mul8x8(T, a.v, b.v);
     fp_mont_reduce<P>(r.v, T);
+}
+
+#ifndef HALO_FP_MUL_VARIANT
+#define HALO_FP_MUL_VARIANT 1
+#endif
+
+template <class P>
+HALO_HD void fp_mul(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
+#if defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+    uint32_t o[8];
+    fp_mul_asm<P, HALO_FP_MUL_VARIANT>(o, a.v, b.v);  // generated straight-line PTX, csrc/fp_mul_asm.cuh
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = o[i];
+#elif !defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+    fp_mul_host64<P>(r.v, a.v, b.v);
+#else
+    fp_mul_portable(r, a, b);
 #endif
 }
 template <class P>
 HALO_HD void fp_sqr(fp_t<P>& r, const fp_t<P>& a) {
+#if defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+    uint32_t o[8];
+    fp_sqr_asm<P, HALO_FP_MUL_VARIANT>(o, a.v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = o[i];
+#else
     fp_mul(r, a, a);
+#endif
 }
 
 // Montgomery form <-> canonical integer

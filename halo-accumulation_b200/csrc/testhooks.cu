@@ -50,7 +50,7 @@ __global__ void k_add_chain(const jac_t* pts, uint64_t n, int dbls, jac_t* out) 
     *out = j;
 }
 
-template <int ILP>
+template <int ILP, int V>
 __global__ void __launch_bounds__(512) k_fp_mul_tp(int iters, uint32_t* sink) {
     fq_t x[ILP], y;
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,7 +65,16 @@ __global__ void __launch_bounds__(512) k_fp_mul_tp(int iters, uint32_t* sink) {
     y.v[7] &= 0x0fffffffu;
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int k = 0; k < ILP; k++) fp_mul(x[k], x[k], y);
+        for (int k = 0; k < ILP; k++) {
+            if (V < 0) {
+                fp_mul_portable(x[k], x[k], y);
+            } else {
+                uint32_t o[8];
+                fp_mul_asm<FqParams, (V < 0 ? 0 : V)>(o, x[k].v, y.v);
+#pragma unroll
+                for (int j = 0; j < 8; j++) x[k].v[j] = o[j];
+            }
+        }
     }
     uint32_t acc = 0;
 #pragma unroll
@@ -80,24 +89,62 @@ template <int KIND>
 __global__ void __launch_bounds__(1024) k_imad_tp(int iters, uint32_t* sink) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t a = tid * 2654435761u + 12345u, b = tid ^ 0x9e3779b9u;
-    uint32_t r[16];
+    uint32_t r[16], cnt[8];
     uint64_t w[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         r[k] = tid + k;
         w[k] = tid + 7 * k;
+        cnt[k & 7] = k;
     }
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            if (KIND == 0) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r[k]) : "r"(a), "r"(b));
-            if (KIND == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"(a), "r"(b));
-            if (KIND == 2) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(r[k]) : "r"(a), "r"(b));
+            // the multiplicand is the accumulator itself, so no product is loop invariant (ptxas otherwise hoists a * b and
+            // the loop degenerates into additions)
+            if (KIND == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[k]) : "r"(a), "r"(b));
+            if (KIND == 1) asm volatile("{.reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(w[k]) : "r"(a));
+            if (KIND == 2) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(r[k]) : "r"(a), "r"(b));
+        }
+        if (KIND == 3) {  // 8 independent wide MADs with carry-OUT captured by an ADDC (IMAD.WIDE P-out + IADD3.X)
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                             : "+r"(r[2 * k]), "+r"(r[2 * k + 1]), "+r"(cnt[k]) : "r"(a), "r"(b));
+        }
+        if (KIND == 4) {  // 2 independent carry chains of 4 fused pairs each (IMAD.WIDE.X with carry in and out)
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+                asm volatile("mad.lo.cc.u32 %0, %9, %10, %0;\n\tmadc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+                             "madc.lo.cc.u32 %2, %9, %10, %2;\n\tmadc.hi.cc.u32 %3, %9, %10, %3;\n\t"
+                             "madc.lo.cc.u32 %4, %9, %10, %4;\n\tmadc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+                             "madc.lo.cc.u32 %6, %9, %10, %6;\n\tmadc.hi.cc.u32 %7, %9, %10, %7;\n\t"
+                             "addc.u32 %8, %8, 0;"
+                             : "+r"(r[8 * k]), "+r"(r[8 * k + 1]), "+r"(r[8 * k + 2]), "+r"(r[8 * k + 3]), "+r"(r[8 * k + 4]),
+                               "+r"(r[8 * k + 5]), "+r"(r[8 * k + 6]), "+r"(r[8 * k + 7]), "+r"(cnt[k])
+                             : "r"(a), "r"(b));
+        }
+        if (KIND == 5) {  // 8 independent fused pairs, no carry in or out (plain IMAD.WIDE through the .cc idiom)
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+                             : "+r"(r[2 * k]), "+r"(r[2 * k + 1]) : "r"(a), "r"(b));
+        }
+        if (KIND == 6) {  // 8 independent wide MADs with carry-IN only (ADD.CC feeding IMAD.WIDE.X, no carry out)
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                asm volatile("add.cc.u32 %2, %2, %3;\n\tmadc.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.u32 %1, %3, %4, %1;"
+                             : "+r"(r[2 * k]), "+r"(r[2 * k + 1]), "+r"(cnt[k]) : "r"(a), "r"(b));
+        }
+        if (KIND == 7) {  // 16 independent 3-input adds with carry chains of length 2 (ALU pipe reference)
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(r[2 * k]), "+r"(r[2 * k + 1]) : "r"(a), "r"(b));
         }
     }
     uint32_t acc = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) acc ^= r[k] ^ (uint32_t)w[k] ^ (uint32_t)(w[k] >> 32);
+    for (int k = 0; k < 16; k++) acc ^= r[k] ^ (uint32_t)w[k] ^ (uint32_t)(w[k] >> 32) ^ cnt[k & 7];
     if (acc == 0x12345678u) sink[0] = acc;
     if (tid == 0) sink[1] = acc;
 }
@@ -190,9 +237,12 @@ int halo_test_fp_mul_throughput(halo_ctx* ctx, int blocks, int threads, int iter
     HALO_CUDA(cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; rep++) {
         HALO_CUDA(cudaEventRecord(e0, ctx->stream));
-        if (ilp == 1) k_fp_mul_tp<1><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
-        else if (ilp == 2) k_fp_mul_tp<2><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
-        else k_fp_mul_tp<4><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        // ilp encodes (ilp, variant): ilp % 10 = independent chains per thread, ilp / 10 = variant + 1 (0 = portable C++)
+        int var = ilp / 10 - 1, il = ilp % 10;
+#define TP(I, V) k_fp_mul_tp<I, V><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>())
+        if (il == 1) { if (var < 0) TP(1, -1); else if (var == 0) TP(1, 0); else if (var == 1) TP(1, 1); else if (var == 2) TP(1, 2); else TP(1, 3); }
+        else { if (var < 0) TP(2, -1); else if (var == 0) TP(2, 0); else if (var == 1) TP(2, 1); else if (var == 2) TP(2, 2); else TP(2, 3); }
+#undef TP
         HALO_CUDA(cudaEventRecord(e1, ctx->stream));
         HALO_CUDA(cudaStreamSynchronize(ctx->stream));
     }
@@ -220,7 +270,12 @@ int halo_test_imad_throughput(halo_ctx* ctx, int kind, int blocks, int threads, 
         HALO_CUDA(cudaEventRecord(e0, ctx->stream));
         if (kind == 0) k_imad_tp<0><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
         else if (kind == 1) k_imad_tp<1><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
-        else k_imad_tp<2><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else if (kind == 2) k_imad_tp<2><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else if (kind == 3) k_imad_tp<3><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else if (kind == 4) k_imad_tp<4><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else if (kind == 5) k_imad_tp<5><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else if (kind == 6) k_imad_tp<6><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
+        else k_imad_tp<7><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>());
         HALO_CUDA(cudaEventRecord(e1, ctx->stream));
         HALO_CUDA(cudaStreamSynchronize(ctx->stream));
     }

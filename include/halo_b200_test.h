@@ -20,8 +20,9 @@ int halo_test_add_chain(halo_ctx *ctx, const uint64_t *jac /*[n][12]*/, uint64_t
 /* Modular-multiplication throughput microbenchmark (K1): `iters` dependent Fq multiplications per thread
  * on blocks x threads threads; returns elapsed ms and a checksum limb. */
 int halo_test_fp_mul_throughput(halo_ctx *ctx, int blocks, int threads, int iters, int ilp, float *ms, uint64_t *checksum);
-/* Integer-pipe peak microbenchmark: independent IMAD chains; kind 0 = mad.lo.u32, 1 = mad.wide.u32,
- * 2 = mad.hi.u32.  Returns elapsed ms; ops = blocks * threads * iters * 16. */
+/* Integer-pipe peak microbenchmark: 16 independent multiply-add chains per thread whose multiplicand is the running
+ * accumulator (nothing is loop invariant).  kind 0 = mad.lo.u32 (IMAD), 1 = mad.wide.u32 (IMAD.WIDE), 2 = mad.hi.u32
+ * (IMAD.HI): ops = blocks * threads * iters * 16.  kinds 3-7: carry-chain forms, 8 (7: 16) ops per iteration. */
 int halo_test_imad_throughput(halo_ctx *ctx, int kind, int blocks, int threads, int iters, float *ms, uint64_t *checksum);
 #ifdef __cplusplus
 }
