@@ -70,6 +70,13 @@ class Context:
         """Resident generators become G_first .. G_{first+n-1} (point slice of the sharded MSM)."""
         self._chk(self._lib.halo_derive_generators_range(self._h, C.c_uint64(first), C.c_uint64(n)))
 
+    def precompute_generators(self, c=0):
+        """FIXED-base tables for the resident generators (optional accelerator; same results)."""
+        self._chk(self._lib.halo_precompute_generators(self._h, int(c)))
+
+    def set_fixed_base(self, on):
+        self._chk(self._lib.halo_set_fixed_base(self._h, int(bool(on))))
+
     def timer_start(self):
         self._chk(self._lib.halo_timer_start(self._h))
 

@@ -91,6 +91,7 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->gens.release();
     ctx->fixed_table.release();
+    ctx->gens_pre.release();
     ctx->stage_scalars.release();
     ctx->stage_bases.release();
     ctx->stage_misc.release();
@@ -197,7 +198,23 @@ int halo_derive_generators_range(halo_ctx* ctx, uint64_t first, uint64_t n) {
     ctx->H = sh[1];
     ctx->have_SH = true;
     ctx->n_gens = n;
+    ctx->pre_n = 0;  // tables of precomputed multiples are stale
     HALO_CATCH(ctx)
+}
+
+int halo_precompute_generators(halo_ctx* ctx, int c) {
+    if (!ctx) return HALO_EINVAL;
+    if (ctx->n_gens == 0) return fail(ctx, HALO_ESTATE, "halo_precompute_generators: no generators resident");
+    if (c != 0 && (c < 8 || c > 24)) return fail(ctx, HALO_EINVAL, "halo_precompute_generators: window must be 0 (auto) or 8..24");
+    HALO_TRY(ctx)
+    msm_precompute_tables(ctx, c);
+    HALO_CATCH(ctx)
+}
+
+int halo_set_fixed_base(halo_ctx* ctx, int on) {
+    if (!ctx) return HALO_EINVAL;
+    ctx->use_fixed = on != 0;
+    return HALO_OK;
 }
 
 int halo_load_generators(halo_ctx* ctx, const uint64_t S_jac[12], const uint64_t H_jac[12], const uint64_t* gs_affine,
@@ -220,6 +237,7 @@ int halo_load_generators(halo_ctx* ctx, const uint64_t S_jac[12], const uint64_t
         ctx->have_SH = true;
     }
     ctx->n_gens = n;
+    ctx->pre_n = 0;
     HALO_CATCH(ctx)
 }
 
@@ -258,7 +276,7 @@ int halo_msm_gens_resident(halo_ctx* ctx, const void* d_scalars, uint64_t off, u
     if (off + n > ctx->n_gens) return fail(ctx, HALO_ESTATE, "halo_msm_gens: range exceeds resident generators");
     HALO_TRY(ctx)
     xyzz_t r;
-    msm_device(ctx, ctx->gens.as<affine_t>() + off, reinterpret_cast<const fr_t*>(d_scalars), n, r);
+    msm_gens_device(ctx, reinterpret_cast<const fr_t*>(d_scalars), off, n, r);
     out_jac_from_xyzz(r, out_jac);
     HALO_CATCH(ctx)
 }
@@ -270,7 +288,7 @@ int halo_msm_gens(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t
     ctx->stage_scalars.reserve((n ? n : 1) * sizeof(fr_t));
     if (n) HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
     xyzz_t r;
-    msm_device(ctx, ctx->gens.as<affine_t>() + off, ctx->stage_scalars.as<fr_t>(), n, r);
+    msm_gens_device(ctx, ctx->stage_scalars.as<fr_t>(), off, n, r);
     out_jac_from_xyzz(r, out_jac);
     HALO_CATCH(ctx)
 }
@@ -383,7 +401,7 @@ int halo_h_msm(halo_ctx* ctx, const uint64_t* xis, uint32_t lg_n, uint64_t out_j
     fp_one(one);
     vec_h_expand(ctx, reinterpret_cast<const fr_t*>(xis), (int)lg_n, one, false, ctx->stage_scalars.as<fr_t>());
     xyzz_t r;
-    msm_device(ctx, ctx->gens.as<affine_t>(), ctx->stage_scalars.as<fr_t>(), n, r);
+    msm_gens_device(ctx, ctx->stage_scalars.as<fr_t>(), 0, n, r);
     out_jac_from_xyzz(r, out_jac);
     HALO_CATCH(ctx)
 }

@@ -69,8 +69,12 @@ struct MsmPlan {
     int c = 0;
     int W = 0;
     uint32_t M = 0;
-    uint32_t NB = 0;  // W * M
+    uint32_t NB = 0;  // W * M (variable base) or M (fixed base: one shared bucket set)
+    bool fixed = false;
     MsmWidths widths;
+    // bucket reduction geometry: slabs of red_T << red_log_s buckets
+    int red_T = 0, red_log_s = 0;
+    uint32_t red_slabs = 0;
 };
 MsmPlan msm_make_plan(uint64_t n, int force_c);
 
@@ -96,6 +100,10 @@ struct halo_ctx {
     halo::affine_t S, H;
     bool have_SH = false;
     halo::DevBuf fixed_table;  // fixed-base table for generator derivation (K6)
+    halo::DevBuf gens_pre;     // precomputed multiples 2^(off_w) G_i for the FIXED-base MSM
+    halo::MsmPlan pre_plan;
+    uint64_t pre_n = 0;
+    bool use_fixed = true;
     // scratch
     halo::MsmWorkspace ws;
     halo::DevBuf stage_scalars, stage_bases, stage_misc;

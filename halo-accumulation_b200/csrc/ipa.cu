@@ -152,7 +152,7 @@ int halo_ipa_blind_commit(halo_ipa* st, const uint64_t* q, uint64_t n_q, uint64_
     HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, q, n_q * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
     vec_pbar(ctx, ctx->stage_scalars.as<fr_t>(), n_q, st->z, st->n, st->pbar.as<fr_t>());
     xyzz_t r;
-    msm_device(ctx, ctx->gens.as<affine_t>(), st->pbar.as<fr_t>(), st->n, r);  // commit(p_bar) without the w_bar S term
+    msm_gens_device(ctx, st->pbar.as<fr_t>(), 0, st->n, r);  // commit(p_bar) without the w_bar S term
     jac_t j;
     xyzz_to_jac(j, r);
     memcpy(out_jac, &j, 96);

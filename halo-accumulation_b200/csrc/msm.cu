@@ -6,8 +6,13 @@
 //   2. exclusive scan    bucket offsets
 //   3. k_digits<SCATTER> counting-sort scatter of (point index | sign) into bucket order
 //   4. k_accumulate      one thread per bucket: XYZZ accumulator in registers, mixed adds of gathered bases
-//   5. k_bucket_reduce   one CTA per window: running sums + block suffix scan -> sum_k k * B_k
-//   6. host              Horner over the W window sums (255 doublings; O(1) in n) and Jacobian output
+//   5. k_reduce_slabs    bucket reduction sum_k k * B_k: CTAs over slabs of buckets (running sums + block suffix scan),
+//                        then one CTA per window over the slab partials
+//   6. host              slab recombination and Horner over the window sums (O(255) doublings, independent of n)
+// Two modes.  VARIABLE base (halo_msm, IPA rounds): W windows, W bucket sets.  FIXED base (resident generators with
+// precomputed multiples 2^(off_w) G_i, halo_precompute_generators): every window's digit indexes ONE shared bucket set
+// and selects the precomputed multiple instead, so the bucket reduction and the Horner doublings are paid once, not W
+// times, and the window can be as wide as the bucket memory allows.
 // Integer pipe bound (IMAD); see DESIGN.md for the roofline accounting.
 #include "common.cuh"
 #include "msm.cuh"
@@ -17,42 +22,65 @@ namespace halo {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-MsmPlan msm_make_plan(uint64_t n, int force_c) {
-    int best_c = 4;
-    double best = 1e300;
-    for (int c = 4; c <= 17; c++) {
-        int W = 255 / c + 1;
-        double M = (double)(1u << (c - 1)) * (255.0 / (W * c) > 0.97 ? 1.0 : 0.75);  // narrower windows use half their slots
-        // bucket accumulation (10 modmul per mixed add) + bucket reduction (2 full adds per bucket, poorly
-        // parallel -> weighted) ; tuned on B200, see profiles/
-        double cost = (double)W * ((double)n * 10.0 + M * 28.0 * 6.0);
-        if (cost < best) {
-            best = cost;
-            best_c = c;
-        }
-    }
-    int c = force_c ? force_c : best_c;
-    if (c < 4) c = 4;  // W = 255 / c + 1 <= MSM_MAX_WINDOWS
-    if (c > 20) c = 20;
-    MsmPlan p;
+static void plan_fill(MsmPlan& p, int c, bool fixed) {
     p.c = c;
+    p.fixed = fixed;
     p.W = 255 / c + 1;  // c * W >= 256 > 255: the top window absorbs the final carry
     p.M = 1u << (c - 1);
-    p.NB = (uint32_t)p.W * p.M;
+    p.NB = fixed ? p.M : (uint32_t)p.W * p.M;
     // near-equal widths summing to 255; the low windows take the remainder so the top window is the narrow one
     int base = 255 / p.W, rem = 255 - base * p.W;
     for (int w = 0; w < MSM_MAX_WINDOWS; w++) p.widths.w[w] = w < p.W ? (uint8_t)(base + (w < rem ? 1 : 0)) : 0;
+    // bucket reduction geometry: slabs of T * s buckets, T threads per CTA
+    p.red_T = p.M < 256u ? (int)p.M : 256;
+    p.red_log_s = 0;
+    while (((uint32_t)p.red_T << p.red_log_s) < p.M && p.red_log_s < 3) p.red_log_s++;
+    p.red_slabs = p.M / ((uint32_t)p.red_T << p.red_log_s);
+}
+
+static int ceil_lg(uint64_t n) {
+    int l = 0;
+    while (((uint64_t)1 << l) < n) l++;
+    return l;
+}
+
+// Window widths below are the measured optima on B200 (scripts/gpu_msm_probe.py sweeps, profiles/r01_msm_window_sweep.txt):
+// total cost = W * (n mixed adds) + bucket reduction (2 full adds per bucket, latency bound when thinly filled).
+MsmPlan msm_make_plan(uint64_t n, int force_c) {
+    const int lg = ceil_lg(n);
+    int c = lg <= 6 ? 4 : lg <= 8 ? 6 : lg <= 10 ? 8 : lg <= 12 ? 10 : lg <= 14 ? 13 : lg <= 18 ? 14 : lg <= 20 ? 15 : 16;
+    if (force_c) c = force_c;
+    if (c < 4) c = 4;  // W = 255 / c + 1 <= MSM_MAX_WINDOWS
+    if (c > 20) c = 20;
+    MsmPlan p;
+    plan_fill(p, c, false);
+    return p;
+}
+
+// Fixed-base plan for `n` resident generators: one bucket set, W precomputed multiples per generator.
+MsmPlan msm_make_fixed_plan(uint64_t n, int force_c) {
+    const int lg = ceil_lg(n);
+    int c = lg <= 17 ? 16 : lg <= 22 ? 19 : 20;
+    if (force_c) c = force_c;
+    if (c < 8) c = 8;
+    if (c > 24) c = 24;
+    while ((double)(255 / c + 1) * (double)n >= 2147483648.0 && c < 24) c++;  // entry = index | sign << 31
+    MsmPlan p;
+    plan_fill(p, c, true);
     return p;
 }
 
 // ------------------------------------------------------------------------------------------------
 // 1/3. digit extraction: count or scatter
 // ------------------------------------------------------------------------------------------------
+// VARIABLE: bucket = w * M + |d| - 1, entry = i.   FIXED: bucket = |d| - 1, entry = w * stride + first + i (the index of
+// the precomputed multiple 2^(off_w) G_{first+i}).
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars, uint32_t n,
                                                 const fr_t* __restrict__ tail_scalars, uint32_t n_tail, const MsmWidths widths,
-                                                int W, uint32_t M, uint32_t* __restrict__ counts,
-                                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
+                                                int W, uint32_t M, uint32_t fixed_stride, uint32_t fixed_first,
+                                                uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                uint32_t* __restrict__ entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n + n_tail) return;
     fr_t s = i < n ? scalars[i] : tail_scalars[i - n];
@@ -73,9 +101,12 @@ __global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars
             carry = 1;
         }
         if (d != 0) {
-            uint32_t b = (uint32_t)w * M + (d - 1);
+            uint32_t b = fixed_stride ? (d - 1) : (uint32_t)w * M + (d - 1);
             uint32_t slot = atomicAdd(&counts[b], 1u);
-            if (SCATTER) entries[offsets[b] + slot] = i | (neg << 31);
+            if (SCATTER) {
+                uint32_t idx = fixed_stride ? (uint32_t)w * fixed_stride + fixed_first + i : i;
+                entries[offsets[b] + slot] = idx | (neg << 31);
+            }
         }
     }
 }
@@ -174,11 +205,14 @@ static void exclusive_scan(const uint32_t* counts, uint32_t* offsets, uint32_t n
 // ------------------------------------------------------------------------------------------------
 // 4. bucket accumulation: one thread per bucket, accumulator in registers
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__ bases, uint32_t n,
-                                                    const affine_t* __restrict__ tail_bases,
-                                                    const uint32_t* __restrict__ offsets,
-                                                    const uint32_t* __restrict__ entries, uint32_t NB,
-                                                    xyzz_t* __restrict__ buckets) {
+#ifndef HALO_ACC_MIN_BLOCKS
+#define HALO_ACC_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate(const affine_t* __restrict__ bases, uint32_t n,
+                                                                         const affine_t* __restrict__ tail_bases,
+                                                                         const uint32_t* __restrict__ offsets,
+                                                                         const uint32_t* __restrict__ entries, uint32_t NB,
+                                                                         xyzz_t* __restrict__ buckets) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= NB) return;
     uint32_t beg = offsets[b], end = offsets[b + 1];
@@ -194,93 +228,144 @@ __global__ void __launch_bounds__(128) k_accumulate(const affine_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// 5. bucket reduction: one CTA per window computes S_w = sum_{k=1..M} k * B_{w,k-1}
+// 5. bucket reduction.  For a slab of T * s items Q_t (s = 2^log_s per thread) a CTA of T threads produces
+//      A = sum_t (t + 1) Q_t ,   R = sum_t Q_t ,   E = sum_t X_t  (plain sum of a second array, optional)
+//    by per-thread running sums, a block-wide suffix scan of the per-thread totals and tree sums.
+//    Level 1: grid (slabs, windows) over the buckets -> (A_g, R_g) per slab g.
+//    Level 2 (slabs > 1): one CTA per window over Q = R_g, X = A_g -> (A2, R2, E).
+//    Window sum  S = sum_k (k+1) B_k = sum_g A_g + slab * sum_g g R_g = E + slab * (A2 - R2)      [host, msm_finish_host]
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q) { xyzz_add(acc, q); }
 __device__ __noinline__ void xyzz_dbl_nl(xyzz_t& acc) { xyzz_dbl(acc, acc); }
 
-constexpr int REDUCE_THREADS = 512;
+constexpr int REDUCE_THREADS = 256;
 
-__global__ void __launch_bounds__(REDUCE_THREADS) k_bucket_reduce(const xyzz_t* __restrict__ buckets, uint32_t M, int T,
-                                                                  int log_s, xyzz_t* __restrict__ wsums) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    xyzz_t* sm = reinterpret_cast<xyzz_t*>(smem_raw);
+__device__ __forceinline__ void block_tree_sum(xyzz_t& v, xyzz_t* sm, int T) {
     const int j = threadIdx.x;
-    const uint32_t s = 1u << log_s;  // buckets per thread; T * s == M
-    const xyzz_t* B = buckets + (size_t)blockIdx.x * M + (size_t)j * s;
-    // running sums from the top: R = sum B_t, A = sum (t + 1) * B_t
+    sm[j] = v;
+    __syncthreads();
+    for (int stride = T >> 1; stride >= 1; stride >>= 1) {
+        if (j < stride) {
+            xyzz_t other = sm[j + stride];
+            xyzz_add_nl(v, other);
+            sm[j] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(REDUCE_THREADS) k_reduce_slabs(const xyzz_t* __restrict__ in, const xyzz_t* __restrict__ extra,
+                                                                 size_t in_stride, int T, int log_s,
+                                                                 xyzz_t* __restrict__ outA, xyzz_t* __restrict__ outR,
+                                                                 xyzz_t* __restrict__ outE, int out_stride) {
+    __shared__ xyzz_t sm[REDUCE_THREADS];
+    const int j = threadIdx.x;
+    const uint32_t s = 1u << log_s;
+    const size_t base = (size_t)blockIdx.y * in_stride + (((size_t)blockIdx.x * T + j) << log_s);
+    const xyzz_t* Q = in + base;
+    // running sums from the top: R = sum Q_t, A = sum (t + 1) Q_t over this thread's s items
     xyzz_t R, A;
     xyzz_set_inf(R);
     xyzz_set_inf(A);
     for (int t = (int)s - 1; t >= 0; t--) {
-        xyzz_t q = B[t];
+        xyzz_t q = Q[t];
         xyzz_add_nl(R, q);
         xyzz_add_nl(A, R);
     }
     // inclusive suffix scan of R over the CTA: Suf_j = sum_{i >= j} R_i
-    sm[j] = R;
+    xyzz_t Suf = R;
+    sm[j] = Suf;
     __syncthreads();
     for (int stride = 1; stride < T; stride <<= 1) {
         bool has = j + stride < T;
         xyzz_t other;
         if (has) other = sm[j + stride];
         __syncthreads();
-        if (has) xyzz_add_nl(R, other);
-        sm[j] = R;
+        if (has) xyzz_add_nl(Suf, other);
+        sm[j] = Suf;
         __syncthreads();
     }
-    // sum_{j >= 1} Suf_j = sum_j j * R_j  -> tree sum (thread 0 contributes nothing)
-    if (j == 0) xyzz_set_inf(R);
-    sm[j] = R;
+    xyzz_t total = sm[0];  // sum of all R_j
     __syncthreads();
-    for (int stride = T >> 1; stride >= 1; stride >>= 1) {
-        if (j < stride) {
-            xyzz_t other = sm[j + stride];
-            xyzz_add_nl(R, other);
-            sm[j] = R;
-        }
-        __syncthreads();
-    }
-    // R (thread 0) = sum_j j * R_j ; scale by s = 2^log_s
+    // sum_{j >= 1} Suf_j = sum_j j R_j: thread j's items carry the extra weight j * s
+    if (j == 0) xyzz_set_inf(Suf);
+    block_tree_sum(Suf, sm, T);
     if (j == 0)
-        for (int t = 0; t < log_s; t++) xyzz_dbl_nl(R);
-    __syncthreads();
-    // tree sum of A_j
-    sm[j] = A;
-    __syncthreads();
-    for (int stride = T >> 1; stride >= 1; stride >>= 1) {
-        if (j < stride) {
-            xyzz_t other = sm[j + stride];
-            xyzz_add_nl(A, other);
-            sm[j] = A;
-        }
-        __syncthreads();
-    }
+        for (int t = 0; t < log_s; t++) xyzz_dbl_nl(Suf);
+    block_tree_sum(A, sm, T);
+    const size_t o = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * out_stride;
     if (j == 0) {
-        xyzz_add_nl(A, R);
-        wsums[blockIdx.x] = A;
+        xyzz_add_nl(A, Suf);
+        outA[o] = A;
+        outR[o] = total;
     }
+    if (extra) {
+        xyzz_t e;
+        xyzz_set_inf(e);
+        for (uint32_t t = 0; t < s; t++) {
+            xyzz_t q = extra[base + t];
+            xyzz_add_nl(e, q);
+        }
+        block_tree_sum(e, sm, T);
+        if (j == 0) outE[o] = e;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-base tables: table[w * n + i] = 2^(off_w) * G_i (affine), w = 0 .. W-1, off_w = sum of the lower window widths
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_precompute(const affine_t* __restrict__ gens, uint32_t n, const MsmWidths widths, int W,
+                                                    affine_t* __restrict__ table) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t g = gens[i];
+    table[i] = g;
+    xyzz_t p;
+    xyzz_from_affine(p, g);
+    for (int w = 1; w < W; w++) {
+        const int c = widths.w[w - 1];
+        for (int k = 0; k < c; k++) xyzz_dbl_nl(p);
+        affine_t a;
+        xyzz_to_affine(a, p);
+        table[(size_t)w * n + i] = a;
+        xyzz_from_affine(p, a);
+    }
+}
+
+void msm_precompute_tables(halo_ctx* ctx, int force_c) {
+    if (ctx->n_gens == 0) throw CudaError{cudaErrorInvalidValue, "precompute: no generators", __FILE__, __LINE__};
+    MsmPlan plan = msm_make_fixed_plan(ctx->n_gens, force_c);
+    uint32_t n = (uint32_t)ctx->n_gens;
+    ctx->gens_pre.reserve((size_t)plan.W * n * sizeof(affine_t));
+    k_precompute<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->gens.as<affine_t>(), n, plan.widths, plan.W,
+                                                          ctx->gens_pre.as<affine_t>());
+    ctx->kernel_launches++;
+    HALO_CUDA(cudaGetLastError());
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->pre_plan = plan;
+    ctx->pre_n = n;
 }
 
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
-static inline bool is_pow2_u32(uint32_t x) { return x && !(x & (x - 1)); }
-
-void msm_window_sums(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_wsums_out) {
-    const affine_t* d_bases = in.bases;
-    const fr_t* d_scalars = in.scalars;
+// Device part of one MSM.  d_out receives 3 points per window (one "window" in FIXED mode): [E, A2, R2] with
+// window sum S = E + slab * (A2 - R2); a single-slab plan writes S into E and leaves A2 = R2 = infinity.
+void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out) {
     const uint32_t n = in.n;
     const uint32_t ntot = in.n + in.n_tail;
     MsmWorkspace& ws = ctx->ws;
     cudaStream_t st = ctx->stream;
     const uint32_t NB = plan.NB;
+    const int nwin = plan.fixed ? 1 : plan.W;
     ws.counts.reserve((size_t)(NB + 1) * 4);
     ws.offsets.reserve((size_t)(NB + 1) * 4);
     ws.entries.reserve((size_t)ntot * plan.W * 4);
     ws.buckets.reserve((size_t)NB * sizeof(xyzz_t));
     ws.scan_tmp.reserve(4096 * 4);
+    ws.task_partial.reserve((size_t)(2 * plan.red_slabs + 3) * nwin * sizeof(xyzz_t));
     if ((NB + SCAN_TILE - 1) / SCAN_TILE > 2048) throw CudaError{cudaErrorInvalidValue, "bucket count too large for scan", __FILE__, __LINE__};
+    if (plan.red_slabs > (uint32_t)REDUCE_THREADS * 16) throw CudaError{cudaErrorInvalidValue, "too many reduction slabs", __FILE__, __LINE__};
 
     uint32_t* counts = ws.counts.as<uint32_t>();
     uint32_t* offsets = ws.offsets.as<uint32_t>();
@@ -290,38 +375,64 @@ void msm_window_sums(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyz
     auto mark = [&](int i) {
         if (prof) HALO_CUDA(cudaEventRecord(ctx->ev[i], st));
     };
+    const uint32_t fstride = plan.fixed ? in.fixed_stride : 0;
 
     mark(0);
     HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, st));
     const int TPB = 256;
     uint32_t grid = (ntot + TPB - 1) / TPB;
-    k_digits<false><<<grid, TPB, 0, st>>>(d_scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, counts, nullptr, nullptr);
+    k_digits<false><<<grid, TPB, 0, st>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
+                                          in.fixed_first, counts, nullptr, nullptr);
     mark(1);
     exclusive_scan(counts, offsets, NB, ws.scan_tmp.as<uint32_t>(), st, &ctx->kernel_launches);
     HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, st));
     mark(2);
-    k_digits<true><<<grid, TPB, 0, st>>>(d_scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, counts, offsets, entries);
+    k_digits<true><<<grid, TPB, 0, st>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
+                                         in.fixed_first, counts, offsets, entries);
     mark(3);
-    k_accumulate<<<(NB + 127) / 128, 128, 0, st>>>(d_bases, n, in.tail_bases, offsets, entries, NB, buckets);
+    // FIXED: every entry indexes the table, there is no tail
+    k_accumulate<<<(NB + 127) / 128, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, offsets, entries, NB,
+                                                   buckets);
     mark(4);
-    int T = plan.M < (uint32_t)REDUCE_THREADS ? (int)plan.M : REDUCE_THREADS;
-    int log_s = 0;
-    while (((uint32_t)T << log_s) < plan.M) log_s++;
-    size_t smem = (size_t)T * sizeof(xyzz_t);
-    HALO_CUDA(cudaFuncSetAttribute(k_bucket_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   REDUCE_THREADS * (int)sizeof(xyzz_t)));
-    k_bucket_reduce<<<plan.W, T, smem, st>>>(buckets, plan.M, T, log_s, d_wsums_out);
+    HALO_CUDA(cudaMemsetAsync(d_out, 0, (size_t)3 * nwin * sizeof(xyzz_t), st));
+    if (plan.red_slabs == 1) {
+        // A is the window sum; R goes to scratch
+        k_reduce_slabs<<<dim3(1, nwin), plan.red_T, 0, st>>>(buckets, nullptr, plan.M, plan.red_T, plan.red_log_s, d_out,
+                                                             ws.task_partial.as<xyzz_t>(), nullptr, 3);
+        // (R lands at stride 3 in scratch; reserve enough)
+        ctx->kernel_launches += 1;
+    } else {
+        xyzz_t* slabA = ws.task_partial.as<xyzz_t>();
+        xyzz_t* slabR = slabA + (size_t)nwin * plan.red_slabs;
+        k_reduce_slabs<<<dim3(plan.red_slabs, nwin), plan.red_T, 0, st>>>(buckets, nullptr, plan.M, plan.red_T, plan.red_log_s,
+                                                                           slabA, slabR, nullptr, 1);
+        int T2 = plan.red_slabs < (uint32_t)REDUCE_THREADS ? (int)plan.red_slabs : REDUCE_THREADS;
+        int log_s2 = 0;
+        while (((uint32_t)T2 << log_s2) < plan.red_slabs) log_s2++;
+        k_reduce_slabs<<<dim3(1, nwin), T2, 0, st>>>(slabR, slabA, plan.red_slabs, T2, log_s2, d_out + 1, d_out + 2, d_out, 3);
+        ctx->kernel_launches += 2;
+    }
     mark(5);
-    ctx->kernel_launches += 4;
+    ctx->kernel_launches += 3;
     HALO_CUDA(cudaGetLastError());
 }
 
-// Horner over window sums (host, O(255) doublings independent of n): total = sum_w 2^(c w) S_w
-void msm_finish_host(const xyzz_t* wsums, const MsmPlan& plan, xyzz_t& out) {
+// Host finish: per window S = E + slab * (A2 - R2), then Horner over the windows (a single term in FIXED mode).
+void msm_finish_host(const xyzz_t* parts, const MsmPlan& plan, xyzz_t& out) {
+    const int nwin = plan.fixed ? 1 : plan.W;
+    const int log_slab = plan.red_log_s + (plan.red_T > 1 ? 31 - __builtin_clz((unsigned)plan.red_T) : 0);
     xyzz_t total;
     xyzz_set_inf(total);
-    for (int w = plan.W - 1; w >= 0; w--) {
-        xyzz_add(total, wsums[w]);
+    for (int w = nwin - 1; w >= 0; w--) {
+        xyzz_t S = parts[3 * w];
+        if (plan.red_slabs > 1) {
+            xyzz_t d = parts[3 * w + 2];
+            if (!xyzz_is_inf(d)) xyzz_neg(d);
+            xyzz_add(d, parts[3 * w + 1]);
+            for (int k = 0; k < log_slab; k++) xyzz_dbl(d, d);
+            xyzz_add(S, d);
+        }
+        xyzz_add(total, S);
         if (w > 0)
             for (int k = 0; k < plan.widths.w[w - 1]; k++) xyzz_dbl(total, total);
     }
@@ -329,24 +440,26 @@ void msm_finish_host(const xyzz_t* wsums, const MsmPlan& plan, xyzz_t& out) {
 }
 
 // Enqueue `count` MSMs back to back on the context stream (they share the workspace, so they serialise on the
-// stream), then one D2H of all window sums, one synchronisation, and the host Horner per MSM.
+// stream), then one D2H of all partial sums, one synchronisation, and the host finish per MSM.
 void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs) {
-    if (count > 4) throw CudaError{cudaErrorInvalidValue, "msm_batch: count > 4", __FILE__, __LINE__};
-    MsmPlan plans[4];
-    ctx->ws.wsums.reserve(4 * MSM_MAX_WINDOWS * sizeof(xyzz_t));
-    xyzz_t* d_wsums = ctx->ws.wsums.as<xyzz_t>();
+    constexpr int MAXB = 4, SLOT = 3 * MSM_MAX_WINDOWS;
+    if (count > MAXB) throw CudaError{cudaErrorInvalidValue, "msm_batch: count > 4", __FILE__, __LINE__};
+    MsmPlan plans[MAXB];
+    ctx->ws.wsums.reserve((size_t)MAXB * SLOT * sizeof(xyzz_t));
+    xyzz_t* d_parts = ctx->ws.wsums.as<xyzz_t>();
     if (!ctx->pinned) {
-        HALO_CUDA(cudaMallocHost(&ctx->pinned, 4 * MSM_MAX_WINDOWS * sizeof(xyzz_t)));
-        ctx->pinned_cap = 4 * MSM_MAX_WINDOWS * sizeof(xyzz_t);
+        HALO_CUDA(cudaMallocHost(&ctx->pinned, (size_t)MAXB * SLOT * sizeof(xyzz_t)));
+        ctx->pinned_cap = (size_t)MAXB * SLOT * sizeof(xyzz_t);
     }
-    xyzz_t* h_wsums = reinterpret_cast<xyzz_t*>(ctx->pinned);
+    xyzz_t* h_parts = reinterpret_cast<xyzz_t*>(ctx->pinned);
     bool any = false;
     for (int k = 0; k < count; k++) {
         if (ins[k].n + ins[k].n_tail == 0) continue;
-        plans[k] = msm_make_plan(ins[k].n + ins[k].n_tail, ctx->force_c);
-        msm_window_sums(ctx, ins[k], plans[k], d_wsums + k * MSM_MAX_WINDOWS);
-        HALO_CUDA(cudaMemcpyAsync(h_wsums + k * MSM_MAX_WINDOWS, d_wsums + k * MSM_MAX_WINDOWS, plans[k].W * sizeof(xyzz_t),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+        plans[k] = ins[k].fixed_stride ? ctx->pre_plan : msm_make_plan(ins[k].n + ins[k].n_tail, ctx->force_c);
+        msm_enqueue(ctx, ins[k], plans[k], d_parts + k * SLOT);
+        const int nwin = plans[k].fixed ? 1 : plans[k].W;
+        HALO_CUDA(cudaMemcpyAsync(h_parts + k * SLOT, d_parts + k * SLOT, (size_t)3 * nwin * sizeof(xyzz_t), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
         any = true;
     }
     if (any) HALO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -364,7 +477,7 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs) {
         if (ins[k].n + ins[k].n_tail == 0)
             xyzz_set_inf(outs[k]);
         else
-            msm_finish_host(h_wsums + k * MSM_MAX_WINDOWS, plans[k], outs[k]);
+            msm_finish_host(h_parts + k * SLOT, plans[k], outs[k]);
     }
 }
 
@@ -373,6 +486,22 @@ void msm_device(halo_ctx* ctx, const affine_t* d_bases, const fr_t* d_scalars, u
     in.bases = d_bases;
     in.scalars = d_scalars;
     in.n = (uint32_t)n;
+    msm_batch(ctx, &in, 1, &out);
+}
+
+// sum_i scalars[i] * G_{first+i} over the resident generators; takes the FIXED-base path when tables exist and the
+// problem is large enough to amortise the (n-independent) bucket reduction of the wide window.
+void msm_gens_device(halo_ctx* ctx, const fr_t* d_scalars, uint64_t first, uint64_t n, xyzz_t& out) {
+    MsmInput in;
+    in.scalars = d_scalars;
+    in.n = (uint32_t)n;
+    if (ctx->use_fixed && ctx->pre_n == ctx->n_gens && ctx->gens_pre.p && n >= (1u << 17) && n * 8 >= ctx->pre_n) {
+        in.bases = ctx->gens_pre.as<affine_t>();
+        in.fixed_stride = ctx->pre_n;
+        in.fixed_first = (uint32_t)first;
+    } else {
+        in.bases = ctx->gens.as<affine_t>() + first;
+    }
     msm_batch(ctx, &in, 1, &out);
 }
 

@@ -12,9 +12,17 @@ struct MsmInput {
     const affine_t* tail_bases = nullptr;
     const fr_t* tail_scalars = nullptr;
     uint32_t n_tail = 0;
+    // FIXED-base mode: bases = table of precomputed multiples, table[w * fixed_stride + fixed_first + i]
+    uint32_t fixed_stride = 0;
+    uint32_t fixed_first = 0;
 };
-// Window sums S_w (XYZZ, device).
-void msm_window_sums(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_wsums_out);
+MsmPlan msm_make_fixed_plan(uint64_t n, int force_c);
+// Device part of one MSM: 3 partial points per window into d_out (see msm.cu).
+void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out);
+// Builds the table of precomputed multiples for the resident generators (FIXED-base mode).
+void msm_precompute_tables(halo_ctx* ctx, int force_c);
+// MSM over resident generators G_first.., FIXED-base when available.
+void msm_gens_device(halo_ctx* ctx, const fr_t* d_scalars, uint64_t first, uint64_t n, xyzz_t& out);
 // Up to 4 MSMs enqueued back to back with a single synchronisation; results on the host.
 void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs);
 void msm_finish_host(const xyzz_t* wsums, const MsmPlan& plan, xyzz_t& out);

@@ -65,6 +65,12 @@ int halo_derive_generators(halo_ctx *ctx, uint64_t n);
 /* Point-slice variant for the sharded MSM: S, H as above, resident generators are G_first .. G_{first+n-1}
  * (rank r of g holds the slice [r n/g, (r+1) n/g); halo_msm_gens offsets are relative to `first`). */
 int halo_derive_generators_range(halo_ctx *ctx, uint64_t first, uint64_t n);
+/* FIXED-base acceleration for halo_msm_gens / halo_h_msm: precomputes the multiples 2^(off_w) G_i of every resident
+ * generator (W x the generator memory) so all windows share one bucket set.  c = window width, 0 = automatic.
+ * Optional; results are identical with or without it.  Invalidated when the generators change. */
+int halo_precompute_generators(halo_ctx *ctx, int c);
+/* Switch the FIXED-base path off / on without dropping the tables (A/B measurements). */
+int halo_set_fixed_base(halo_ctx *ctx, int on);
 /* Alternative: take the reference's own constants (consts::S, consts::H as Jacobian, consts::GS affine). */
 int halo_load_generators(halo_ctx *ctx, const uint64_t S_jac[12], const uint64_t H_jac[12],
                          const uint64_t *gs_affine /*[n][8]*/, uint64_t n);
