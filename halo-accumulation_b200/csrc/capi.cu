@@ -95,6 +95,7 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     ctx->stage_scalars.release();
     ctx->stage_bases.release();
     ctx->stage_misc.release();
+    for (halo::DevBuf* b : {&ctx->ipa_G, &ctx->ipa_cs, &ctx->ipa_zs, &ctx->ipa_pbar, &ctx->ipa_tail}) b->release();
     MsmWorkspace& ws = ctx->ws;
     for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,
                       &ws.task_bucket, &ws.task_partial})

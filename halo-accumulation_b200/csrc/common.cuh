@@ -107,6 +107,10 @@ struct halo_ctx {
     // scratch
     halo::MsmWorkspace ws;
     halo::DevBuf stage_scalars, stage_bases, stage_misc;
+    // buffers of the (single) in-flight PCDL opening, kept across openings: cudaMalloc / cudaFree of 100+ MB per open
+    // costs tens of milliseconds
+    halo::DevBuf ipa_G, ipa_cs, ipa_zs, ipa_pbar, ipa_tail;
+    bool ipa_busy = false;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     int force_c = 0;

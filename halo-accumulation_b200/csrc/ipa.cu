@@ -21,24 +21,42 @@ using namespace halo;
 
 namespace halo {
 
-struct NafDigits {
-    int8_t d[257];  // signed NAF digits of the canonical challenge, LSB first
-    int16_t top;    // index of the most significant non-zero digit (-1 if xi == 0)
+// ---- GLV: xi * P = k1 * P + k2 * phi(P), phi(x, y) = (beta x, y) = lambda * P, |k1|, |k2| < 2^129 ------------------
+// Pallas has j-invariant 0, so Fq contains a primitive cube root of unity beta and Fr the matching lambda
+// (lambda * (x, y) = (beta x, y); pair fixed by checking lambda * G on the generator).  The shared challenge of a
+// round is decomposed once on the host (Babai rounding against the reduced basis (a1, b1), (a2, b2) of the lattice
+// {(a, b): a + b lambda = 0 mod r}); the kernel then needs 129 doublings instead of 255.
+struct GlvDigits {
+    int8_t d1[136];  // signed NAF digits of k1 (sign folded in), LSB first
+    int8_t d2[136];  // signed NAF digits of k2
+    int16_t top;     // highest index with a non-zero digit in either (-1 if xi == 0)
 };
 
-// K4 point part: G[j] <- affine(G[j] + xi * G[j + m]).  One thread per output element; the digit loop is
-// uniform across the grid (same xi for every element of a round).
-__global__ void __launch_bounds__(128) k_fold_points(affine_t* __restrict__ G, uint64_t m, NafDigits naf) {
+__device__ __constant__ uint32_t c_beta_mont[8] = {0x9e65eac8u, 0xfbdfd7aau, 0xe50025fbu, 0x0cd4d654u,
+                                                   0x3785b99au, 0xd59892a3u, 0x585e8789u, 0x2a27fb62u};
+
+// K4 point part: G[j] <- affine(G[j] + xi * G[j + m]) with xi = k1 + k2 lambda.  One thread per output element; the
+// joint digit loop is uniform across the grid (same xi for every element of a round).
+__global__ void __launch_bounds__(128) k_fold_points(affine_t* __restrict__ G, uint64_t m, GlvDigits dg) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     affine_t hi = G[j + m];
+    affine_t hip;  // phi(hi) = (beta x, y); infinity (0, 0) maps to itself
+    {
+        fq_t beta;
+#pragma unroll
+        for (int i = 0; i < 8; i++) beta.v[i] = c_beta_mont[i];
+        fp_mul(hip.x, hi.x, beta);
+        hip.y = hi.y;
+    }
     xyzz_t acc;
     xyzz_set_inf(acc);
 #pragma unroll 1
-    for (int i = naf.top; i >= 0; i--) {
+    for (int i = dg.top; i >= 0; i--) {
         xyzz_dbl(acc, acc);
-        int d = naf.d[i];
-        if (d != 0) xyzz_madd(acc, hi, d < 0);
+        int d1 = dg.d1[i], d2 = dg.d2[i];
+        if (d1 != 0) xyzz_madd(acc, hi, d1 < 0);
+        if (d2 != 0) xyzz_madd(acc, hip, d2 < 0);
     }
     affine_t lo = G[j];
     xyzz_madd(acc, lo, false);
@@ -47,31 +65,118 @@ __global__ void __launch_bounds__(128) k_fold_points(affine_t* __restrict__ G, u
     G[j] = out;
 }
 
-static void make_naf(const fr_t& xi, NafDigits& naf) {
-    uint32_t k[9];
-    fp_to_canon(k, xi);
-    k[8] = 0;
-    naf.top = -1;
-    for (int i = 0; i < 257; i++) {
+// ---- host: decomposition and NAF ---------------------------------------------------------------------------------
+namespace glv {
+typedef unsigned __int128 u128;
+// out[0 .. na+nb) = a * b (little-endian u64 limbs)
+static void mul(uint64_t* out, const uint64_t* a, int na, const uint64_t* b, int nb) {
+    for (int i = 0; i < na + nb; i++) out[i] = 0;
+    for (int i = 0; i < na; i++) {
+        u128 c = 0;
+        for (int j = 0; j < nb; j++) {
+            c += (u128)a[i] * b[j] + out[i + j];
+            out[i + j] = (uint64_t)c;
+            c >>= 64;
+        }
+        out[i + nb] = (uint64_t)c;
+    }
+}
+// 5-limb two's complement helpers
+static void add5(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+    u128 c = 0;
+    for (int i = 0; i < 5; i++) {
+        c += (u128)a[i] + b[i];
+        r[i] = (uint64_t)c;
+        c >>= 64;
+    }
+}
+static void neg5(uint64_t* r, const uint64_t* a) {
+    u128 c = 1;
+    for (int i = 0; i < 5; i++) {
+        c += (uint64_t)~a[i];
+        r[i] = (uint64_t)c;
+        c >>= 64;
+    }
+}
+static void sub5(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+    uint64_t nb[5];
+    neg5(nb, b);
+    add5(r, a, nb);
+}
+// basis and fixed-point reciprocals g_i = floor(|.| 2^384 / r) (tools: see DESIGN.md; checked by the open parity tests)
+static const uint64_t A1[2] = {0x8cb1279300000000ull, 0x49e69d1640a89953ull};            // a1 = b2
+static const uint64_t B1N[2] = {0x7fcae1c700000001ull, 0x49e69d1640f04915ull};           // -b1
+static const uint64_t A2[3] = {0x0c7c095a00000001ull, 0x93cd3a2c8198e269ull, 0x0ull};    // a2
+static const uint64_t G1[5] = {0x4a95a2d972171db4ull, 0x61afdea68480fa55ull, 0x32c49e4bffffffffull, 0x279a745902a2654eull, 0x1ull};
+static const uint64_t G2[5] = {0xc689c5879f98a4deull, 0x61afdea683e7688aull, 0xff2b871c00000003ull, 0x279a745903c12455ull, 0x1ull};
+
+// |k| as NAF digits (LSB first) with overall sign; returns the index of the top non-zero digit or -1
+static int naf(const uint64_t mag[3], bool negative, int8_t* out, int len) {
+    uint64_t k[3] = {mag[0], mag[1], mag[2]};
+    int top = -1;
+    for (int i = 0; i < len; i++) {
         int d = 0;
         if (k[0] & 1u) {
-            d = 2 - (int)(k[0] & 3u);  // +1 or -1 so that (k - d) is divisible by 4
+            d = 2 - (int)(k[0] & 3u);
             if (d < 0) {
-                // k += 1
-                for (int l = 0; l < 9; l++)
+                for (int l = 0; l < 3; l++)
                     if (++k[l] != 0) break;
             } else {
-                k[0] -= 1;  // odd, no borrow
+                k[0] -= 1;
             }
-            naf.top = (int16_t)i;
+            top = i;
         }
-        naf.d[i] = (int8_t)d;
-        for (int l = 0; l < 8; l++) k[l] = (k[l] >> 1) | (k[l + 1] << 31);
-        k[8] >>= 1;
+        out[i] = (int8_t)(negative ? -d : d);
+        k[0] = (k[0] >> 1) | (k[1] << 63);
+        k[1] = (k[1] >> 1) | (k[2] << 63);
+        k[2] >>= 1;
     }
+    return top;
+}
+}  // namespace glv
+
+static void make_glv(const fr_t& xi, GlvDigits& dg) {
+    using namespace glv;
+    uint32_t kc[8];
+    fp_to_canon(kc, xi);
+    uint64_t k[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) k[i] = (uint64_t)kc[2 * i] | ((uint64_t)kc[2 * i + 1] << 32);
+    // c1 = (k * g1) >> 384, c2 = (k * g2) >> 384   (< 2^130)
+    uint64_t prod[9], c1[3], c2[3];
+    mul(prod, k, 4, G1, 5);
+    c1[0] = prod[6]; c1[1] = prod[7]; c1[2] = prod[8];
+    mul(prod, k, 4, G2, 5);
+    c2[0] = prod[6]; c2[1] = prod[7]; c2[2] = prod[8];
+    // k1 = k - c1 a1 - c2 a2 ; k2 = c1 (-b1) - c2 b2   (b2 = a1), as 5-limb two's complement
+    uint64_t t1[6], t2[6], k1[5], k2[5], s[5];
+    mul(t1, c1, 3, A1, 2);   // 5 limbs
+    mul(t2, c2, 3, A2, 3);   // 6 limbs, top is zero
+    add5(s, t1, t2);
+    sub5(k1, k, s);
+    mul(t1, c1, 3, B1N, 2);
+    mul(t2, c2, 3, A1, 2);
+    sub5(k2, t1, t2);
+    bool n1 = (k1[4] >> 63) != 0, n2 = (k2[4] >> 63) != 0;
+    if (n1) neg5(k1, k1);
+    if (n2) neg5(k2, k2);
+    for (int i = 0; i < 136; i++) dg.d1[i] = dg.d2[i] = 0;
+    int top1 = naf(k1, n1, dg.d1, 134);
+    int top2 = naf(k2, n2, dg.d2, 134);
+    dg.top = (int16_t)(top1 > top2 ? top1 : top2);
 }
 
 }  // namespace halo
+
+extern "C" int halo_test_glv_decompose(const uint64_t xi[4], int8_t d1[136], int8_t d2[136], int* top) {
+    fr_t x;
+    memcpy(&x, xi, 32);
+    GlvDigits dg;
+    make_glv(x, dg);
+    memcpy(d1, dg.d1, 136);
+    memcpy(d2, dg.d2, 136);
+    *top = dg.top;
+    return 0;
+}
 
 #define IPA_TRY(st)  \
     halo_ctx* ctx = (st)->ctx; \
@@ -97,6 +202,10 @@ int halo_ipa_begin(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, uin
         ctx->last_error = "halo_ipa_begin: n must be a power of two <= resident generators and >= n_coeffs";
         return HALO_EINVAL;
     }
+    if (ctx->ipa_busy) {
+        ctx->last_error = "halo_ipa_begin: another opening is in flight on this context";
+        return HALO_ESTATE;
+    }
     halo_ipa* st = new halo_ipa();
     st->ctx = ctx;
     try {
@@ -104,18 +213,18 @@ int halo_ipa_begin(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, uin
         st->n = st->cur = n;
         while (((uint64_t)1 << st->lg_n) < n) st->lg_n++;
         memcpy(&st->z, z, 32);
-        st->G.reserve(n * sizeof(affine_t));
-        st->cs.reserve(n * sizeof(fr_t));
-        st->zs.reserve(n * sizeof(fr_t));
-        st->tail.reserve(sizeof(affine_t) + (2 + VEC_DOT_MAX_BLOCKS) * sizeof(fr_t));
+        ctx->ipa_G.reserve(n * sizeof(affine_t));
+        ctx->ipa_cs.reserve(n * sizeof(fr_t));
+        ctx->ipa_zs.reserve(n * sizeof(fr_t));
+        ctx->ipa_tail.reserve(sizeof(affine_t) + (2 + VEC_DOT_MAX_BLOCKS) * sizeof(fr_t));
         cudaStream_t s = ctx->stream;
-        HALO_CUDA(cudaMemcpyAsync(st->G.p, ctx->gens.p, n * sizeof(affine_t), cudaMemcpyDeviceToDevice, s));  // pcdl.rs:185
-        HALO_CUDA(cudaMemsetAsync(st->cs.p, 0, n * sizeof(fr_t), s));                                         // pcdl.rs:183-184
-        if (n_coeffs) HALO_CUDA(cudaMemcpyAsync(st->cs.p, coeffs, n_coeffs * sizeof(fr_t), cudaMemcpyHostToDevice, s));
-        vec_powers(ctx, st->z, n, st->zs.as<fr_t>());  // pcdl.rs:186
+        HALO_CUDA(cudaMemcpyAsync(ctx->ipa_G.p, ctx->gens.p, n * sizeof(affine_t), cudaMemcpyDeviceToDevice, s));  // pcdl.rs:185
+        HALO_CUDA(cudaMemsetAsync(ctx->ipa_cs.p, 0, n * sizeof(fr_t), s));                                         // pcdl.rs:183-184
+        if (n_coeffs) HALO_CUDA(cudaMemcpyAsync(ctx->ipa_cs.p, coeffs, n_coeffs * sizeof(fr_t), cudaMemcpyHostToDevice, s));
+        vec_powers(ctx, st->z, n, ctx->ipa_zs.as<fr_t>());  // pcdl.rs:186
         if (v_out) {                                   // v = p(z) = <c, z-powers>  (pcdl.rs:135)
-            fr_t* scal = reinterpret_cast<fr_t*>(reinterpret_cast<char*>(st->tail.p) + sizeof(affine_t));
-            vec_dot(ctx, st->cs.as<fr_t>(), st->zs.as<fr_t>(), n, scal + 2, scal);
+            fr_t* scal = reinterpret_cast<fr_t*>(reinterpret_cast<char*>(ctx->ipa_tail.p) + sizeof(affine_t));
+            vec_dot(ctx, ctx->ipa_cs.as<fr_t>(), ctx->ipa_zs.as<fr_t>(), n, scal + 2, scal);
             HALO_CUDA(cudaMemcpyAsync(v_out, scal, 32, cudaMemcpyDeviceToHost, s));
         }
         HALO_CUDA(cudaStreamSynchronize(s));
@@ -124,6 +233,7 @@ int halo_ipa_begin(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, uin
         delete st;
         return HALO_ECUDA;
     }
+    ctx->ipa_busy = true;
     *out = st;
     return HALO_OK;
 }
@@ -132,11 +242,7 @@ void halo_ipa_destroy(halo_ipa* st) {
     if (!st) return;
     cudaSetDevice(st->ctx->device);
     cudaStreamSynchronize(st->ctx->stream);
-    st->G.release();
-    st->cs.release();
-    st->zs.release();
-    st->pbar.release();
-    st->tail.release();
+    st->ctx->ipa_busy = false;  // the buffers stay with the context for the next opening
     delete st;
 }
 
@@ -147,26 +253,27 @@ int halo_ipa_blind_commit(halo_ipa* st, const uint64_t* q, uint64_t n_q, uint64_
         return HALO_EINVAL;
     }
     IPA_TRY(st)
-    st->pbar.reserve(st->n * sizeof(fr_t));
+    ctx->ipa_pbar.reserve(st->n * sizeof(fr_t));
     ctx->stage_scalars.reserve(n_q * sizeof(fr_t));
     HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, q, n_q * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
-    vec_pbar(ctx, ctx->stage_scalars.as<fr_t>(), n_q, st->z, st->n, st->pbar.as<fr_t>());
+    vec_pbar(ctx, ctx->stage_scalars.as<fr_t>(), n_q, st->z, st->n, ctx->ipa_pbar.as<fr_t>());
     xyzz_t r;
-    msm_gens_device(ctx, st->pbar.as<fr_t>(), 0, st->n, r);  // commit(p_bar) without the w_bar S term
+    msm_gens_device(ctx, ctx->ipa_pbar.as<fr_t>(), 0, st->n, r);  // commit(p_bar) without the w_bar S term
     jac_t j;
     xyzz_to_jac(j, r);
     memcpy(out_jac, &j, 96);
+    st->have_pbar = true;
     IPA_CATCH
 }
 
 int halo_ipa_blind_apply(halo_ipa* st, const uint64_t alpha[4]) {
-    if (!st || !alpha || !st->pbar.p || st->round != 0) return HALO_EINVAL;
+    if (!st || !alpha || !st->have_pbar || st->round != 0) return HALO_EINVAL;
     IPA_TRY(st)
     fr_t a;
     memcpy(&a, alpha, 32);
-    vec_axpy(ctx, st->cs.as<fr_t>(), st->pbar.as<fr_t>(), a, st->n);  // p' = p + alpha p_bar  (pcdl.rs:156)
+    vec_axpy(ctx, ctx->ipa_cs.as<fr_t>(), ctx->ipa_pbar.as<fr_t>(), a, st->n);  // p' = p + alpha p_bar  (pcdl.rs:156)
     HALO_CUDA(cudaStreamSynchronize(ctx->stream));
-    st->pbar.release();
+    st->have_pbar = false;
     IPA_CATCH
 }
 
@@ -179,7 +286,7 @@ int halo_ipa_set_hprime(halo_ipa* st, const uint64_t Hprime_jac[12]) {
     jac_to_xyzz(x, j);
     affine_t a;
     xyzz_to_affine(a, x);
-    HALO_CUDA(cudaMemcpyAsync(st->tail.p, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream));
+    HALO_CUDA(cudaMemcpyAsync(ctx->ipa_tail.p, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream));
     HALO_CUDA(cudaStreamSynchronize(ctx->stream));
     st->have_hprime = true;
     IPA_CATCH
@@ -193,11 +300,11 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
     }
     IPA_TRY(st)
     const uint64_t m = st->cur / 2;
-    affine_t* G = st->G.as<affine_t>();
-    fr_t* c = st->cs.as<fr_t>();
-    fr_t* z = st->zs.as<fr_t>();
-    affine_t* Hp = st->tail.as<affine_t>();
-    fr_t* scal = reinterpret_cast<fr_t*>(reinterpret_cast<char*>(st->tail.p) + sizeof(affine_t));
+    affine_t* G = ctx->ipa_G.as<affine_t>();
+    fr_t* c = ctx->ipa_cs.as<fr_t>();
+    fr_t* z = ctx->ipa_zs.as<fr_t>();
+    affine_t* Hp = ctx->ipa_tail.as<affine_t>();
+    fr_t* scal = reinterpret_cast<fr_t*>(reinterpret_cast<char*>(ctx->ipa_tail.p) + sizeof(affine_t));
     vec_dot(ctx, c + m, z, m, scal + 2, scal);          // dot_l = <c_r, z_l>
     vec_dot(ctx, c, z + m, m, scal + 2, scal + 1);      // dot_r = <c_l, z_r>
     MsmInput in[2];
@@ -233,12 +340,12 @@ int halo_ipa_round_fold(halo_ipa* st, const uint64_t xi[4], const uint64_t xi_in
     fr_t x, xinv;
     memcpy(&x, xi, 32);
     memcpy(&xinv, xi_inv, 32);
-    NafDigits naf;
-    make_naf(x, naf);
-    k_fold_points<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(st->G.as<affine_t>(), m, naf);
+    GlvDigits dg;
+    make_glv(x, dg);
+    k_fold_points<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_G.as<affine_t>(), m, dg);
     ctx->kernel_launches++;
     HALO_CUDA(cudaGetLastError());
-    vec_fold_scalars(ctx, st->cs.as<fr_t>(), st->zs.as<fr_t>(), m, x, xinv);
+    vec_fold_scalars(ctx, ctx->ipa_cs.as<fr_t>(), ctx->ipa_zs.as<fr_t>(), m, x, xinv);
     st->cur = m;
     st->round++;
     st->lr_done = false;
@@ -253,8 +360,8 @@ int halo_ipa_finish(halo_ipa* st, uint64_t U_jac[12], uint64_t c_out[4]) {
     }
     IPA_TRY(st)
     affine_t u;
-    HALO_CUDA(cudaMemcpyAsync(&u, st->G.p, sizeof u, cudaMemcpyDeviceToHost, ctx->stream));
-    HALO_CUDA(cudaMemcpyAsync(c_out, st->cs.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    HALO_CUDA(cudaMemcpyAsync(&u, ctx->ipa_G.p, sizeof u, cudaMemcpyDeviceToHost, ctx->stream));
+    HALO_CUDA(cudaMemcpyAsync(c_out, ctx->ipa_cs.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     HALO_CUDA(cudaStreamSynchronize(ctx->stream));
     xyzz_t x;
     xyzz_from_affine(x, u);

@@ -11,8 +11,8 @@ struct halo_ipa {
     bool have_hprime = false;
     bool lr_done = false;
     halo::fr_t z;
-    halo::DevBuf G;        // affine working copy of GS[0..n)  (pcdl.rs:185)
-    halo::DevBuf cs, zs;   // coefficient and z-power vectors (pcdl.rs:183-186)
-    halo::DevBuf pbar;     // hiding polynomial (pcdl.rs:140-142)
-    halo::DevBuf tail;     // [affine H'] then [fr dot_l, fr dot_r] and dot partials
+    // device buffers live in the context (ctx->ipa_*): G = affine working copy of GS[0..n) (pcdl.rs:185), cs / zs =
+    // coefficient and z-power vectors (pcdl.rs:183-186), pbar = hiding polynomial (pcdl.rs:140-142),
+    // tail = [affine H'] then [fr dot_l, fr dot_r] and dot partials
+    bool have_pbar = false;
 };
