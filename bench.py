@@ -77,6 +77,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def host_threads():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1; the CPU arm must not inherit that."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)  # read by libgomp when the oracle library is loaded
+    return n
+
+
 def cpu_msm_baseline(log_n_sample, threads, seed=4):
     """The reference's CPU path (arkworks-shaped Pippenger restated in oracle/halo_oracle.c) on a bounded sample."""
     from oracle import oracle as O
@@ -94,9 +104,9 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    threads = host_threads()
     from oracle import oracle as O
 
-    threads = O.lib().orc_num_threads()
     n = 1 << args.cpu_log_n
     bases = O.derive_points(2, n)
     scalars = O.random_scalars(n, 4)
@@ -220,9 +230,7 @@ def run_ours(args):
         achieved = alg_imad / (phases["accumulate"] * 1e-3) / 1e12
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle as O
-
-            threads_cpu = O.lib().orc_num_threads()
+            threads_cpu = host_threads()
             v, dt = cpu_msm_baseline(args.cpu_log_n, threads_cpu)
             cpu = {"value": v, "unit": UNIT, "cores": threads_cpu, "kind": "port",
                    "sample": f"one MSM of 2^{args.cpu_log_n} points ({dt:.1f} s), arkworks-shaped Pippenger restated in C, windows over {threads_cpu} threads"}
@@ -322,7 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-n", type=int, default=24, help="log2 of the points per GPU")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--cpu-log-n", type=int, default=18, help="log2 of the bounded CPU sample")
+    ap.add_argument("--cpu-log-n", type=int, default=20, help="log2 of the bounded CPU sample")
     ap.add_argument("--secondary-log-n", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")

@@ -138,6 +138,9 @@ class Context:
     def set_msm_window(self, c):
         self._chk(self._lib.halo_set_msm_window(self._h, int(c)))
 
+    def set_tuning(self, key, value):
+        self._chk(self._lib.halo_set_tuning(self._h, key.encode(), int(value)))
+
     def set_profiling(self, on):
         self._chk(self._lib.halo_set_profiling(self._h, int(bool(on))))
 

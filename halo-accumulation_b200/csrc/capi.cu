@@ -76,6 +76,7 @@ int halo_ctx_create(int device, uint64_t max_n, halo_ctx** out) {
     try {
         HALO_CUDA(cudaSetDevice(device));
         HALO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        HALO_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
         for (auto& e : ctx->ev) HALO_CUDA(cudaEventCreate(&e));
     } catch (const halo::CudaError&) {
         delete ctx;
@@ -113,6 +114,13 @@ uint64_t halo_num_generators(halo_ctx* ctx) { return ctx ? ctx->n_gens : 0; }
 int halo_set_msm_window(halo_ctx* ctx, int c) {
     if (!ctx || c < 0 || c > 20) return HALO_EINVAL;
     ctx->force_c = c;
+    return HALO_OK;
+}
+int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return HALO_EINVAL;
+    if (!strcmp(key, "acc_static")) ctx->tune_acc_static = value;
+    else if (!strcmp(key, "acc_blocks_per_sm")) ctx->tune_acc_blocks_per_sm = value;
+    else return fail(ctx, HALO_EINVAL, "halo_set_tuning: unknown key");
     return HALO_OK;
 }
 int halo_set_profiling(halo_ctx* ctx, int on) {

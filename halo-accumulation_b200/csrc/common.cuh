@@ -92,6 +92,7 @@ struct Timings {
 // The opaque handle behind `halo_ctx*` (include/halo_b200.h).
 struct halo_ctx {
     int device = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
     uint64_t max_n = 0;
     // public parameters (consts.rs:23-68): G_0..G_{n_gens-1} resident in HBM as Montgomery affine, S and H on host
@@ -114,6 +115,7 @@ struct halo_ctx {
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     int force_c = 0;
+    int tune_acc_static = 0, tune_acc_blocks_per_sm = 0;
     uint64_t kernel_launches = 0;
     halo::Timings last;
     bool profile = false;

@@ -333,9 +333,23 @@ HALO_HD void fp_mul_portable(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
 #define HALO_FP_MUL_VARIANT 1
 #endif
 
+#if defined(__CUDACC__)
+// Out-of-line copy of the multiplication (arguments and result by value: they travel in registers, no local memory).
+// Kernels whose body would otherwise inline 10-20 copies of the 210-instruction multiplication overflow the
+// instruction cache (ncu: sm__icc_request_hit_rate 84 %, "no instruction" the third largest stall of k_accumulate).
+template <class P>
+__device__ __noinline__ fp_t<P> fp_mul_call(fp_t<P> a, fp_t<P> b) {
+    fp_t<P> r;
+    fp_mul_asm<P, HALO_FP_MUL_VARIANT>(r.v, a.v, b.v);
+    return r;
+}
+#endif
+
 template <class P>
 HALO_HD void fp_mul(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
-#if defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+#if defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE) && defined(HALO_FP_MUL_CALL)
+    r = fp_mul_call<P>(a, b);
+#elif defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
     uint32_t o[8];
     fp_mul_asm<P, HALO_FP_MUL_VARIANT>(o, a.v, b.v);  // generated straight-line PTX, csrc/fp_mul_asm.cuh
 #pragma unroll
@@ -348,7 +362,9 @@ HALO_HD void fp_mul(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
 }
 template <class P>
 HALO_HD void fp_sqr(fp_t<P>& r, const fp_t<P>& a) {
-#if defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+#if defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE) && defined(HALO_FP_MUL_CALL)
+    r = fp_mul_call<P>(a, a);
+#elif defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
     uint32_t o[8];
     fp_sqr_asm<P, HALO_FP_MUL_VARIANT>(o, a.v);
 #pragma unroll

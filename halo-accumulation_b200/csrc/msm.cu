@@ -205,6 +205,10 @@ static void exclusive_scan(const uint32_t* counts, uint32_t* offsets, uint32_t n
 // ------------------------------------------------------------------------------------------------
 // 4. bucket accumulation: one thread per bucket, accumulator in registers
 // ------------------------------------------------------------------------------------------------
+// Lanes do not own a fixed bucket: a lane that has drained its bucket stores it and claims the next unprocessed one
+// (one warp-aggregated atomicAdd per claim round), so every lane of a warp stays busy until the work runs out.  With
+// a static thread-per-bucket mapping the warp waits for its fullest bucket: bucket loads are Poisson, which costs
+// 10 % at 416 entries per bucket and 21 % at 96 (c = 22).
 #ifndef HALO_ACC_MIN_BLOCKS
 #define HALO_ACC_MIN_BLOCKS 4
 #endif
@@ -212,17 +216,92 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate(const a
                                                                          const affine_t* __restrict__ tail_bases,
                                                                          const uint32_t* __restrict__ offsets,
                                                                          const uint32_t* __restrict__ entries, uint32_t NB,
-                                                                         xyzz_t* __restrict__ buckets) {
+                                                                         xyzz_t* __restrict__ buckets,
+                                                                         uint32_t* __restrict__ next_bucket) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t b = 0xffffffffu;  // no bucket yet
+    uint32_t e = 0, end = 0;
+    bool exhausted = false;
+    xyzz_t acc;
+    xyzz_set_inf(acc);
+    uint32_t ent1 = 0, ent2 = 0;
+    affine_t p1;
+    affine_set_inf(p1);
+    while (true) {
+        const bool need = !exhausted && e == end;
+        if (need && b != 0xffffffffu) buckets[b] = acc;
+        const unsigned want = __ballot_sync(0xffffffffu, need);
+        if (want) {
+            uint32_t base = 0;
+            const int leader = __ffs(want) - 1;
+            if ((int)lane == leader) base = atomicAdd(next_bucket, (uint32_t)__popc(want));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) {
+                b = base + (uint32_t)__popc(want & lt_mask);
+                if (b < NB) {
+                    e = offsets[b];
+                    end = offsets[b + 1];
+                    xyzz_set_inf(acc);
+                    // refill the software pipeline (entry two ahead, base one ahead)
+                    if (e < end) {
+                        ent1 = entries[e];
+                        if (e + 1 < end) ent2 = entries[e + 1];
+                        uint32_t idx = ent1 & 0x7fffffffu;
+                        p1 = idx < n ? bases[idx] : tail_bases[idx - n];
+                    }
+                } else {
+                    b = 0xffffffffu;
+                    e = end = 0;
+                    exhausted = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, exhausted)) break;
+        if (e < end) {
+            const uint32_t ent0 = ent1;
+            const affine_t p0 = p1;
+            ent1 = ent2;
+            if (e + 2 < end) ent2 = entries[e + 2];
+            if (e + 1 < end) {
+                uint32_t idx = ent1 & 0x7fffffffu;
+                p1 = idx < n ? bases[idx] : tail_bases[idx - n];
+            }
+            xyzz_madd(acc, p0, (ent0 >> 31) != 0);
+            e++;
+        }
+    }
+}
+
+// Static mapping (one thread per bucket) kept for A/B measurements: halo_set_tuning(ctx, "acc_static", 1).
+__global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_static(const affine_t* __restrict__ bases, uint32_t n,
+                                                                                const affine_t* __restrict__ tail_bases,
+                                                                                const uint32_t* __restrict__ offsets,
+                                                                                const uint32_t* __restrict__ entries, uint32_t NB,
+                                                                                xyzz_t* __restrict__ buckets) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= NB) return;
     uint32_t beg = offsets[b], end = offsets[b + 1];
     xyzz_t acc;
     xyzz_set_inf(acc);
+    // software pipeline: the entry two steps ahead and the base one step ahead are in flight during each mixed add
+    uint32_t ent1 = beg < end ? entries[beg] : 0;
+    uint32_t ent2 = beg + 1 < end ? entries[beg + 1] : 0;
+    affine_t p1;
+    {
+        uint32_t idx = ent1 & 0x7fffffffu;
+        if (beg < end) p1 = idx < n ? bases[idx] : tail_bases[idx - n];
+    }
     for (uint32_t e = beg; e < end; e++) {
-        uint32_t ent = entries[e];
-        uint32_t idx = ent & 0x7fffffffu;
-        affine_t p = idx < n ? bases[idx] : tail_bases[idx - n];
-        xyzz_madd(acc, p, (ent >> 31) != 0);
+        const uint32_t ent0 = ent1;
+        const affine_t p0 = p1;
+        ent1 = ent2;
+        if (e + 2 < end) ent2 = entries[e + 2];
+        if (e + 1 < end) {
+            uint32_t idx = ent1 & 0x7fffffffu;
+            p1 = idx < n ? bases[idx] : tail_bases[idx - n];
+        }
+        xyzz_madd(acc, p0, (ent0 >> 31) != 0);
     }
     buckets[b] = acc;
 }
@@ -391,8 +470,21 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
                                          in.fixed_first, counts, offsets, entries);
     mark(3);
     // FIXED: every entry indexes the table, there is no tail
-    k_accumulate<<<(NB + 127) / 128, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, offsets, entries, NB,
-                                                   buckets);
+    // thread-per-bucket is ~8 % faster when buckets are deep and evenly filled (variable base, large n); lane-level
+    // claiming wins everywhere else (measured: profiles/r01_accumulate_static_vs_dynamic.txt)
+    const bool deep = !plan.fixed && (uint64_t)ntot * plan.W >= (uint64_t)NB * 256;
+    if (ctx->tune_acc_static == 1 || (ctx->tune_acc_static == 0 && deep)) {
+        k_accumulate_static<<<(NB + 127) / 128, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, offsets, entries,
+                                                             NB, buckets);
+    } else {
+        // persistent lanes: enough CTAs to fill the machine, capped by the amount of work
+        uint32_t want_blocks = (NB + 127) / 128;
+        uint32_t max_blocks = (uint32_t)ctx->sm_count * (ctx->tune_acc_blocks_per_sm ? ctx->tune_acc_blocks_per_sm : HALO_ACC_MIN_BLOCKS);
+        uint32_t blocks = want_blocks < max_blocks ? want_blocks : max_blocks;
+        uint32_t* next_bucket = counts + NB;  // spare slot at the end of the counter array (zeroed above)
+        k_accumulate<<<blocks, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, offsets, entries, NB, buckets,
+                                             next_bucket);
+    }
     mark(4);
     HALO_CUDA(cudaMemsetAsync(d_out, 0, (size_t)3 * nwin * sizeof(xyzz_t), st));
     if (plan.red_slabs == 1) {

@@ -53,6 +53,9 @@ const char *halo_last_error(halo_ctx *ctx);
 uint64_t halo_kernel_launches(halo_ctx *ctx);
 /* Tuning / diagnostics: force the Pippenger window width (0 = automatic). */
 int halo_set_msm_window(halo_ctx *ctx, int c);
+/* Measurement knobs (no effect on results): "acc_static" 1 / 2 = force thread-per-bucket / lane-level bucket claiming (0 = automatic)
+ * in the accumulation kernel; "acc_blocks_per_sm" = CTAs per SM of the persistent accumulation grid (0 = default). */
+int halo_set_tuning(halo_ctx *ctx, const char *key, int value);
 /* Enable per-phase CUDA-event timing of the MSM; read back with halo_last_msm_timings (ms):
  * [digits, scan, scatter, accumulate, bucket_reduce, total]. */
 int halo_set_profiling(halo_ctx *ctx, int on);
