@@ -99,7 +99,7 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     for (halo::DevBuf* b : {&ctx->ipa_G, &ctx->ipa_cs, &ctx->ipa_zs, &ctx->ipa_pbar, &ctx->ipa_tail}) b->release();
     MsmWorkspace& ws = ctx->ws;
     for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,
-                      &ws.task_bucket, &ws.task_partial})
+                      &ws.task_bucket, &ws.task_partial, &ws.split_ctrl, &ws.split_tasks, &ws.split_buckets, &ws.split_partials})
         b->release();
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);

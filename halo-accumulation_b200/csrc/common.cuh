@@ -80,7 +80,8 @@ MsmPlan msm_make_plan(uint64_t n, int force_c);
 
 struct MsmWorkspace {
     DevBuf counts, offsets, cursor, entries, buckets, wsums, scan_tmp;
-    DevBuf task_bucket, task_partial;  // bucket splitting for skewed inputs
+    DevBuf task_bucket, task_partial;  // slab partials of the bucket reduction
+    DevBuf split_ctrl, split_tasks, split_buckets, split_partials;  // oversized-bucket splitting
 };
 
 struct Timings {

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate(const a
                                                                          const uint32_t* __restrict__ offsets,
                                                                          const uint32_t* __restrict__ entries, uint32_t NB,
                                                                          xyzz_t* __restrict__ buckets,
-                                                                         uint32_t* __restrict__ next_bucket) {
+                                                                         uint32_t* __restrict__ next_bucket, uint32_t split_len) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t b = 0xffffffffu;  // no bucket yet
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate(const a
     affine_set_inf(p1);
     while (true) {
         const bool need = !exhausted && e == end;
-        if (need && b != 0xffffffffu) buckets[b] = acc;
+        if (need && b < 0xfffffffeu) buckets[b] = acc;
         const unsigned want = __ballot_sync(0xffffffffu, need);
         if (want) {
             uint32_t base = 0;
@@ -243,6 +243,10 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate(const a
                     e = offsets[b];
                     end = offsets[b + 1];
                     xyzz_set_inf(acc);
+                    if (end - e > split_len) {  // oversized bucket: handled by k_accumulate_split, never stored here
+                        b = 0xfffffffeu;
+                        end = e;
+                    }
                     // refill the software pipeline (entry two ahead, base one ahead)
                     if (e < end) {
                         ent1 = entries[e];
@@ -278,10 +282,11 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_static(
                                                                                 const affine_t* __restrict__ tail_bases,
                                                                                 const uint32_t* __restrict__ offsets,
                                                                                 const uint32_t* __restrict__ entries, uint32_t NB,
-                                                                                xyzz_t* __restrict__ buckets) {
+                                                                                xyzz_t* __restrict__ buckets, uint32_t split_len) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= NB) return;
     uint32_t beg = offsets[b], end = offsets[b + 1];
+    if (end - beg > split_len) return;  // oversized bucket: k_accumulate_split
     xyzz_t acc;
     xyzz_set_inf(acc);
     // software pipeline: the entry two steps ahead and the base one step ahead are in flight during each mixed add
@@ -306,6 +311,127 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_static(
     buckets[b] = acc;
 }
 
+__device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q) { xyzz_add(acc, q); }
+__device__ __noinline__ void xyzz_dbl_nl(xyzz_t& acc) { xyzz_dbl(acc, acc); }
+
+// ------------------------------------------------------------------------------------------------
+// 4b. oversized buckets.  Uniform scalars fill buckets evenly, but legal inputs can pile everything into a few buckets
+//     (all scalars equal, tiny scalars, a constant polynomial): one lane would then add millions of points serially.
+//     Buckets deeper than split_len are cut into chunks of split_len entries ("split tasks"), accumulated by lane-level
+//     claiming like ordinary buckets, and merged by one warp per bucket.  Costs three near-empty launches when no bucket
+//     is oversized.
+// ------------------------------------------------------------------------------------------------
+struct SplitTask {
+    uint32_t beg, end;  // entry range
+};
+struct SplitBucket {
+    uint32_t bucket, first_task, n_tasks;
+};
+// ctrl[0] = number of split tasks, ctrl[1] = number of split buckets, ctrl[2] = claim counter
+__global__ void __launch_bounds__(256) k_split_plan(const uint32_t* __restrict__ offsets, uint32_t NB, uint32_t split_len,
+                                                    uint32_t max_tasks, uint32_t max_buckets, uint32_t* __restrict__ ctrl,
+                                                    SplitTask* __restrict__ tasks, SplitBucket* __restrict__ sbuckets) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    uint32_t beg = offsets[b], end = offsets[b + 1];
+    uint32_t cnt = end - beg;
+    if (cnt <= split_len) return;
+    uint32_t nt = (cnt + split_len - 1) / split_len;
+    uint32_t first = atomicAdd(&ctrl[0], nt);
+    uint32_t slot = atomicAdd(&ctrl[1], 1u);
+    if (first + nt > max_tasks || slot >= max_buckets) {
+        ctrl[3] = 1;  // capacity exceeded (cannot happen: capacities are sized from the entry count), flagged for the host
+        return;
+    }
+    sbuckets[slot] = SplitBucket{b, first, nt};
+    for (uint32_t t = 0; t < nt; t++) {
+        uint32_t tb = beg + t * split_len;
+        uint32_t te = tb + split_len < end ? tb + split_len : end;
+        tasks[first + t] = SplitTask{tb, te};
+    }
+}
+
+__global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_split(const affine_t* __restrict__ bases, uint32_t n,
+                                                                               const affine_t* __restrict__ tail_bases,
+                                                                               const uint32_t* __restrict__ entries,
+                                                                               const SplitTask* __restrict__ tasks,
+                                                                               uint32_t* __restrict__ ctrl,
+                                                                               xyzz_t* __restrict__ partials) {
+    const uint32_t NT = ctrl[0];
+    if (NT == 0) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t t = 0xffffffffu, e = 0, end = 0;
+    bool exhausted = false;
+    xyzz_t acc;
+    xyzz_set_inf(acc);
+    while (true) {
+        const bool need = !exhausted && e == end;
+        if (need && t != 0xffffffffu) partials[t] = acc;
+        const unsigned want = __ballot_sync(0xffffffffu, need);
+        if (want) {
+            uint32_t base = 0;
+            const int leader = __ffs(want) - 1;
+            if ((int)lane == leader) base = atomicAdd(&ctrl[2], (uint32_t)__popc(want));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) {
+                t = base + (uint32_t)__popc(want & lt_mask);
+                if (t < NT) {
+                    SplitTask tk = tasks[t];
+                    e = tk.beg;
+                    end = tk.end;
+                    xyzz_set_inf(acc);
+                } else {
+                    t = 0xffffffffu;
+                    e = end = 0;
+                    exhausted = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, exhausted)) break;
+        if (e < end) {
+            uint32_t ent = entries[e];
+            uint32_t idx = ent & 0x7fffffffu;
+            affine_t p = idx < n ? bases[idx] : tail_bases[idx - n];
+            xyzz_madd(acc, p, (ent >> 31) != 0);
+            e++;
+        }
+    }
+}
+
+// one warp per oversized bucket: lanes stride over the bucket's partial sums, then a shuffle tree
+__device__ __forceinline__ void xyzz_shfl_down(xyzz_t& dst, const xyzz_t& src, int delta) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        dst.x.v[i] = __shfl_down_sync(0xffffffffu, src.x.v[i], delta);
+        dst.y.v[i] = __shfl_down_sync(0xffffffffu, src.y.v[i], delta);
+        dst.zz.v[i] = __shfl_down_sync(0xffffffffu, src.zz.v[i], delta);
+        dst.zzz.v[i] = __shfl_down_sync(0xffffffffu, src.zzz.v[i], delta);
+    }
+}
+__global__ void __launch_bounds__(128) k_merge_split(const SplitBucket* __restrict__ sbuckets, const uint32_t* __restrict__ ctrl,
+                                                     const xyzz_t* __restrict__ partials, xyzz_t* __restrict__ buckets) {
+    const uint32_t NS = ctrl[1];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t s = warp; s < NS; s += nwarps) {
+        SplitBucket sb = sbuckets[s];
+        xyzz_t acc;
+        xyzz_set_inf(acc);
+        for (uint32_t t = lane; t < sb.n_tasks; t += 32) {
+            xyzz_t q = partials[sb.first_task + t];
+            xyzz_add_nl(acc, q);
+        }
+        for (int delta = 16; delta >= 1; delta >>= 1) {
+            xyzz_t other;
+            xyzz_shfl_down(other, acc, delta);
+            xyzz_add_nl(acc, other);
+        }
+        if (lane == 0) buckets[sb.bucket] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 5. bucket reduction.  For a slab of T * s items Q_t (s = 2^log_s per thread) a CTA of T threads produces
 //      A = sum_t (t + 1) Q_t ,   R = sum_t Q_t ,   E = sum_t X_t  (plain sum of a second array, optional)
@@ -314,8 +440,6 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_static(
 //    Level 2 (slabs > 1): one CTA per window over Q = R_g, X = A_g -> (A2, R2, E).
 //    Window sum  S = sum_k (k+1) B_k = sum_g A_g + slab * sum_g g R_g = E + slab * (A2 - R2)      [host, msm_finish_host]
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q) { xyzz_add(acc, q); }
-__device__ __noinline__ void xyzz_dbl_nl(xyzz_t& acc) { xyzz_dbl(acc, acc); }
 
 constexpr int REDUCE_THREADS = 256;
 
@@ -470,12 +594,24 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
                                          in.fixed_first, counts, offsets, entries);
     mark(3);
     // FIXED: every entry indexes the table, there is no tail
+    // oversized-bucket threshold: 4x the mean fill, at least 1024 entries (uniform scalars never reach it)
+    const uint64_t total_entries_max = (uint64_t)ntot * plan.W;
+    uint32_t split_len = (uint32_t)(4 * (total_entries_max / NB + 1));
+    if (split_len < 1024) split_len = 1024;
+    const uint32_t max_split_tasks = (uint32_t)(total_entries_max / split_len + 1) * 2 + 16;  // sum ceil(cnt/L) <= E/L + #split
+    const uint32_t max_split_buckets = (uint32_t)(total_entries_max / split_len + 1);
+    ws.split_ctrl.reserve(16);
+    ws.split_tasks.reserve((size_t)max_split_tasks * sizeof(SplitTask));
+    ws.split_buckets.reserve((size_t)max_split_buckets * sizeof(SplitBucket));
+    ws.split_partials.reserve((size_t)max_split_tasks * sizeof(xyzz_t));
+    uint32_t* split_ctrl = ws.split_ctrl.as<uint32_t>();
+    HALO_CUDA(cudaMemsetAsync(split_ctrl, 0, 16, st));
     // thread-per-bucket is ~8 % faster when buckets are deep and evenly filled (variable base, large n); lane-level
     // claiming wins everywhere else (measured: profiles/r01_accumulate_static_vs_dynamic.txt)
     const bool deep = !plan.fixed && (uint64_t)ntot * plan.W >= (uint64_t)NB * 256;
     if (ctx->tune_acc_static == 1 || (ctx->tune_acc_static == 0 && deep)) {
         k_accumulate_static<<<(NB + 127) / 128, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, offsets, entries,
-                                                             NB, buckets);
+                                                             NB, buckets, split_len);
     } else {
         // persistent lanes: enough CTAs to fill the machine, capped by the amount of work
         uint32_t want_blocks = (NB + 127) / 128;
@@ -483,7 +619,20 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
         uint32_t blocks = want_blocks < max_blocks ? want_blocks : max_blocks;
         uint32_t* next_bucket = counts + NB;  // spare slot at the end of the counter array (zeroed above)
         k_accumulate<<<blocks, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, offsets, entries, NB, buckets,
-                                             next_bucket);
+                                             next_bucket, split_len);
+    }
+    {
+        k_split_plan<<<(NB + 255) / 256, 256, 0, st>>>(offsets, NB, split_len, max_split_tasks, max_split_buckets, split_ctrl,
+                                                       ws.split_tasks.as<SplitTask>(), ws.split_buckets.as<SplitBucket>());
+        uint32_t sblocks = (uint32_t)ctx->sm_count * HALO_ACC_MIN_BLOCKS;
+        uint32_t cap = (max_split_tasks + 127) / 128;
+        if (sblocks > cap) sblocks = cap;
+        k_accumulate_split<<<sblocks, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, entries,
+                                                    ws.split_tasks.as<SplitTask>(), split_ctrl, ws.split_partials.as<xyzz_t>());
+        uint32_t mblocks = (max_split_buckets + 3) / 4;
+        if (mblocks > (uint32_t)ctx->sm_count * 4) mblocks = (uint32_t)ctx->sm_count * 4;
+        k_merge_split<<<mblocks, 128, 0, st>>>(ws.split_buckets.as<SplitBucket>(), split_ctrl, ws.split_partials.as<xyzz_t>(), buckets);
+        ctx->kernel_launches += 3;
     }
     mark(4);
     HALO_CUDA(cudaMemsetAsync(d_out, 0, (size_t)3 * nwin * sizeof(xyzz_t), st));

@@ -230,3 +230,38 @@ def test_msm_fixed_base_tables(ctx, oracle, c):
             assert O.pt_eq(ctx.msm_gens(sc), O.msm_affine(gs, sc, threads=8)), (c, name)
     finally:
         ctx.derive_generators(1 << 16)
+
+
+@pytest.mark.parametrize("fixed", [False, True])
+def test_msm_oversized_buckets(ctx, oracle, fixed):
+    """Degenerate digit distributions (every entry in a handful of buckets) go through the bucket-splitting path:
+    same result as the oracle, and no serial accumulation of a whole bucket by one lane."""
+    import time
+
+    O = oracle
+    n = 1 << 16
+    ctx.derive_generators(n)
+    try:
+        if fixed:
+            ctx.precompute_generators(0)
+        ctx.set_fixed_base(fixed)
+        gs = ctx.get_generators(0, n)
+        big = O.random_scalars(1, 5)[0]
+        cases = {
+            "all_equal": np.tile(big, (n, 1)),
+            "all_one": np.tile(O.to_mont([1])[0], (n, 1)),
+            "all_minus_one": np.tile(O.to_mont([R_MOD - 1])[0], (n, 1)),
+            "two_values": np.where((np.arange(n) % 3 == 0)[:, None], big[None, :], O.random_scalars(1, 6)[0][None, :]),
+            "small": O.to_mont([i % 5 for i in range(n)]),
+            "half_uniform_half_equal": np.concatenate([O.random_scalars(n // 2, 7), np.tile(big, (n // 2, 1))]),
+        }
+        for name, sc in cases.items():
+            sc = np.ascontiguousarray(sc, dtype=np.uint64)
+            t = time.perf_counter()
+            got = ctx.msm_gens(sc)
+            dt = time.perf_counter() - t
+            assert O.pt_eq(got, O.msm_affine(gs, sc, threads=8)), name
+            assert dt < 0.5, f"{name}: {dt:.3f} s -- oversized buckets are being accumulated serially"
+    finally:
+        ctx.set_fixed_base(True)
+        ctx.derive_generators(1 << 16)
