@@ -228,6 +228,13 @@ def run_ours(args):
         imad_peak = blocks * threads * iters * 16 / imad_ms / 1e9  # T IMAD32/s: dependent-multiplicand mad.lo.u32 chains
         alg_imad = n * CANON_W * 10 * IMAD_PER_MODMUL  # algorithmic IMAD32 of one k_accumulate launch (canonical c = 16)
         achieved = alg_imad / (phases["accumulate"] * 1e-3) / 1e12
+        traffic = None  # dram__bytes_read + dram__bytes_write of one k_accumulate launch, from the committed ncu capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_accumulate"]
+            if tj["workload"] == f"pallas_msm_2^{args.log_n}_per_gpu" and tj["fixed_base_tables"] == (not args.no_precompute):
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads_cpu = host_threads()
@@ -252,7 +259,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD32/s",
-                         "frac": achieved / imad_peak, "traffic": None,
+                         "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r01_traffic.json)",
                          "peak_source": "measured in this run (libhalo_b200 mad.lo.u32 microbenchmark, 16 independent chains per thread, all SMs); MEASURED_PEAKS.json has no integer-pipe figure. IMAD.WIDE / IMAD.HI issue at half this rate (profiles/r01_imad_pipe_rates.jsonl)",
                          "algorithmic": f"{n} pts x {CANON_W} windows x 10 modmul x {IMAD_PER_MODMUL} IMAD32 per launch",
                          "launch_ms": phases["accumulate"], "phases_ms": phases,
