@@ -111,6 +111,18 @@ class Context:
         self._chk(self._lib.halo_msm_gens(self._h, p64(s), C.c_uint64(off), C.c_uint64(s.shape[0]), p64(out)))
         return out
 
+    def msm_gens_submit(self, scalars, off=0):
+        """Pipelined halo_msm_gens: returns a ticket; `scalars` must stay alive (ideally pinned) until collect."""
+        s = arr(scalars).reshape(-1, 4)
+        t = C.c_int()
+        self._chk(self._lib.halo_msm_gens_submit(self._h, p64(s), C.c_uint64(off), C.c_uint64(s.shape[0]), C.byref(t)))
+        return t.value, s
+
+    def msm_gens_collect(self, ticket):
+        out = np.zeros(12, dtype=np.uint64)
+        self._chk(self._lib.halo_msm_gens_collect(self._h, int(ticket[0]), p64(out)))
+        return out
+
     def msm_gens_resident(self, d_ptr, n, off=0):
         out = np.zeros(12, dtype=np.uint64)
         self._chk(self._lib.halo_msm_gens_resident(self._h, C.c_void_p(d_ptr), C.c_uint64(off), C.c_uint64(n), p64(out)))

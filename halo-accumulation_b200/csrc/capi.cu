@@ -39,6 +39,18 @@ int set_error(halo_ctx* ctx, int code, const char* fmt, const char* a, const cha
 
 }  // namespace halo
 
+namespace halo {
+static void async_init(halo_ctx* ctx) {
+    if (ctx->copy_stream) return;
+    HALO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& s : ctx->slots) {
+        HALO_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+        HALO_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        HALO_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_parts), 3 * MSM_MAX_WINDOWS * sizeof(xyzz_t)));
+    }
+}
+}  // namespace halo
+
 #define HALO_TRY(ctx) \
     try {             \
         HALO_CUDA(cudaSetDevice((ctx)->device));
@@ -104,6 +116,13 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& s : ctx->slots) {
+        s.scalars.release();
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.h_parts) cudaFreeHost(s.h_parts);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -298,6 +317,63 @@ int halo_msm_gens(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t
     if (n) HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
     xyzz_t r;
     msm_gens_device(ctx, ctx->stage_scalars.as<fr_t>(), off, n, r);
+    out_jac_from_xyzz(r, out_jac);
+    HALO_CATCH(ctx)
+}
+
+int halo_msm_gens_submit(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t n, int* ticket) {
+    if (!ctx || !ticket || (!scalars && n)) return HALO_EINVAL;
+    if (off + n > ctx->n_gens) return fail(ctx, HALO_ESTATE, "halo_msm_gens_submit: range exceeds resident generators");
+    HALO_TRY(ctx)
+    async_init(ctx);
+    const int si = ctx->next_slot;
+    halo_ctx::AsyncSlot& s = ctx->slots[si];
+    if (s.active) return fail(ctx, HALO_ESTATE, "halo_msm_gens_submit: both pipeline slots are in flight; collect one first");
+    s.empty = n == 0;
+    if (!s.empty) {
+        s.scalars.reserve(n * sizeof(fr_t));
+        HALO_CUDA(cudaMemcpyAsync(s.scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        HALO_CUDA(cudaEventRecord(s.copied, ctx->copy_stream));
+        HALO_CUDA(cudaStreamWaitEvent(ctx->stream, s.copied, 0));
+        MsmInput in;
+        in.scalars = s.scalars.as<fr_t>();
+        in.n = (uint32_t)n;
+        const bool fixed = ctx->use_fixed && ctx->pre_n == ctx->n_gens && ctx->gens_pre.p && n >= (1u << 17) && n * 8 >= ctx->pre_n;
+        if (fixed) {
+            in.bases = ctx->gens_pre.as<affine_t>();
+            in.fixed_stride = (uint32_t)ctx->pre_n;
+            in.fixed_first = (uint32_t)off;
+            s.plan = ctx->pre_plan;
+        } else {
+            in.bases = ctx->gens.as<affine_t>() + off;
+            s.plan = msm_make_plan(n, ctx->force_c);
+        }
+        ctx->ws.wsums.reserve((size_t)6 * 3 * MSM_MAX_WINDOWS * sizeof(xyzz_t));
+        xyzz_t* d_parts = ctx->ws.wsums.as<xyzz_t>() + (size_t)(4 + si) * 3 * MSM_MAX_WINDOWS;  // slots 0-3 belong to msm_batch
+        msm_enqueue(ctx, in, s.plan, d_parts);
+        const int nwin = s.plan.fixed ? 1 : s.plan.W;
+        HALO_CUDA(cudaMemcpyAsync(s.h_parts, d_parts, (size_t)3 * nwin * sizeof(xyzz_t), cudaMemcpyDeviceToHost, ctx->stream));
+        HALO_CUDA(cudaEventRecord(s.done, ctx->stream));
+    }
+    s.active = true;
+    *ticket = si;
+    ctx->next_slot = si ^ 1;
+    HALO_CATCH(ctx)
+}
+
+int halo_msm_gens_collect(halo_ctx* ctx, int ticket, uint64_t out_jac[12]) {
+    if (!ctx || !out_jac || ticket < 0 || ticket > 1) return HALO_EINVAL;
+    halo_ctx::AsyncSlot& s = ctx->slots[ticket];
+    if (!s.active) return fail(ctx, HALO_ESTATE, "halo_msm_gens_collect: ticket not in flight");
+    HALO_TRY(ctx)
+    xyzz_t r;
+    if (s.empty) {
+        xyzz_set_inf(r);
+    } else {
+        HALO_CUDA(cudaEventSynchronize(s.done));
+        msm_finish_host(s.h_parts, s.plan, r);
+    }
+    s.active = false;
     out_jac_from_xyzz(r, out_jac);
     HALO_CATCH(ctx)
 }

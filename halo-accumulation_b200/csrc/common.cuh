@@ -113,6 +113,18 @@ struct halo_ctx {
     // costs tens of milliseconds
     halo::DevBuf ipa_G, ipa_cs, ipa_zs, ipa_pbar, ipa_tail;
     bool ipa_busy = false;
+    // asynchronous MSM pipeline (halo_msm_gens_submit / _collect): two in-flight slots, H2D on its own stream so the copy
+    // of call k+1 overlaps the kernels of call k
+    struct AsyncSlot {
+        halo::DevBuf scalars;
+        cudaEvent_t copied = nullptr, done = nullptr;
+        halo::xyzz_t* h_parts = nullptr;  // pinned
+        halo::MsmPlan plan;
+        bool active = false;
+        bool empty = false;
+    } slots[2];
+    cudaStream_t copy_stream = nullptr;
+    int next_slot = 0;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     int force_c = 0;

@@ -686,7 +686,7 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs) {
     constexpr int MAXB = 4, SLOT = 3 * MSM_MAX_WINDOWS;
     if (count > MAXB) throw CudaError{cudaErrorInvalidValue, "msm_batch: count > 4", __FILE__, __LINE__};
     MsmPlan plans[MAXB];
-    ctx->ws.wsums.reserve((size_t)MAXB * SLOT * sizeof(xyzz_t));
+    ctx->ws.wsums.reserve((size_t)6 * SLOT * sizeof(xyzz_t));  // 4 batch slots + 2 asynchronous pipeline slots
     xyzz_t* d_parts = ctx->ws.wsums.as<xyzz_t>();
     if (!ctx->pinned) {
         HALO_CUDA(cudaMallocHost(&ctx->pinned, (size_t)MAXB * SLOT * sizeof(xyzz_t)));

@@ -79,6 +79,9 @@ def emulate(prog, env):
         elif op == "shr":
             d, a, k = ins[1:]
             env[d] = val(a) >> k
+        elif op == "shf.l":  # funnel shift left: upper 32 bits of (hi:lo) << k
+            d, lo, hi, k = ins[1:]
+            env[d] = (((val(hi) << 32) | val(lo)) << k >> 32) & MASK
         elif op == "mov":
             d, a = ins[1:]
             env[d] = val(a)
@@ -110,6 +113,17 @@ def chain_mad(pg, acc, mults, scalar, carry_in, top, fresh_top):
         pg.emit("addc", top, top, 0)
 
 
+def chain_pairs(pg, acc, pairs, scalar, carry_in, top):
+    """acc[2k], acc[2k+1] += mult * scalar for (k, mult) in pairs (consecutive k up to 3), one carry chain -> top."""
+    first = True
+    for k, m in pairs:
+        lo, hi = acc[2 * k], acc[2 * k + 1]
+        pg.emit("madc.lo.cc" if (carry_in or not first) else "mad.lo.cc", lo, m, scalar, lo)
+        pg.emit("madc.hi.cc", hi, m, scalar, hi)
+        first = False
+    pg.emit("addc", top, top, 0)
+
+
 def build_mul(p, variant, square=False):
     """Returns a Prog computing r = a * b * 2^-256 mod p on registers a0..a7, b0..b7 -> r0..r7."""
     P = [(p >> (32 * i)) & MASK for i in range(8)]
@@ -121,9 +135,47 @@ def build_mul(p, variant, square=False):
     X = [pg.t("x") for _ in range(9)]
     Y = [pg.t("y") for _ in range(9)]
     stray = None
+    if square:
+        # limbs of 2a: d[j] = (a_j << 1) | (a_{j-1} >> 31); e[j] = a_j << 1 (no incoming bit)
+        d = {j: pg.t("d") for j in range(1, 8)}
+        e = {j: pg.t("e") for j in range(1, 8)}
+        for j in range(1, 8):
+            pg.emit("shf.l", d[j], a[j - 1], a[j], 1)
+            pg.emit("shl", e[j], a[j], 1)
+
+        def mult(i, j):  # multiplicand at relative position j of row i (j >= i): a_i^2 once, cross terms doubled
+            return a[i] if j == i else (e[j] if j == i + 1 else d[j])
     for i in range(8):
         bi = b[i]
-        if i == 0:
+        if square and i == 0:
+            for k in range(4):
+                pg.emit("mul.lo", X[2 * k], mult(0, 2 * k), bi)
+                pg.emit("mul.hi", X[2 * k + 1], mult(0, 2 * k), bi)
+                pg.emit("mul.lo", Y[2 * k], mult(0, 2 * k + 1), bi)
+                pg.emit("mul.hi", Y[2 * k + 1], mult(0, 2 * k + 1), bi)
+            pg.emit("mov", X[8], 0)
+            pg.emit("mov", Y[8], 0)
+        elif square:
+            # row i only holds the products a_i * (2a)_j with j >= i (a^2 = sum a_i^2 + 2 sum_{i<j} a_i a_j)
+            xp = [(j // 2, mult(i, j)) for j in range(i, 8) if j % 2 == 0]
+            yp = [((j - 1) // 2, mult(i, j)) for j in range(i, 8) if j % 2 == 1]
+            pg.emit("add.cc", X[0], X[0], stray)
+            if yp and yp[0][0] == 0:
+                chain_pairs(pg, Y, yp, bi, True, Y[8])  # the stray limb's carry enters Y[0] (relative position 1)
+                if xp:
+                    chain_pairs(pg, X, xp, bi, False, X[8])
+            else:
+                # the carry is absorbed by X[1] and rippled up to where the X chain starts
+                first_x = 2 * xp[0][0] if xp else 8
+                for l in range(1, first_x):
+                    pg.emit("addc.cc", X[l], X[l], 0)
+                if xp:
+                    chain_pairs(pg, X, xp, bi, True, X[8])
+                else:
+                    pg.emit("addc", X[8], X[8], 0)
+                if yp:
+                    chain_pairs(pg, Y, yp, bi, False, Y[8])
+        elif i == 0:
             for k in range(4):
                 pg.emit("mul.lo", X[2 * k], a[2 * k], bi)
                 pg.emit("mul.hi", X[2 * k + 1], a[2 * k], bi)
@@ -248,6 +300,8 @@ def to_ptx(pg, square):
             lines.append(f"selp.u32 {reg(ins[1])}, {reg(ins[2])}, {reg(ins[3])}, {ins[4]};")
         elif op in ("shl", "shr"):
             lines.append(f"{op}.b32 {reg(ins[1])}, {reg(ins[2])}, {ins[3]};" if op == "shl" else f"shr.u32 {reg(ins[1])}, {reg(ins[2])}, {ins[3]};")
+        elif op == "shf.l":
+            lines.append(f"shf.l.wrap.b32 {reg(ins[1])}, {reg(ins[2])}, {reg(ins[3])}, {ins[4]};")
         elif op == "mov":
             lines.append(f"mov.u32 {reg(ins[1])}, {reg(ins[2])};")
         else:

@@ -96,6 +96,12 @@ int halo_msm(halo_ctx *ctx, const uint64_t *bases_affine /*[n][8]*/, const uint8
 /* Same as group.rs:18-21 `point_dot`: Jacobian bases, normalised on the device (batched inversion). */
 int halo_msm_jac(halo_ctx *ctx, const uint64_t *bases_jac /*[n][12]*/, const uint64_t *scalars /*[n][4]*/, uint64_t n,
                  uint64_t out_jac[12]);
+/* Pipelined form of halo_msm_gens for streams of commitments (an IVC chain, a batch of polynomials): submit enqueues
+ * the host-to-device copy on a copy stream and the MSM behind it and returns at once; collect waits for that MSM and
+ * finishes it.  Two tickets may be in flight, so the copy of call k+1 overlaps the kernels of call k.  `scalars` must
+ * stay valid (and should be pinned) until the ticket is collected. */
+int halo_msm_gens_submit(halo_ctx *ctx, const uint64_t *scalars /*[n][4]*/, uint64_t off, uint64_t n, int *ticket);
+int halo_msm_gens_collect(halo_ctx *ctx, int ticket, uint64_t out_jac[12]);
 /* Device-resident variant for throughput measurement: d_scalars is a CUDA device pointer to n scalars. */
 int halo_msm_gens_resident(halo_ctx *ctx, const void *d_scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]);
 

@@ -265,3 +265,27 @@ def test_msm_oversized_buckets(ctx, oracle, fixed):
     finally:
         ctx.set_fixed_base(True)
         ctx.derive_generators(1 << 16)
+
+
+def test_msm_pipelined_submit_collect(ctx, oracle):
+    """halo_msm_gens_submit / _collect: two MSMs in flight give the same points as the blocking call and the oracle."""
+    O = oracle
+    n = 1 << 14
+    gs = ctx.get_generators(0, n)
+    scs = [O.random_scalars(n, 300 + k) for k in range(5)]
+    exp = [O.msm_affine(gs, sc, threads=8) for sc in scs]
+    got = []
+    t = ctx.msm_gens_submit(scs[0])
+    for k in range(len(scs)):
+        nxt = ctx.msm_gens_submit(scs[k + 1]) if k + 1 < len(scs) else None
+        got.append(ctx.msm_gens_collect(t))
+        t = nxt
+    for g, e in zip(got, exp):
+        assert O.pt_eq(g, e)
+    # a third submit without collecting is refused, not queued silently
+    import halo_accumulation_b200 as H
+    t0, t1 = ctx.msm_gens_submit(scs[0]), ctx.msm_gens_submit(scs[1])
+    with pytest.raises(H.HaloError):
+        ctx.msm_gens_submit(scs[2])
+    assert O.pt_eq(ctx.msm_gens_collect(t0), exp[0]) and O.pt_eq(ctx.msm_gens_collect(t1), exp[1])
+    assert O.pt_to_affine(ctx.msm_gens_collect(ctx.msm_gens_submit(np.zeros((0, 4), dtype=np.uint64))))[1]
