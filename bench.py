@@ -138,6 +138,8 @@ def run_ours(args):
     from halo_accumulation_b200 import parallel
 
     rank, world, local = dist_env()
+    if not os.path.exists(os.path.join(ROOT, "halo-accumulation_b200", "lib", "libhalo_b200.so")) and rank == 0:
+        H.build()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)

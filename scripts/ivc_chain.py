@@ -1,0 +1,40 @@
+"""BASELINE config 4: ASDL IVC chain -- k accumulation steps (random_instance + prover, benches/acc.rs:76-98) followed
+by the fast path (k verifiers + one decider, benches/acc.rs:64-74) at n = 2^lg.  Times each phase on the GPU path."""
+import json, sys, time
+import numpy as np
+sys.path.insert(0, ".")
+import halo_accumulation_b200 as H
+from halo_accumulation_b200 import acc, group, pcdl
+
+lg = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+n, d = 1 << lg, (1 << lg) - 1
+ctx = H.Context(0, n)
+t0 = time.perf_counter(); ctx.derive_generators(n); ctx.precompute_generators(0); setup_s = time.perf_counter() - t0
+rng = np.random.Generator(np.random.PCG64(3))
+def rs(m):
+    a = rng.integers(0, 1 << 64, size=(m, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 62) - 1); return a
+
+def random_instance():
+    dp = int(rng.integers(d // 2, d))            # benches/acc.rs:16
+    p, w, z, wb = rs(dp + 1), rs(1)[0], rs(1)[0], rs(1)[0]
+    Cm = pcdl.commit(ctx, p, d, w)
+    v = group.scalar_dot(ctx, p, group.construct_powers(ctx, z, dp + 1))
+    pi = pcdl.open(ctx, p, Cm, d, z, w, rs(dp), wb)
+    return acc.new_instance(Cm, d, z, v, pi)
+
+t_inst = t_prov = t_ver = 0.0
+a, qss, accs = None, [], []
+for s in range(k):
+    t = time.perf_counter(); q = random_instance(); t_inst += time.perf_counter() - t
+    qs = [acc.to_instance(a), q] if a is not None else [q]
+    t = time.perf_counter(); a = acc.prover(ctx, d, qs, rs(2), rs(1)[0], rs(n - 1), rs(1)[0]); t_prov += time.perf_counter() - t
+    qss.append(qs); accs.append(a)
+t = time.perf_counter()
+for qs, ac in zip(qss, accs):
+    acc.verifier(ctx, d, qs, ac)
+t_ver = time.perf_counter() - t
+t = time.perf_counter(); acc.decider(ctx, accs[-1]); t_dec = time.perf_counter() - t
+print(json.dumps({"config": f"ivc_chain_2^{lg}_k{k}", "setup_s": setup_s, "random_instance_ms": t_inst / k * 1e3, "prover_ms": t_prov / k * 1e3,
+                  "verifier_ms": t_ver / k * 1e3, "decider_ms": t_dec * 1e3, "fast_path_total_s": t_ver + t_dec,
+                  "chain_total_s": t_inst + t_prov, "kernel_launches": ctx.kernel_launches(), "all_accept": True}))
