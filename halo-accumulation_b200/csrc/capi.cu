@@ -108,7 +108,8 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     ctx->stage_scalars.release();
     ctx->stage_bases.release();
     ctx->stage_misc.release();
-    for (halo::DevBuf* b : {&ctx->ipa_G, &ctx->ipa_cs, &ctx->ipa_zs, &ctx->ipa_pbar, &ctx->ipa_tail}) b->release();
+    ctx->poly_dev.release();
+    for (halo::DevBuf* b : {&ctx->ipa_G, &ctx->ipa_cs, &ctx->ipa_zs, &ctx->ipa_pbar, &ctx->ipa_tail, &ctx->ipa_frozen}) b->release();
     MsmWorkspace& ws = ctx->ws;
     for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,
                       &ws.task_bucket, &ws.task_partial, &ws.split_ctrl, &ws.split_tasks, &ws.split_buckets, &ws.split_partials})
@@ -491,23 +492,59 @@ int halo_h_msm(halo_ctx* ctx, const uint64_t* xis, uint32_t lg_n, uint64_t out_j
     HALO_CATCH(ctx)
 }
 
-int halo_h_lincomb(halo_ctx* ctx, const uint64_t* h0, uint64_t n_h0, const uint64_t* alphas, const uint64_t* xis, uint64_t m,
-                   uint32_t lg_n, uint64_t* out) {
-    if (!ctx || !out || (!h0 && n_h0) || ((!alphas || !xis) && m)) return HALO_EINVAL;
+// out != NULL: coefficients to the host.  out == NULL: the polynomial stays on the device (ctx->poly_dev) and
+// *degree_out receives its degree (DensePolynomial::degree: index of the highest non-zero coefficient).
+static int h_lincomb_impl(halo_ctx* ctx, const uint64_t* h0, uint64_t n_h0, const uint64_t* alphas, const uint64_t* xis,
+                          uint64_t m, uint32_t lg_n, uint64_t* out, uint64_t* degree_out) {
+    if (!ctx || (!out && !degree_out) || (!h0 && n_h0) || ((!alphas || !xis) && m)) return HALO_EINVAL;
     if (int rc = check_lg(ctx, lg_n, false)) return rc;
     uint64_t n = (uint64_t)1 << lg_n;
     if (n_h0 > n) return fail(ctx, HALO_EINVAL, "halo_h_lincomb: h_0 longer than n");
     HALO_TRY(ctx)
-    ctx->stage_scalars.reserve(n * sizeof(fr_t));
-    fr_t* d = ctx->stage_scalars.as<fr_t>();
+    DevBuf& buf = out ? ctx->stage_scalars : ctx->poly_dev;
+    buf.reserve(n * sizeof(fr_t));
+    fr_t* d = buf.as<fr_t>();
     HALO_CUDA(cudaMemsetAsync(d, 0, n * sizeof(fr_t), ctx->stream));
     if (n_h0) HALO_CUDA(cudaMemcpyAsync(d, h0, n_h0 * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
     const fr_t* al = reinterpret_cast<const fr_t*>(alphas);
     const fr_t* xs = reinterpret_cast<const fr_t*>(xis);
     for (uint64_t i = 0; i < m; i++) vec_h_expand(ctx, xs + i * (lg_n + 1), (int)lg_n, al[i + 1], true, d);  // acc.rs:90-92
-    HALO_CUDA(cudaMemcpyAsync(out, d, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
-    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out) {
+        HALO_CUDA(cudaMemcpyAsync(out, d, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+        HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+        // degree: scan down from the top in chunks (the leading coefficient is non-zero except with negligible probability)
+        ctx->poly_n = n;
+        uint64_t hi = n, deg = 0;
+        bool found = false;
+        std::vector<fr_t> chunk(64);
+        while (hi > 0 && !found) {
+            uint64_t lo = hi > 64 ? hi - 64 : 0;
+            HALO_CUDA(cudaMemcpyAsync(chunk.data(), d + lo, (hi - lo) * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+            HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (uint64_t i = hi; i-- > lo;)
+                if (!fp_is_zero(chunk[i - lo])) {
+                    deg = i;
+                    found = true;
+                    break;
+                }
+            hi = lo;
+        }
+        *degree_out = deg;
+    }
     HALO_CATCH(ctx)
+}
+
+int halo_h_lincomb(halo_ctx* ctx, const uint64_t* h0, uint64_t n_h0, const uint64_t* alphas, const uint64_t* xis, uint64_t m,
+                   uint32_t lg_n, uint64_t* out) {
+    if (!out) return HALO_EINVAL;
+    return h_lincomb_impl(ctx, h0, n_h0, alphas, xis, m, lg_n, out, nullptr);
+}
+
+int halo_h_lincomb_resident(halo_ctx* ctx, const uint64_t* h0, uint64_t n_h0, const uint64_t* alphas, const uint64_t* xis,
+                            uint64_t m, uint32_t lg_n, uint64_t* degree_out) {
+    if (!degree_out) return HALO_EINVAL;
+    return h_lincomb_impl(ctx, h0, n_h0, alphas, xis, m, lg_n, nullptr, degree_out);
 }
 
 }  // extern "C"

@@ -109,9 +109,11 @@ struct halo_ctx {
     // scratch
     halo::MsmWorkspace ws;
     halo::DevBuf stage_scalars, stage_bases, stage_misc;
+    halo::DevBuf poly_dev;  // polynomial left on the device by halo_h_lincomb_resident for halo_ipa_begin_resident
+    uint64_t poly_n = 0;
     // buffers of the (single) in-flight PCDL opening, kept across openings: cudaMalloc / cudaFree of 100+ MB per open
     // costs tens of milliseconds
-    halo::DevBuf ipa_G, ipa_cs, ipa_zs, ipa_pbar, ipa_tail;
+    halo::DevBuf ipa_G, ipa_cs, ipa_zs, ipa_pbar, ipa_tail, ipa_frozen;
     bool ipa_busy = false;
     // asynchronous MSM pipeline (halo_msm_gens_submit / _collect): two in-flight slots, H2D on its own stream so the copy
     // of call k+1 overlaps the kernels of call k

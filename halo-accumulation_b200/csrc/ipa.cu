@@ -21,6 +21,11 @@ using namespace halo;
 
 namespace halo {
 
+#ifndef HALO_IPA_FREEZE_LEN
+#define HALO_IPA_FREEZE_LEN 8192
+#endif
+constexpr uint64_t IPA_FREEZE_LEN = HALO_IPA_FREEZE_LEN;
+
 // ---- GLV: xi * P = k1 * P + k2 * phi(P), phi(x, y) = (beta x, y) = lambda * P, |k1|, |k2| < 2^129 ------------------
 // Pallas has j-invariant 0, so Fq contains a primitive cube root of unity beta and Fr the matching lambda
 // (lambda * (x, y) = (beta x, y); pair fixed by checking lambda * G on the generator).  The shared challenge of a
@@ -63,6 +68,48 @@ __global__ void __launch_bounds__(128) k_fold_points(affine_t* __restrict__ G, u
     affine_t out;
     xyzz_to_affine(out, acc);
     G[j] = out;
+}
+
+// ---- frozen tail: once the vectors are short the generators stop being folded -------------------------------------
+// Folding m elements costs one ~2300-modmul serial chain per element no matter how small m is (about a millisecond of
+// latency per round), so for the last rounds the generator vector is frozen at G0 = G^(r0) (M0 elements) and only the
+// coefficient s_j with which G0_j enters the current folded generator is tracked (s_j <- xi s_j when j falls in the high
+// half, pcdl.rs:218 unrolled).  Then, with cur the logical length and m = cur / 2,
+//   L = <c_hi, G_lo> = sum_{j: j mod cur <  m} c[(j mod cur) + m] s_j G0_j ,
+//   R = <c_lo, G_hi> = sum_{j: j mod cur >= m} c[(j mod cur) - m] s_j G0_j ,   U = sum_j s_j G0_j
+// are MSMs over the fixed affine vector G0: same group elements as folding, without the folds.
+__global__ void __launch_bounds__(256) k_frozen_scalars(const fr_t* __restrict__ c, const fr_t* __restrict__ s, uint32_t M0,
+                                                        uint32_t cur, fr_t* __restrict__ tL, fr_t* __restrict__ tR) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M0) return;
+    const uint32_t m = cur >> 1, jj = j & (cur - 1);
+    fr_t zero, v;
+    fp_zero(zero);
+    if (jj < m) {
+        fp_mul(v, c[jj + m], s[j]);
+        tL[j] = v;
+        tR[j] = zero;
+    } else {
+        fp_mul(v, c[jj - m], s[j]);
+        tL[j] = zero;
+        tR[j] = v;
+    }
+}
+__global__ void __launch_bounds__(256) k_frozen_fold_s(fr_t* __restrict__ s, uint32_t M0, uint32_t cur, fr_t xi) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M0) return;
+    if ((j & (cur - 1)) >= (cur >> 1)) {
+        fr_t v = s[j];
+        fp_mul(v, v, xi);
+        s[j] = v;
+    }
+}
+__global__ void __launch_bounds__(256) k_fill_one(fr_t* __restrict__ s, uint32_t n) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    fr_t one;
+    fp_one(one);
+    s[j] = one;
 }
 
 // ---- host: decomposition and NAF ---------------------------------------------------------------------------------
@@ -194,9 +241,9 @@ static inline bool is_pow2(uint64_t n) { return n && !(n & (n - 1)); }
 
 extern "C" {
 
-int halo_ipa_begin(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, uint64_t n, const uint64_t z[4], halo_ipa** out,
-                   uint64_t v_out[4]) {
-    if (!ctx || !out || !z || (!coeffs && n_coeffs)) return HALO_EINVAL;
+static int ipa_begin_impl(halo_ctx* ctx, const uint64_t* coeffs, bool resident, uint64_t n_coeffs, uint64_t n, const uint64_t z[4],
+                          halo_ipa** out, uint64_t v_out[4]) {
+    if (!ctx || !out || !z || (!coeffs && !resident && n_coeffs)) return HALO_EINVAL;
     *out = nullptr;
     if (!is_pow2(n) || n > ctx->n_gens || n_coeffs > n) {  // pcdl.rs:128-132
         ctx->last_error = "halo_ipa_begin: n must be a power of two <= resident generators and >= n_coeffs";
@@ -220,7 +267,9 @@ int halo_ipa_begin(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, uin
         cudaStream_t s = ctx->stream;
         HALO_CUDA(cudaMemcpyAsync(ctx->ipa_G.p, ctx->gens.p, n * sizeof(affine_t), cudaMemcpyDeviceToDevice, s));  // pcdl.rs:185
         HALO_CUDA(cudaMemsetAsync(ctx->ipa_cs.p, 0, n * sizeof(fr_t), s));                                         // pcdl.rs:183-184
-        if (n_coeffs) HALO_CUDA(cudaMemcpyAsync(ctx->ipa_cs.p, coeffs, n_coeffs * sizeof(fr_t), cudaMemcpyHostToDevice, s));
+        if (n_coeffs)
+            HALO_CUDA(cudaMemcpyAsync(ctx->ipa_cs.p, resident ? ctx->poly_dev.p : (const void*)coeffs, n_coeffs * sizeof(fr_t),
+                                      resident ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
         vec_powers(ctx, st->z, n, ctx->ipa_zs.as<fr_t>());  // pcdl.rs:186
         if (v_out) {                                   // v = p(z) = <c, z-powers>  (pcdl.rs:135)
             fr_t* scal = reinterpret_cast<fr_t*>(reinterpret_cast<char*>(ctx->ipa_tail.p) + sizeof(affine_t));
@@ -236,6 +285,19 @@ int halo_ipa_begin(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, uin
     ctx->ipa_busy = true;
     *out = st;
     return HALO_OK;
+}
+
+int halo_ipa_begin(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, uint64_t n, const uint64_t z[4], halo_ipa** out,
+                   uint64_t v_out[4]) {
+    return ipa_begin_impl(ctx, coeffs, false, n_coeffs, n, z, out, v_out);
+}
+
+int halo_ipa_begin_resident(halo_ctx* ctx, uint64_t n, const uint64_t z[4], halo_ipa** out, uint64_t v_out[4]) {
+    if (!ctx || ctx->poly_n == 0 || ctx->poly_n > n) {
+        if (ctx) ctx->last_error = "halo_ipa_begin_resident: no resident polynomial (call halo_h_lincomb_resident first)";
+        return HALO_ESTATE;
+    }
+    return ipa_begin_impl(ctx, nullptr, true, ctx->poly_n, n, z, out, v_out);
 }
 
 void halo_ipa_destroy(halo_ipa* st) {
@@ -307,13 +369,32 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
     fr_t* scal = reinterpret_cast<fr_t*>(reinterpret_cast<char*>(ctx->ipa_tail.p) + sizeof(affine_t));
     vec_dot(ctx, c + m, z, m, scal + 2, scal);          // dot_l = <c_r, z_l>
     vec_dot(ctx, c, z + m, m, scal + 2, scal + 1);      // dot_r = <c_l, z_r>
+    if (!st->frozen && st->cur <= IPA_FREEZE_LEN) {     // freeze the generator vector (see k_frozen_scalars)
+        st->frozen = true;
+        st->M0 = (uint32_t)st->cur;
+        ctx->ipa_frozen.reserve((size_t)3 * st->M0 * sizeof(fr_t));
+        k_fill_one<<<(st->M0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ipa_frozen.as<fr_t>(), st->M0);
+        ctx->kernel_launches++;
+    }
     MsmInput in[2];
-    in[0].bases = G;       // L = <c_r, g_l> + dot_l H'
-    in[0].scalars = c + m;
-    in[1].bases = G + m;   // R = <c_l, g_r> + dot_r H'
-    in[1].scalars = c;
+    if (st->frozen) {
+        fr_t* sv = ctx->ipa_frozen.as<fr_t>();
+        fr_t* tL = sv + st->M0;
+        fr_t* tR = tL + st->M0;
+        k_frozen_scalars<<<(st->M0 + 255) / 256, 256, 0, ctx->stream>>>(c, sv, st->M0, (uint32_t)st->cur, tL, tR);
+        ctx->kernel_launches++;
+        in[0].bases = G;
+        in[0].scalars = tL;
+        in[1].bases = G;
+        in[1].scalars = tR;
+    } else {
+        in[0].bases = G;       // L = <c_r, g_l> + dot_l H'
+        in[0].scalars = c + m;
+        in[1].bases = G + m;   // R = <c_l, g_r> + dot_r H'
+        in[1].scalars = c;
+    }
     for (int k = 0; k < 2; k++) {
-        in[k].n = (uint32_t)m;
+        in[k].n = st->frozen ? st->M0 : (uint32_t)m;
         in[k].tail_bases = Hp;
         in[k].tail_scalars = scal + k;
         in[k].n_tail = 1;
@@ -340,9 +421,13 @@ int halo_ipa_round_fold(halo_ipa* st, const uint64_t xi[4], const uint64_t xi_in
     fr_t x, xinv;
     memcpy(&x, xi, 32);
     memcpy(&xinv, xi_inv, 32);
-    GlvDigits dg;
-    make_glv(x, dg);
-    k_fold_points<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_G.as<affine_t>(), m, dg);
+    if (st->frozen) {
+        k_frozen_fold_s<<<(st->M0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ipa_frozen.as<fr_t>(), st->M0, (uint32_t)st->cur, x);
+    } else {
+        GlvDigits dg;
+        make_glv(x, dg);
+        k_fold_points<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_G.as<affine_t>(), m, dg);
+    }
     ctx->kernel_launches++;
     HALO_CUDA(cudaGetLastError());
     vec_fold_scalars(ctx, ctx->ipa_cs.as<fr_t>(), ctx->ipa_zs.as<fr_t>(), m, x, xinv);
@@ -359,12 +444,17 @@ int halo_ipa_finish(halo_ipa* st, uint64_t U_jac[12], uint64_t c_out[4]) {
         return HALO_ESTATE;
     }
     IPA_TRY(st)
-    affine_t u;
-    HALO_CUDA(cudaMemcpyAsync(&u, ctx->ipa_G.p, sizeof u, cudaMemcpyDeviceToHost, ctx->stream));
-    HALO_CUDA(cudaMemcpyAsync(c_out, ctx->ipa_cs.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
     xyzz_t x;
-    xyzz_from_affine(x, u);
+    if (st->frozen) {  // U = sum_j s_j G0_j
+        HALO_CUDA(cudaMemcpyAsync(c_out, ctx->ipa_cs.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        msm_device(ctx, ctx->ipa_G.as<affine_t>(), ctx->ipa_frozen.as<fr_t>(), st->M0, x);
+    } else {
+        affine_t u;
+        HALO_CUDA(cudaMemcpyAsync(&u, ctx->ipa_G.p, sizeof u, cudaMemcpyDeviceToHost, ctx->stream));
+        HALO_CUDA(cudaMemcpyAsync(c_out, ctx->ipa_cs.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+        xyzz_from_affine(x, u);
+    }
     jac_t j;
     xyzz_to_jac(j, x);
     memcpy(U_jac, &j, 96);  // U = G_(lg n)[0]  (pcdl.rs:230)

@@ -15,4 +15,6 @@ struct halo_ipa {
     // coefficient and z-power vectors (pcdl.rs:183-186), pbar = hiding polynomial (pcdl.rs:140-142),
     // tail = [affine H'] then [fr dot_l, fr dot_r] and dot partials
     bool have_pbar = false;
+    bool frozen = false;  // generator vector frozen at M0 elements (ctx->ipa_frozen holds s, tL, tR)
+    uint32_t M0 = 0;
 };

@@ -27,6 +27,22 @@ PallasPoly AccumulatedHPolys::get_poly(halo_ctx* ctx, uint32_t lg_n) const {
     return out;
 }
 
+uint64_t AccumulatedHPolys::get_poly_resident(halo_ctx* ctx, uint32_t lg_n) const {
+    size_t n = (size_t)1 << lg_n;
+    std::vector<PallasScalar> xis;
+    xis.reserve(hs.size() * (lg_n + 1));
+    for (const auto& h : hs) {
+        ensure(h.xis.size() == lg_n + 1, HALO_EINVAL, "HPoly size mismatch");
+        xis.insert(xis.end(), h.xis.begin(), h.xis.end());
+    }
+    size_t n_h0 = have_h0 ? (h_0.size() < n ? h_0.size() : n) : 0;
+    uint64_t deg = 0;
+    check_rc(ctx, halo_h_lincomb_resident(ctx, reinterpret_cast<const uint64_t*>(h_0.data()), n_h0,
+                                          reinterpret_cast<const uint64_t*>(alphas.data()),
+                                          reinterpret_cast<const uint64_t*>(xis.data()), hs.size(), lg_n, &deg));
+    return deg;
+}
+
 PallasScalar AccumulatedHPolys::eval(const PallasScalar& z) const {
     PallasScalar v = scalar_zero();
     if (have_h0) {  // h_0.evaluate(z), Horner
@@ -102,7 +118,7 @@ static CommonOut common_subroutine(halo_ctx* ctx, uint64_t d, const std::vector<
 }
 
 Accumulator prover(halo_ctx* ctx, uint64_t d, const std::vector<Instance>& qs, const PallasPoly& h_0, const PallasScalar& w,
-                   const PallasPoly& q, const PallasScalar& w_bar) {
+                   PolyView q, const PallasScalar& w_bar) {
     ensure(h_0.size() == 2, HALO_EINVAL, "h_0 must be PallasPoly::rand(1): two coefficients");  // :192
     // U_0 = PCDL.Commit(h_0, d, None) (:195)
     PallasPoint U_0 = pcdl::commit(ctx, h_0, d, nullptr);
@@ -110,8 +126,9 @@ Accumulator prover(halo_ctx* ctx, uint64_t d, const std::vector<Instance>& qs, c
     CommonOut c = common_subroutine(ctx, d, qs, pi_V);  // :202
     PallasScalar v = c.hs.eval(c.z);                    // :205
     // pi = PCDL.Open(h(X), C_bar, d, z; w) (:209)
-    PallasPoly hpoly = c.hs.get_poly(ctx, ilog2(d + 1));
-    pcdl::EvalProof pi = pcdl::open(ctx, hpoly, c.C_bar, d, c.z, &w, &q, &w_bar);
+    // h.get_poly() (:85-94) is expanded on the device and opened from there
+    uint64_t deg = c.hs.get_poly_resident(ctx, ilog2(d + 1));
+    pcdl::EvalProof pi = pcdl::open_resident(ctx, deg, c.C_bar, d, c.z, &w, &q, &w_bar);
     return Accumulator{c.C_bar, c.d, c.z, v, pi, pi_V};  // :212-219
 }
 

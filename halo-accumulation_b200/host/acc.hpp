@@ -45,13 +45,14 @@ struct AccumulatedHPolys {
         have_alpha = true;
     }
     PallasPoly get_poly(halo_ctx* ctx, uint32_t lg_n) const;  // :85-94, on the device
+    uint64_t get_poly_resident(halo_ctx* ctx, uint32_t lg_n) const;  // same, left on the device; returns the degree
     PallasScalar eval(const PallasScalar& z) const;           // :97-106
     void serialize(Transcript& t) const;                      // #[derive(CanonicalSerialize)] (:61)
 };
 
 // acc.rs:190-220; rng draws explicit in the reference's order: h_0 (2 coefficients, :192), w (:198), open's q, w_bar
 Accumulator prover(halo_ctx* ctx, uint64_t d, const std::vector<Instance>& qs, const PallasPoly& h_0, const PallasScalar& w,
-                   const PallasPoly& q, const PallasScalar& w_bar);
+                   PolyView q, const PallasScalar& w_bar);
 // acc.rs:223-243
 void verifier(halo_ctx* ctx, uint64_t D, const std::vector<Instance>& qs, const Accumulator& acc);
 // acc.rs:245-255

@@ -25,11 +25,7 @@ int guarded(F&& f) {
         return HALO_EINVAL;
     }
 }
-PallasPoly poly_from(const uint64_t* c, uint64_t n) {
-    PallasPoly p(n);
-    if (n) std::memcpy(p.data(), c, n * 32);
-    return p;
-}
+PolyView poly_from(const uint64_t* c, uint64_t n) { return PolyView(reinterpret_cast<const PallasScalar*>(c), n); }
 }  // namespace
 
 extern "C" {
@@ -59,7 +55,7 @@ int halo_pcdl_open(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, con
                    halo_eval_proof* pi) {
     return guarded([&] {
         PallasScalar ws, wbs;
-        PallasPoly qp;
+        PolyView qp(nullptr, 0);
         if (w) {
             ensure(q && w_bar, HALO_EINVAL, "hiding open needs q and w_bar");
             ws = scalar_load(w);

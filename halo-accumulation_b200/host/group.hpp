@@ -23,6 +23,15 @@ struct PallasPoint {  // Projective; kept as XYZZ on the host, Jacobian on the w
     xyzz_t p;
 };
 using PallasPoly = std::vector<PallasScalar>;  // DensePolynomial coefficients, low degree first
+struct PolyView {  // borrowed coefficients (no copy of 32 n bytes at the C boundary)
+    const PallasScalar* data_;
+    size_t size_;
+    PolyView(const PallasScalar* d, size_t n) : data_(d), size_(n) {}
+    PolyView(const PallasPoly& p) : data_(p.data()), size_(p.size()) {}
+    const PallasScalar* data() const { return data_; }
+    size_t size() const { return size_; }
+    const PallasScalar& operator[](size_t i) const { return data_[i]; }
+};
 
 struct HaloFailure : std::runtime_error {  // carries a HALO_E* / HALO_REJECT_* code; the analogue of panic / Err
     int code;

@@ -13,7 +13,7 @@ static uint32_t ilog2(uint64_t n) {
     while (((uint64_t)1 << (l + 1)) <= n) l++;
     return l;
 }
-static uint64_t degree(const PallasPoly& p) {  // DensePolynomial::degree (trailing zeros trimmed)
+static uint64_t degree(PolyView p) {  // DensePolynomial::degree (trailing zeros trimmed)
     uint64_t n = p.size();
     while (n > 0 && fp_is_zero(p[n - 1])) n--;
     return n ? n - 1 : 0;
@@ -38,7 +38,7 @@ PallasScalar HPoly::eval(const PallasScalar& z) const {
     return v;
 }
 
-PallasPoint commit(halo_ctx* ctx, const PallasPoly& p, uint64_t d, const PallasScalar* w) {
+PallasPoint commit(halo_ctx* ctx, PolyView p, uint64_t d, const PallasScalar* w) {
     uint64_t n = d + 1;
     ensure(is_pow2(n), HALO_EINVAL, "d+1 is not a power of 2");  // pcdl.rs:102
     ensure(degree(p) <= d, HALO_EINVAL, "p.degree() > d");       // pcdl.rs:103
@@ -48,11 +48,22 @@ PallasPoint commit(halo_ctx* ctx, const PallasPoly& p, uint64_t d, const PallasS
     return pedersen::commit(ctx, w, nullptr, n, p.data(), n_coeffs, true);
 }
 
-EvalProof open(halo_ctx* ctx, const PallasPoly& p, const PallasPoint& C, uint64_t d, const PallasScalar& z,
-               const PallasScalar* w, const PallasPoly* q, const PallasScalar* w_bar) {
+static EvalProof open_impl(halo_ctx* ctx, const PolyView* p, uint64_t deg, const PallasPoint& C, uint64_t d, const PallasScalar& z,
+                           const PallasScalar* w, const PolyView* q, const PallasScalar* w_bar);
+
+EvalProof open(halo_ctx* ctx, PolyView p, const PallasPoint& C, uint64_t d, const PallasScalar& z, const PallasScalar* w,
+               const PolyView* q, const PallasScalar* w_bar) {
+    return open_impl(ctx, &p, degree(p), C, d, z, w, q, w_bar);
+}
+EvalProof open_resident(halo_ctx* ctx, uint64_t deg, const PallasPoint& C, uint64_t d, const PallasScalar& z,
+                        const PallasScalar* w, const PolyView* q, const PallasScalar* w_bar) {
+    return open_impl(ctx, nullptr, deg, C, d, z, w, q, w_bar);
+}
+
+static EvalProof open_impl(halo_ctx* ctx, const PolyView* p, uint64_t deg, const PallasPoint& C, uint64_t d, const PallasScalar& z,
+                           const PallasScalar* w, const PolyView* q, const PallasScalar* w_bar) {
     uint64_t n = d + 1;
     ensure(is_pow2(n), HALO_EINVAL, "d+1 is not a power of 2");  // pcdl.rs:130
-    uint64_t deg = degree(p);
     ensure(deg <= d, HALO_EINVAL, "p.degree() > d");             // pcdl.rs:131
     ensure(n <= halo_num_generators(ctx), HALO_EINVAL, "d > D");  // pcdl.rs:132
     uint32_t lg_n = ilog2(n);
@@ -62,9 +73,13 @@ EvalProof open(halo_ctx* ctx, const PallasPoly& p, const PallasPoint& C, uint64_
     // device state: c (zero padded), G, z-powers; v = p(z) (pcdl.rs:135, :183-186)
     halo_ipa* st = nullptr;
     uint64_t vbuf[4];
-    uint64_t n_coeffs = p.size() < n ? p.size() : n;
-    check_rc(ctx, halo_ipa_begin(ctx, reinterpret_cast<const uint64_t*>(p.data()), n_coeffs, n,
-                                 reinterpret_cast<const uint64_t*>(&z), &st, vbuf));
+    if (p) {
+        uint64_t n_coeffs = p->size() < n ? p->size() : n;
+        check_rc(ctx, halo_ipa_begin(ctx, reinterpret_cast<const uint64_t*>(p->data()), n_coeffs, n,
+                                     reinterpret_cast<const uint64_t*>(&z), &st, vbuf));
+    } else {
+        check_rc(ctx, halo_ipa_begin_resident(ctx, n, reinterpret_cast<const uint64_t*>(&z), &st, vbuf));
+    }
     struct Guard {
         halo_ipa* s;
         ~Guard() { halo_ipa_destroy(s); }

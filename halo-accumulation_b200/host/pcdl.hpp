@@ -27,10 +27,13 @@ struct HPoly {
 };
 
 // pcdl.rs:99-110
-PallasPoint commit(halo_ctx* ctx, const PallasPoly& p, uint64_t d, const PallasScalar* w);
+PallasPoint commit(halo_ctx* ctx, PolyView p, uint64_t d, const PallasScalar* w);
 // pcdl.rs:120-242; rng draws made explicit: q (deg p coefficients), w_bar
-EvalProof open(halo_ctx* ctx, const PallasPoly& p, const PallasPoint& C, uint64_t d, const PallasScalar& z,
-               const PallasScalar* w, const PallasPoly* q, const PallasScalar* w_bar);
+EvalProof open(halo_ctx* ctx, PolyView p, const PallasPoint& C, uint64_t d, const PallasScalar& z, const PallasScalar* w,
+               const PolyView* q, const PallasScalar* w_bar);
+// Same for a polynomial of degree `deg` that already sits on the device (halo_h_lincomb_resident): acc.rs:209.
+EvalProof open_resident(halo_ctx* ctx, uint64_t deg, const PallasPoint& C, uint64_t d, const PallasScalar& z,
+                        const PallasScalar* w, const PolyView* q, const PallasScalar* w_bar);
 // pcdl.rs:252-314; throws HaloFailure(HALO_REJECT_SUCCINCT) on reject
 std::pair<HPoly, PallasPoint> succinct_check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z,
                                              const PallasScalar& v, const EvalProof& pi);

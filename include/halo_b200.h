@@ -132,12 +132,19 @@ int halo_h_msm(halo_ctx *ctx, const uint64_t *xis /*[lg_n+1][4]*/, uint32_t lg_n
 int halo_h_lincomb(halo_ctx *ctx, const uint64_t *h0 /*[n_h0][4]*/, uint64_t n_h0, const uint64_t *alphas /*[m+1][4]*/,
                    const uint64_t *xis /*[m][lg_n+1][4]*/, uint64_t m, uint32_t lg_n, uint64_t *out /*[2^lg_n][4]*/);
 
+/* Same, but the polynomial stays on the device for a following halo_ipa_begin_resident (acc.rs:209 opens h.get_poly():
+ * no reason to move 32 n bytes to the host and back); *degree_out = its degree (DensePolynomial::degree). */
+int halo_h_lincomb_resident(halo_ctx *ctx, const uint64_t *h0, uint64_t n_h0, const uint64_t *alphas, const uint64_t *xis,
+                            uint64_t m, uint32_t lg_n, uint64_t *degree_out);
+
 /* ---- K3 / K4 / K7: the rounds of PCDL.open (pcdl.rs:183-231) ----------------------------------------- */
 typedef struct halo_ipa halo_ipa;
 /* Uploads the coefficients of p (zero-padded to n, pcdl.rs:183-184), copies GS[0..n) (pcdl.rs:185), builds
  * (1, z, .., z^{n-1}) on the device (pcdl.rs:186) and returns v = p(z) (pcdl.rs:135). */
 int halo_ipa_begin(halo_ctx *ctx, const uint64_t *coeffs /*[n_coeffs][4]*/, uint64_t n_coeffs, uint64_t n,
                    const uint64_t z[4], halo_ipa **out, uint64_t v_out[4]);
+/* halo_ipa_begin on the polynomial left on the device by halo_h_lincomb_resident. */
+int halo_ipa_begin_resident(halo_ctx *ctx, uint64_t n, const uint64_t z[4], halo_ipa **out, uint64_t v_out[4]);
 void halo_ipa_destroy(halo_ipa *st);
 /* Hiding (pcdl.rs:137-164): p_bar = q (X - z) on the device, returns <GS, p_bar> (the caller adds w_bar * S). */
 int halo_ipa_blind_commit(halo_ipa *st, const uint64_t *q /*[n_q][4]*/, uint64_t n_q, uint64_t out_jac[12]);

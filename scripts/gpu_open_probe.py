@@ -22,8 +22,8 @@ for rep in range(2):
     assert lib.halo_ipa_set_hprime(st, p64(Hh)) == 0
     rows = []
     L, R = np.zeros(12, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
-    xi, xinv = rs(1)[0], rs(1)[0]
     for r in range(lg):
+        xi, xinv = rs(1)[0], rs(1)[0]  # a fresh challenge per round, as the transcript produces
         t1 = time.perf_counter(); assert lib.halo_ipa_round_lr(st, p64(L), p64(R)) == 0
         t2 = time.perf_counter(); assert lib.halo_ipa_round_fold(st, p64(xi), p64(xinv)) == 0
         # fold is asynchronous: force completion for timing
