@@ -124,6 +124,70 @@ inline void serialize_compressed(const PallasPoint& a, uint8_t out[33]) {
     if (gt) out[32] = 0x80;
 }
 
+// Montgomery's trick: all inverses for one field inversion (zero entries stay zero).
+template <class P>
+inline void batch_inverse(std::vector<fp_t<P>>& v) {
+    std::vector<fp_t<P>> prefix(v.size());
+    fp_t<P> acc;
+    fp_one(acc);
+    for (size_t i = 0; i < v.size(); i++) {
+        prefix[i] = acc;
+        if (!fp_is_zero(v[i])) fp_mul(acc, acc, v[i]);
+    }
+    fp_t<P> inv;
+    fp_inv(inv, acc);
+    for (size_t i = v.size(); i-- > 0;) {
+        if (fp_is_zero(v[i])) continue;
+        fp_t<P> t;
+        fp_mul(t, inv, prefix[i]);
+        fp_mul(inv, inv, v[i]);
+        v[i] = t;
+    }
+}
+// Normalise many points with one inversion; infinity -> (0, 0).
+inline std::vector<affine_t> batch_to_affine(const std::vector<PallasPoint>& pts) {
+    std::vector<fq_t> d(pts.size());
+    for (size_t i = 0; i < pts.size(); i++) fp_mul(d[i], pts[i].p.zz, pts[i].p.zzz);  // zero for infinity
+    batch_inverse(d);
+    std::vector<affine_t> out(pts.size());
+    for (size_t i = 0; i < pts.size(); i++) {
+        if (xyzz_is_inf(pts[i].p)) {
+            affine_set_inf(out[i]);
+            continue;
+        }
+        fq_t t;
+        fp_mul(t, d[i], pts[i].p.zzz);  // 1 / zz
+        fp_mul(out[i].x, pts[i].p.x, t);
+        fp_mul(t, d[i], pts[i].p.zz);   // 1 / zzz
+        fp_mul(out[i].y, pts[i].p.y, t);
+    }
+    return out;
+}
+// compressed form of an already normalised point (same bytes as serialize_compressed)
+inline void serialize_compressed_affine(const affine_t& aff, uint8_t out[33]) {
+    std::memset(out, 0, 33);
+    if (affine_is_inf(aff)) {
+        out[32] = 0x40;
+        return;
+    }
+    uint32_t x[8], y[8], ny[8];
+    fq_t negy;
+    fp_to_canon(x, aff.x);
+    fp_to_canon(y, aff.y);
+    fp_neg(negy, aff.y);
+    fp_to_canon(ny, negy);
+    for (int i = 0; i < 8; i++)
+        for (int b = 0; b < 4; b++) out[4 * i + b] = (uint8_t)(x[i] >> (8 * b));
+    bool gt = false;
+    for (int i = 7; i >= 0; i--) {
+        if (y[i] != ny[i]) {
+            gt = y[i] > ny[i];
+            break;
+        }
+    }
+    if (gt) out[32] = 0x80;
+}
+
 // ---- Fiat-Shamir transcript: group.rs:41-64 (rho_0!, tag 0) and :66-89 (rho_1!, tag 1) -----------------
 class Transcript {
     std::vector<uint8_t> data_;
@@ -132,6 +196,12 @@ public:
     Transcript& point(const PallasPoint& p) {
         uint8_t b[33];
         serialize_compressed(p, b);
+        data_.insert(data_.end(), b, b + 33);
+        return *this;
+    }
+    Transcript& point_affine(const affine_t& a) {  // a point normalised earlier (batch_to_affine)
+        uint8_t b[33];
+        serialize_compressed_affine(a, b);
         data_.insert(data_.end(), b, b + 33);
         return *this;
     }

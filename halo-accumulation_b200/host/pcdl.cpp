@@ -154,31 +154,42 @@ std::pair<HPoly, PallasPoint> succinct_check(halo_ctx* ctx, const PallasPoint& C
     }
     // xi_0, challenges (:282-293); the group arithmetic of :285-298 and :307-310 is one small MSM:
     //   C_lg == c U + v' H'   <=>   C' + (xi_0 v - xi_0 v') H + sum_i (xi_{i+1}^-1 L_i + xi_{i+1} R_i) - c U == 0
+    // all points that enter the transcript or the MSM are normalised with ONE field inversion (the reference normalises
+    // each point separately inside serialize_compressed; same bytes)
+    std::vector<PallasPoint> pts;
+    pts.reserve(2 * (size_t)lg_n + 2);
+    for (uint32_t i = 0; i < lg_n; i++) {
+        pts.push_back(pi.Ls[i]);
+        pts.push_back(pi.Rs[i]);
+    }
+    pts.push_back(H);
+    pts.push_back(pi.U);
+    std::vector<affine_t> aff = batch_to_affine(pts);
+    std::vector<uint8_t> inf(aff.size());
+    for (size_t i = 0; i < aff.size(); i++) inf[i] = affine_is_inf(aff[i]) ? 1 : 0;
     std::vector<PallasScalar> xis;
     xis.reserve(lg_n + 1);
     xis.push_back(Transcript().point(C_prime).scalar(z).scalar(v).finish(0));
-    std::vector<PallasScalar> scalars;
-    std::vector<uint64_t> bases;
-    scalars.reserve(2 * lg_n + 2);
-    bases.resize(12 * (2 * (size_t)lg_n + 2));
-    size_t k = 0;
     for (uint32_t i = 0; i < lg_n; i++) {
-        PallasScalar xi_next = Transcript().scalar(xis[i]).point(pi.Ls[i]).point(pi.Rs[i]).finish(0);  // :293
-        ensure(!fp_is_zero(xi_next), HALO_EINVAL, "challenge is zero (inverse().unwrap())");            // :297
+        PallasScalar xi_next = Transcript().scalar(xis[i]).point_affine(aff[2 * i]).point_affine(aff[2 * i + 1]).finish(0);  // :293
+        ensure(!fp_is_zero(xi_next), HALO_EINVAL, "challenge is zero (inverse().unwrap())");                                 // :297
         xis.push_back(xi_next);
-        point_store(&bases[12 * k++], pi.Ls[i]);
-        scalars.push_back(scalar_inverse(xi_next));
-        point_store(&bases[12 * k++], pi.Rs[i]);
-        scalars.push_back(xi_next);
+    }
+    std::vector<PallasScalar> inv(xis.begin() + 1, xis.end());
+    batch_inverse(inv);  // xi_{i+1}^-1, one inversion for all rounds
+    std::vector<PallasScalar> scalars;
+    scalars.reserve(2 * (size_t)lg_n + 2);
+    for (uint32_t i = 0; i < lg_n; i++) {
+        scalars.push_back(inv[i]);      // xi_{i+1}^-1 L_i
+        scalars.push_back(xis[i + 1]);  // xi_{i+1}   R_i
     }
     HPoly h(xis);                                   // :301
     PallasScalar v_prime = pi.c * h.eval(z);        // :304
-    point_store(&bases[12 * k++], H);
     scalars.push_back(xis[0] * v - xis[0] * v_prime);  // v H' - v' H' with H' = xi_0 H  (:285, :288, :308)
-    point_store(&bases[12 * k++], pi.U);
-    scalars.push_back(-pi.c);
+    scalars.push_back(-pi.c);                          // - c U
     uint64_t out[12];
-    check_rc(ctx, halo_msm_jac(ctx, bases.data(), reinterpret_cast<const uint64_t*>(scalars.data()), k, out));
+    check_rc(ctx, halo_msm(ctx, reinterpret_cast<const uint64_t*>(aff.data()), inf.data(),
+                           reinterpret_cast<const uint64_t*>(scalars.data()), aff.size(), out));
     PallasPoint lhs = C_prime + point_load(out);
     ensure(xyzz_is_inf(lhs.p), HALO_REJECT_SUCCINCT, "C_(log_n) != CM.Commit_Sigma(c || v')");  // :307-310
     return {h, pi.U};                                                                           // :313
