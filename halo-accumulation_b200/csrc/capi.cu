@@ -89,6 +89,9 @@ int halo_ctx_create(int device, uint64_t max_n, halo_ctx** out) {
         HALO_CUDA(cudaSetDevice(device));
         HALO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         HALO_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+        HALO_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        HALO_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        HALO_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         for (auto& e : ctx->ev) HALO_CUDA(cudaEventCreate(&e));
     } catch (const halo::CudaError&) {
         delete ctx;
@@ -110,10 +113,15 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     ctx->stage_misc.release();
     ctx->poly_dev.release();
     for (halo::DevBuf* b : {&ctx->ipa_G, &ctx->ipa_cs, &ctx->ipa_zs, &ctx->ipa_pbar, &ctx->ipa_tail, &ctx->ipa_frozen}) b->release();
-    MsmWorkspace& ws = ctx->ws;
+    for (MsmWorkspace* wsp : {&ctx->ws, &ctx->ws2}) {
+    MsmWorkspace& ws = *wsp;
     for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,
                       &ws.task_bucket, &ws.task_partial, &ws.split_ctrl, &ws.split_tasks, &ws.split_buckets, &ws.split_partials})
         b->release();
+    }
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

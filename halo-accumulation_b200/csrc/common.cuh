@@ -107,7 +107,9 @@ struct halo_ctx {
     uint64_t pre_n = 0;
     bool use_fixed = true;
     // scratch
-    halo::MsmWorkspace ws;
+    halo::MsmWorkspace ws, ws2;  // ws2 / stream2: second lane for a pair of small MSMs (msm_batch)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     halo::DevBuf stage_scalars, stage_bases, stage_misc;
     halo::DevBuf poly_dev;  // polynomial left on the device by halo_h_lincomb_resident for halo_ipa_begin_resident
     uint64_t poly_n = 0;

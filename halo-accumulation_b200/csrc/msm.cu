@@ -48,7 +48,7 @@ static int ceil_lg(uint64_t n) {
 // total cost = W * (n mixed adds) + bucket reduction (2 full adds per bucket, latency bound when thinly filled).
 MsmPlan msm_make_plan(uint64_t n, int force_c) {
     const int lg = ceil_lg(n);
-    int c = lg <= 6 ? 4 : lg <= 8 ? 6 : lg <= 10 ? 8 : lg <= 12 ? 10 : lg <= 14 ? 13 : lg <= 18 ? 14 : lg <= 20 ? 15 : 16;
+    int c = lg <= 6 ? 4 : lg <= 8 ? 6 : lg <= 10 ? 8 : lg <= 12 ? 10 : lg <= 14 ? 12 : lg <= 18 ? 14 : lg <= 20 ? 15 : 16;  // c <= 12: single reduction slab
     if (force_c) c = force_c;
     if (c < 4) c = 4;  // W = 255 / c + 1 <= MSM_MAX_WINDOWS
     if (c > 20) c = 20;
@@ -554,11 +554,13 @@ void msm_precompute_tables(halo_ctx* ctx, int force_c) {
 // ------------------------------------------------------------------------------------------------
 // Device part of one MSM.  d_out receives 3 points per window (one "window" in FIXED mode): [E, A2, R2] with
 // window sum S = E + slab * (A2 - R2); a single-slab plan writes S into E and leaves A2 = R2 = infinity.
-void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out) {
+void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out, int lane) {
     const uint32_t n = in.n;
     const uint32_t ntot = in.n + in.n_tail;
-    MsmWorkspace& ws = ctx->ws;
-    cudaStream_t st = ctx->stream;
+    // lane 0: the context's stream and workspace.  lane 1: a second stream and workspace, so two latency-bound MSMs of
+    // one IPA round (L and R) overlap instead of queueing behind each other.
+    MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
+    cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
     const uint32_t NB = plan.NB;
     const int nwin = plan.fixed ? 1 : plan.W;
     ws.counts.reserve((size_t)(NB + 1) * 4);
@@ -574,7 +576,7 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
     uint32_t* offsets = ws.offsets.as<uint32_t>();
     uint32_t* entries = ws.entries.as<uint32_t>();
     xyzz_t* buckets = ws.buckets.as<xyzz_t>();
-    const bool prof = ctx->profile;
+    const bool prof = ctx->profile && lane == 0;
     auto mark = [&](int i) {
         if (prof) HALO_CUDA(cudaEventRecord(ctx->ev[i], st));
     };
@@ -694,14 +696,27 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs) {
     }
     xyzz_t* h_parts = reinterpret_cast<xyzz_t*>(ctx->pinned);
     bool any = false;
+    // two MSMs in a batch that are small enough to be latency bound run on two streams with separate workspaces
+    bool two_lanes = false;
+    if (count == 2 && ctx->stream2 && ins[0].n + ins[0].n_tail > 0 && ins[1].n + ins[1].n_tail > 0 &&
+        (uint64_t)ins[0].n + ins[1].n <= (1u << 19) && !ctx->profile) {
+        two_lanes = true;
+        HALO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));       // inputs produced on the main stream are complete
+        HALO_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    }
     for (int k = 0; k < count; k++) {
         if (ins[k].n + ins[k].n_tail == 0) continue;
         plans[k] = ins[k].fixed_stride ? ctx->pre_plan : msm_make_plan(ins[k].n + ins[k].n_tail, ctx->force_c);
-        msm_enqueue(ctx, ins[k], plans[k], d_parts + k * SLOT);
+        const int lane = two_lanes ? k : 0;
+        cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
+        msm_enqueue(ctx, ins[k], plans[k], d_parts + k * SLOT, lane);
         const int nwin = plans[k].fixed ? 1 : plans[k].W;
-        HALO_CUDA(cudaMemcpyAsync(h_parts + k * SLOT, d_parts + k * SLOT, (size_t)3 * nwin * sizeof(xyzz_t), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
+        HALO_CUDA(cudaMemcpyAsync(h_parts + k * SLOT, d_parts + k * SLOT, (size_t)3 * nwin * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
         any = true;
+    }
+    if (two_lanes) {
+        HALO_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        HALO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later main-stream work (the fold) is ordered after lane 1
     }
     if (any) HALO_CUDA(cudaStreamSynchronize(ctx->stream));
     if (any && ctx->profile) {

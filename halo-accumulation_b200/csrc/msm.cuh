@@ -18,7 +18,7 @@ struct MsmInput {
 };
 MsmPlan msm_make_fixed_plan(uint64_t n, int force_c);
 // Device part of one MSM: 3 partial points per window into d_out (see msm.cu).
-void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out);
+void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out, int lane = 0);
 // Builds the table of precomputed multiples for the resident generators (FIXED-base mode).
 void msm_precompute_tables(halo_ctx* ctx, int force_c);
 // MSM over resident generators G_first.., FIXED-base when available.
