@@ -321,12 +321,18 @@ def secondary_metrics(ctx, args):
 
     p, z = rs(n), rs(1)[0]
     w, wb, q = rs(1)[0], rs(1)[0], rs(n - 1)
-    t = time.perf_counter()
-    Cm = pcdl.commit(ctx, p, d, w)
-    commit_ms = (time.perf_counter() - t) * 1e3
-    t = time.perf_counter()
-    pi = pcdl.open(ctx, p, Cm, d, z, w, q, wb)
-    open_ms = (time.perf_counter() - t) * 1e3
+    def timed(f, reps=2):  # one warm-up call (first use allocates the context's device buffers), then the best of `reps`
+        out = f()
+        best = 1e18
+        for _ in range(reps):
+            t = time.perf_counter()
+            out = f()
+            best = min(best, (time.perf_counter() - t) * 1e3)
+        return out, best
+
+    Cm, commit_ms = timed(lambda: pcdl.commit(ctx, p, d, w))
+    pi, open_ms = timed(lambda: pcdl.open(ctx, p, Cm, d, z, w, q, wb))
+    _, open_plain_ms = timed(lambda: pcdl.open(ctx, p, pcdl.commit(ctx, p, d), d, z))
     from halo_accumulation_b200 import group
 
     v = group.scalar_dot(ctx, p, group.construct_powers(ctx, z, n))
@@ -338,17 +344,16 @@ def secondary_metrics(ctx, args):
         best = min(best, (time.perf_counter() - t) * 1e3)
     # one accumulation step + decider
     q0 = acc.new_instance(Cm, d, z, v, pi)
-    t = time.perf_counter()
-    a = acc.prover(ctx, d, [q0], rs(2), rs(1)[0], rs(n - 1), rs(1)[0])
-    prover_ms = (time.perf_counter() - t) * 1e3
+    h0r, wr, qr, wbr = rs(2), rs(1)[0], rs(n - 1), rs(1)[0]
+    a, prover_ms = timed(lambda: acc.prover(ctx, d, [q0], h0r, wr, qr, wbr))
     acc.verifier(ctx, d, [q0], a)
     dec = 1e9
     for _ in range(3):
         t = time.perf_counter()
         acc.decider(ctx, a)
         dec = min(dec, (time.perf_counter() - t) * 1e3)
-    return {f"asdl_decider_ms_2^{lg}": dec, f"pcdl_check_ms_2^{lg}": best, f"pcdl_open_hiding_ms_2^{lg}": open_ms,
-            f"pcdl_commit_ms_2^{lg}": commit_ms, f"asdl_prover_ms_2^{lg}": prover_ms, "timing": "host wall clock around the synchronous call"}
+    return {f"asdl_decider_ms_2^{lg}": dec, f"pcdl_check_ms_2^{lg}": best, f"pcdl_open_hiding_ms_2^{lg}": open_ms, f"pcdl_open_ms_2^{lg}": open_plain_ms,
+            f"pcdl_commit_ms_2^{lg}": commit_ms, f"asdl_prover_ms_2^{lg}": prover_ms, "timing": "host wall clock around the synchronous call, best of 2 after one warm-up (open_ms includes a commit)"}
 
 
 def main():
