@@ -144,6 +144,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("HALO_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = 1 << args.log_n
     ctx = H.Context(local, n)
