@@ -240,8 +240,8 @@ int halo_test_fp_mul_throughput(halo_ctx* ctx, int blocks, int threads, int iter
         // ilp encodes (ilp, variant): ilp % 10 = independent chains per thread, ilp / 10 = variant + 1 (0 = portable C++)
         int var = ilp / 10 - 1, il = ilp % 10;
 #define TP(I, V) k_fp_mul_tp<I, V><<<blocks, threads, 0, ctx->stream>>>(iters, sink.as<uint32_t>())
-        if (il == 1) { if (var < 0) TP(1, -1); else if (var == 0) TP(1, 0); else if (var == 1) TP(1, 1); else if (var == 2) TP(1, 2); else TP(1, 3); }
-        else { if (var < 0) TP(2, -1); else if (var == 0) TP(2, 0); else if (var == 1) TP(2, 1); else if (var == 2) TP(2, 2); else TP(2, 3); }
+        if (il == 1) { if (var < 0) TP(1, -1); else if (var == 0) TP(1, 0); else if (var == 1) TP(1, 1); else if (var == 2) TP(1, 2); else if (var == 3) TP(1, 3); else TP(1, 4); }
+        else { if (var < 0) TP(2, -1); else if (var == 0) TP(2, 0); else if (var == 1) TP(2, 1); else if (var == 2) TP(2, 2); else if (var == 3) TP(2, 3); else TP(2, 4); }
 #undef TP
         HALO_CUDA(cudaEventRecord(e1, ctx->stream));
         HALO_CUDA(cudaStreamSynchronize(ctx->stream));

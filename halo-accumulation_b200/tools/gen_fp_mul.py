@@ -30,12 +30,23 @@ class Prog:
     def __init__(self):
         self.ins = []
         self.tmp = 0
+        self.zero = set()      # virtual registers known to hold 0 and never materialised
+        self.lazy_zero = False  # variant 4: use the literal 0 instead of a zeroed register
 
     def t(self, hint="t"):
         self.tmp += 1
         return f"{hint}{self.tmp}"
 
     def emit(self, op, *args):
+        if self.lazy_zero:
+            if op == "mov" and args[1] == 0:
+                self.zero.add(args[0])
+                return
+            n_pred = 1 if op == "selp" else 0
+            src = [0 if (isinstance(a, str) and a in self.zero) else a for a in args[1:len(args) - n_pred]]
+            args = (args[0],) + tuple(src) + tuple(args[len(args) - n_pred:] if n_pred else ())
+            if op != "setp.ne":
+                self.zero.discard(args[0])
         self.ins.append((op,) + args)
 
 
@@ -79,6 +90,12 @@ def emulate(prog, env):
         elif op == "shr":
             d, a, k = ins[1:]
             env[d] = val(a) >> k
+        elif op == "not":
+            d, a = ins[1:]
+            env[d] = (~val(a)) & MASK
+        elif op == "shf.r.clamp":  # funnel shift right: lower 32 bits of (hi:lo) >> k
+            d, lo, hi, k = ins[1:]
+            env[d] = ((((val(hi) << 32) | val(lo)) >> k) & MASK)
         elif op == "shf.l":  # funnel shift left: upper 32 bits of (hi:lo) << k
             d, lo, hi, k = ins[1:]
             env[d] = (((val(hi) << 32) | val(lo)) << k >> 32) & MASK
@@ -130,6 +147,7 @@ def build_mul(p, variant, square=False):
     assert P[0] == 1 and P[4] == P[5] == P[6] == 0 and P[7] == 0x40000000
     P1, P2, P3 = P[1], P[2], P[3]
     pg = Prog()
+    pg.lazy_zero = variant == 4
     a = [f"a{i}" for i in range(8)]
     b = [f"a{i}" for i in range(8)] if square else [f"b{i}" for i in range(8)]
     X = [pg.t("x") for _ in range(9)]
@@ -190,9 +208,17 @@ def build_mul(p, variant, square=False):
             chain_mad(pg, X, [a[0], a[2], a[4], a[6]], bi, False, X[8], False)
         # m = -X[0]
         m = pg.t("m")
-        pg.emit("sub", m, 0, X[0])
+        if variant == 4:
+            nx = pg.t("n")
+            pg.emit("not", nx, X[0])
+            pg.emit("add", m, nx, 1)
+        else:
+            pg.emit("sub", m, 0, X[0])
         # X += m * (1, P2, 0, 0): X[0] cancels to zero
-        pg.emit("add.cc", X[0], X[0], m)
+        if variant == 4:
+            pg.emit("add.cc", X[0], X[0], 0xFFFFFFFF)  # carry = (X[0] != 0); the limb itself is dropped by the shift
+        else:
+            pg.emit("add.cc", X[0], X[0], m)
         pg.emit("addc.cc", X[1], X[1], 0)
         pg.emit("madc.lo.cc", X[2], m, P2, X[2])
         pg.emit("madc.hi.cc", X[3], m, P2, X[3])
@@ -219,6 +245,14 @@ def build_mul(p, variant, square=False):
             pg.emit("madc.hi.cc", Y[5], m, 0, Y[5])
             pg.emit("madc.lo.cc", Y[6], m, 0x40000000, Y[6])
             pg.emit("madc.hi.cc", Y[7], m, 0x40000000, Y[7])
+        elif variant == 4:
+            lo30, hi2 = pg.t("s"), pg.t("s")
+            pg.emit("shf.l", lo30, 0, m, 30)       # (m:0) << 30 upper word = m << 30
+            pg.emit("shf.r.clamp", hi2, m, 0, 2)   # (0:m) >> 2 lower word = m >> 2
+            pg.emit("addc.cc", Y[4], Y[4], 0)
+            pg.emit("addc.cc", Y[5], Y[5], 0)
+            pg.emit("addc.cc", Y[6], Y[6], lo30)
+            pg.emit("addc.cc", Y[7], Y[7], hi2)
         else:
             lo30, hi2 = pg.t("s"), pg.t("s")
             pg.emit("shl", lo30, m, 30)
@@ -300,6 +334,10 @@ def to_ptx(pg, square):
             lines.append(f"selp.u32 {reg(ins[1])}, {reg(ins[2])}, {reg(ins[3])}, {ins[4]};")
         elif op in ("shl", "shr"):
             lines.append(f"{op}.b32 {reg(ins[1])}, {reg(ins[2])}, {ins[3]};" if op == "shl" else f"shr.u32 {reg(ins[1])}, {reg(ins[2])}, {ins[3]};")
+        elif op == "not":
+            lines.append(f"not.b32 {reg(ins[1])}, {reg(ins[2])};")
+        elif op == "shf.r.clamp":
+            lines.append(f"shf.r.clamp.b32 {reg(ins[1])}, {reg(ins[2])}, {reg(ins[3])}, {ins[4]};")
         elif op == "shf.l":
             lines.append(f"shf.l.wrap.b32 {reg(ins[1])}, {reg(ins[2])}, {reg(ins[3])}, {ins[4]};")
         elif op == "mov":
@@ -351,7 +389,7 @@ def main():
         "template <class P, int V> __device__ __forceinline__ void fp_mul_asm(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]);",
         "template <class P, int V> __device__ __forceinline__ void fp_sqr_asm(uint32_t r[8], const uint32_t a[8]);",
     ]
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4):
         for params, p in FIELDS.items():
             for square in (False, True):
                 pg = check(p, variant, square, iters=1500)
