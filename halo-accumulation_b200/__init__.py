@@ -196,6 +196,11 @@ class Context:
         self._chk(self._lib.halo_test_fp_mul_throughput(self._h, blocks, threads, iters, ilp, C.byref(ms), C.byref(ck)))
         return ms.value
 
+    def test_vec_bench(self, kind, n):
+        ms = C.c_float()
+        self._chk(self._lib.halo_test_vec_bench(self._h, int(kind), C.c_uint64(n), C.byref(ms)))
+        return ms.value
+
     def test_imad_throughput(self, kind, blocks, threads, iters):
         ms, ck = C.c_float(), C.c_uint64()
         self._chk(self._lib.halo_test_imad_throughput(self._h, kind, blocks, threads, iters, C.byref(ms), C.byref(ck)))

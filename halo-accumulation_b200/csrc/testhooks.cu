@@ -3,6 +3,7 @@
 
 #include "../../include/halo_b200_test.h"
 #include "common.cuh"
+#include "vec.cuh"
 
 using namespace halo;
 
@@ -288,6 +289,54 @@ int halo_test_imad_throughput(halo_ctx* ctx, int kind, int blocks, int threads, 
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     sink.release();
+    T_CATCH(ctx)
+}
+
+// Times one Fr vector kernel on device-resident synthetic data (CUDA events on the context stream, best of 5):
+// kind 0 = scalar folds (pcdl.rs:221-223), 1 = h-expansion, 2 = dot product, 3 = powers of z.
+int halo_test_vec_bench(halo_ctx* ctx, int kind, uint64_t n, float* ms) {
+    if (!ctx || !ms || n < 8) return HALO_EINVAL;
+    T_TRY(ctx)
+    DevBuf a, b, scratch;
+    a.reserve(n * sizeof(fr_t));
+    b.reserve(n * sizeof(fr_t));
+    scratch.reserve((2 + VEC_DOT_MAX_BLOCKS) * sizeof(fr_t));
+    fr_t z;
+    fp_one(z);
+    z.v[0] ^= 0x1234567u;
+    z.v[5] ^= 0x0abcdefu;
+    vec_powers(ctx, z, n, a.as<fr_t>());
+    vec_powers(ctx, z, n, b.as<fr_t>());
+    fr_t xis[33];
+    for (int i = 0; i < 33; i++) {
+        xis[i] = z;
+        xis[i].v[1] ^= (uint32_t)i * 2654435761u;
+        xis[i].v[7] &= 0x0fffffffu;
+    }
+    int lg = 0;
+    while (((uint64_t)2 << lg) <= n) lg++;
+    cudaEvent_t e0, e1;
+    HALO_CUDA(cudaEventCreate(&e0));
+    HALO_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {
+        HALO_CUDA(cudaEventRecord(e0, ctx->stream));
+        if (kind == 0) vec_fold_scalars(ctx, a.as<fr_t>(), b.as<fr_t>(), n / 2, z, xis[3]);
+        else if (kind == 1) vec_h_expand(ctx, xis, lg, z, false, a.as<fr_t>());
+        else if (kind == 2) vec_dot(ctx, a.as<fr_t>(), b.as<fr_t>(), n, scratch.as<fr_t>() + 2, scratch.as<fr_t>());
+        else vec_powers(ctx, z, n, a.as<fr_t>());
+        HALO_CUDA(cudaEventRecord(e1, ctx->stream));
+        HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+        float t;
+        HALO_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        if (rep > 0 && t < best) best = t;
+    }
+    *ms = best;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    a.release();
+    b.release();
+    scratch.release();
     T_CATCH(ctx)
 }
 }
