@@ -289,3 +289,25 @@ def test_msm_pipelined_submit_collect(ctx, oracle):
         ctx.msm_gens_submit(scs[2])
     assert O.pt_eq(ctx.msm_gens_collect(t0), exp[0]) and O.pt_eq(ctx.msm_gens_collect(t1), exp[1])
     assert O.pt_to_affine(ctx.msm_gens_collect(ctx.msm_gens_submit(np.zeros((0, 4), dtype=np.uint64))))[1]
+
+
+def test_msm_2_22_fixed_and_variable_vs_oracle(halo, oracle):
+    """BASELINE config 5 at a size the oracle still finishes in seconds: n = 2^22, FIXED-base and variable-base paths
+    against the oracle's Pippenger, byte for byte after normalisation."""
+    O = oracle
+    n = 1 << 22
+    c = halo.Context(0, n)
+    try:
+        c.derive_generators(n)
+        gs = c.get_generators(0, n)
+        sc = O.random_scalars(n, 4)
+        exp, _ = O.pt_to_affine(O.msm_affine(gs, sc, threads=16))
+        c.set_fixed_base(False)
+        assert O.pt_to_affine(c.msm_gens(sc))[0].tobytes() == exp.tobytes()
+        c.precompute_generators(0)
+        c.set_fixed_base(True)
+        assert O.pt_to_affine(c.msm_gens(sc))[0].tobytes() == exp.tobytes()
+        t = c.msm_gens_submit(sc)
+        assert O.pt_to_affine(c.msm_gens_collect(t))[0].tobytes() == exp.tobytes()
+    finally:
+        c.close()

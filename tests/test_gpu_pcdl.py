@@ -266,3 +266,36 @@ def test_open_check_2_16_full_parity(env):
     _same_proof(O, pi, O.pcdl_open(p, Cm, d, z, threads=8))
     v = O.scalar_dot(p, O.construct_powers(z, n))
     pcdl.check(ctx, Cm, d, z, v, pi)
+
+
+def test_open_and_full_check_2_20(ctx, oracle):
+    """BASELINE config 3: PCDL open + full check at n = 2^20 on one GPU.  The oracle cannot re-open at this size in
+    seconds, so parity is by properties: the GPU proof is accepted by the GPU check AND by the oracle's full check
+    (succinct check + h-expansion + its own MSM over the same generators), a flipped proof is rejected by both with the
+    same failing condition, and v = p(z) agrees with the oracle's dot product."""
+    from halo_accumulation_b200 import group, pcdl
+
+    O = oracle
+    n = 1 << 20
+    d = n - 1
+    ctx.derive_generators(n)
+    try:
+        ctx.precompute_generators(0)
+        S, Hh = ctx.get_SH()
+        O.set_params(S, Hh, ctx.get_generators(0, n))
+        p = O.random_scalars(n - 12345, 2)  # ragged degree d' < d
+        z = O.random_scalars(1, 3)[0]
+        Cm = pcdl.commit(ctx, p, d)
+        pi = pcdl.open(ctx, p, Cm, d, z)
+        v = group.scalar_dot(ctx, p, group.construct_powers(ctx, z, p.shape[0]))
+        assert v.tolist() == O.scalar_dot(p, O.construct_powers(z, p.shape[0])).tolist()
+        pcdl.check(ctx, Cm, d, z, v, pi)
+        assert O.pcdl_check(Cm, d, z, v, O.EvalProof.from_buffer_copy(bytes(pi)), threads=16) == 0
+        bad = type(pi).from_buffer_copy(bytes(pi))
+        bad.Rs[7][0] ^= 1
+        with pytest.raises(pcdl.Rejected) as e:
+            pcdl.check(ctx, Cm, d, z, v, bad)
+        # (the flipped limb may take the point off the curve; both sides only need to reject at the same check)
+        assert e.value.code == O.pcdl_check(Cm, d, z, v, O.EvalProof.from_buffer_copy(bytes(bad)), threads=16)
+    finally:
+        ctx.derive_generators(1 << 16)
