@@ -25,6 +25,9 @@ namespace halo {
 #define HALO_IPA_FREEZE_LEN 8192
 #endif
 constexpr uint64_t IPA_FREEZE_LEN = HALO_IPA_FREEZE_LEN;
+#ifndef HALO_FOLD_MIN_BLOCKS
+#define HALO_FOLD_MIN_BLOCKS 3  // 168 registers; 4 CTAs per SM (128 registers) spills and measures 10 % slower
+#endif
 
 // ---- GLV: xi * P = k1 * P + k2 * phi(P), phi(x, y) = (beta x, y) = lambda * P, |k1|, |k2| < 2^129 ------------------
 // Pallas has j-invariant 0, so Fq contains a primitive cube root of unity beta and Fr the matching lambda
@@ -42,7 +45,7 @@ __device__ __constant__ uint32_t c_beta_mont[8] = {0x9e65eac8u, 0xfbdfd7aau, 0xe
 
 // K4 point part: G[j] <- affine(G[j] + xi * G[j + m]) with xi = k1 + k2 lambda.  One thread per output element; the
 // joint digit loop is uniform across the grid (same xi for every element of a round).
-__global__ void __launch_bounds__(128) k_fold_points(affine_t* __restrict__ G, uint64_t m, GlvDigits dg) {
+__global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_points(affine_t* __restrict__ G, uint64_t m, GlvDigits dg) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     affine_t hi = G[j + m];
