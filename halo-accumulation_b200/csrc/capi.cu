@@ -116,7 +116,8 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     for (MsmWorkspace* wsp : {&ctx->ws, &ctx->ws2}) {
     MsmWorkspace& ws = *wsp;
     for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,
-                      &ws.task_bucket, &ws.task_partial, &ws.split_ctrl, &ws.split_tasks, &ws.split_buckets, &ws.split_partials})
+                      &ws.task_bucket, &ws.task_partial, &ws.split_ctrl, &ws.split_tasks, &ws.split_buckets, &ws.split_partials,
+                      &ws.pt_a, &ws.pt_b, &ws.pt_prefix, &ws.pt_levels})
         b->release();
     }
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -148,6 +149,7 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return HALO_EINVAL;
     if (!strcmp(key, "acc_static")) ctx->tune_acc_static = value;
     else if (!strcmp(key, "acc_blocks_per_sm")) ctx->tune_acc_blocks_per_sm = value;
+    else if (!strcmp(key, "pair_passes")) ctx->tune_pair_passes = value;
     else return fail(ctx, HALO_EINVAL, "halo_set_tuning: unknown key");
     return HALO_OK;
 }

@@ -82,6 +82,7 @@ struct MsmWorkspace {
     DevBuf counts, offsets, cursor, entries, buckets, wsums, scan_tmp;
     DevBuf task_bucket, task_partial;  // slab partials of the bucket reduction
     DevBuf split_ctrl, split_tasks, split_buckets, split_partials;  // oversized-bucket splitting
+    DevBuf pt_a, pt_b, pt_prefix, pt_levels;  // pair-tree passes (msm_pairs.cu): ping-pong slot arrays, prefixes, product hierarchy
 };
 
 struct Timings {
@@ -133,6 +134,7 @@ struct halo_ctx {
     size_t pinned_cap = 0;
     int force_c = 0;
     int tune_acc_static = 0, tune_acc_blocks_per_sm = 0;
+    int tune_pair_passes = -1;  // -1: automatic; 0: XYZZ accumulation only; P > 0: force P pair-tree passes
     uint64_t kernel_launches = 0;
     halo::Timings last;
     bool profile = false;

@@ -79,8 +79,7 @@ template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars, uint32_t n,
                                                 const fr_t* __restrict__ tail_scalars, uint32_t n_tail, const MsmWidths widths,
                                                 int W, uint32_t M, uint32_t fixed_stride, uint32_t fixed_first,
-                                                uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                                                uint32_t* __restrict__ entries) {
+                                                uint32_t* __restrict__ counts, uint32_t* __restrict__ entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n + n_tail) return;
     fr_t s = i < n ? scalars[i] : tail_scalars[i - n];
@@ -102,10 +101,13 @@ __global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars
         }
         if (d != 0) {
             uint32_t b = fixed_stride ? (d - 1) : (uint32_t)w * M + (d - 1);
-            uint32_t slot = atomicAdd(&counts[b], 1u);
+            // COUNT: histogram (a fire-and-forget RED).  SCATTER: `counts` holds the running write cursor of every bucket,
+            // initialised to the bucket offsets, so the returned value is the absolute slot (one random L2 access less per
+            // entry than offsets[b] + slot).
+            uint32_t pos = atomicAdd(&counts[b], 1u);
             if (SCATTER) {
                 uint32_t idx = fixed_stride ? (uint32_t)w * fixed_stride + fixed_first + i : i;
-                entries[offsets[b] + slot] = idx | (neg << 31);
+                entries[pos] = idx | (neg << 31);
             }
         }
     }
@@ -144,14 +146,15 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return base + x - v;
 }
 
+// `round_mask` = 2^P - 1 rounds every count up to a multiple of 2^P first (padded segments for the pair tree, msm_pairs.cu)
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                             uint32_t n, uint32_t* __restrict__ tile_sums) {
+                                                             uint32_t n, uint32_t round_mask, uint32_t* __restrict__ tile_sums) {
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t sum = 0;
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; j++) {
-        v[j] = (base + j < n) ? in[base + j] : 0;
+        v[j] = (base + j < n) ? ((in[base + j] + round_mask) & ~round_mask) : 0;
         sum += v[j];
     }
     uint32_t total;
@@ -192,11 +195,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* __restrict_
         if (base + j < n) out[base + j] += add;
 }
 
+// Pad slots [offsets[b] + counts[b], offsets[b + 1]) of every bucket segment get the "infinity" entry (pair tree only).
+__global__ void __launch_bounds__(256) k_fill_pads(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t NB,
+                                                   uint32_t* __restrict__ entries) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    for (uint32_t e = offsets[b] + counts[b], end = offsets[b + 1]; e < end; e++) entries[e] = 0xffffffffu;
+}
+__global__ void __launch_bounds__(256) k_shift_offsets(const uint32_t* __restrict__ in, uint32_t n, int shift, uint32_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] >> shift;
+}
+
 // offsets[0..n] = exclusive scan of counts[0..n) with offsets[n] = total
-static void exclusive_scan(const uint32_t* counts, uint32_t* offsets, uint32_t n, uint32_t* tmp, cudaStream_t st,
-                           uint64_t* launches) {
+static void exclusive_scan(const uint32_t* counts, uint32_t* offsets, uint32_t n, uint32_t round_mask, uint32_t* tmp,
+                           cudaStream_t st, uint64_t* launches) {
     uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_local<<<ntiles, SCAN_THREADS, 0, st>>>(counts, offsets, n, tmp);
+    k_scan_local<<<ntiles, SCAN_THREADS, 0, st>>>(counts, offsets, n, round_mask, tmp);
     k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(tmp, ntiles, offsets + n);
     k_scan_add<<<ntiles, SCAN_THREADS, 0, st>>>(offsets, n, tmp);
     *launches += 3;
@@ -209,9 +224,29 @@ static void exclusive_scan(const uint32_t* counts, uint32_t* offsets, uint32_t n
 // (one warp-aggregated atomicAdd per claim round), so every lane of a warp stays busy until the work runs out.  With
 // a static thread-per-bucket mapping the warp waits for its fullest bucket: bucket loads are Poisson, which costs
 // 10 % at 416 entries per bucket and 21 % at 96 (c = 22).
+// Entry / base fetch of the accumulation kernels.  Indirect: entries[e] = (index | sign << 31) into bases (or the tail).
+// DIRECT (after the pair-tree passes, msm_pairs.cu): slot e itself holds an affine partial sum, infinity is marked by
+// x = 2^256 - 1 and is mapped to the (0, 0) encoding xyzz_madd skips.
+template <bool DIRECT>
+__device__ __forceinline__ uint32_t acc_entry(const uint32_t* __restrict__ entries, uint32_t e) {
+    return DIRECT ? e : entries[e];
+}
+template <bool DIRECT>
+__device__ __forceinline__ affine_t acc_base(const affine_t* __restrict__ bases, uint32_t n, const affine_t* __restrict__ tail_bases,
+                                             uint32_t ent) {
+    if (DIRECT) {
+        affine_t p = bases[ent];
+        if (p.x.v[7] == 0xffffffffu) affine_set_inf(p);
+        return p;
+    }
+    const uint32_t idx = ent & 0x7fffffffu;
+    return idx < n ? bases[idx] : tail_bases[idx - n];
+}
+
 #ifndef HALO_ACC_MIN_BLOCKS
 #define HALO_ACC_MIN_BLOCKS 4
 #endif
+template <bool DIRECT>
 __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate(const affine_t* __restrict__ bases, uint32_t n,
                                                                          const affine_t* __restrict__ tail_bases,
                                                                          const uint32_t* __restrict__ offsets,
@@ -249,10 +284,9 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate(const a
                     }
                     // refill the software pipeline (entry two ahead, base one ahead)
                     if (e < end) {
-                        ent1 = entries[e];
-                        if (e + 1 < end) ent2 = entries[e + 1];
-                        uint32_t idx = ent1 & 0x7fffffffu;
-                        p1 = idx < n ? bases[idx] : tail_bases[idx - n];
+                        ent1 = acc_entry<DIRECT>(entries, e);
+                        if (e + 1 < end) ent2 = acc_entry<DIRECT>(entries, e + 1);
+                        p1 = acc_base<DIRECT>(bases, n, tail_bases, ent1);
                     }
                 } else {
                     b = 0xffffffffu;
@@ -266,18 +300,16 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate(const a
             const uint32_t ent0 = ent1;
             const affine_t p0 = p1;
             ent1 = ent2;
-            if (e + 2 < end) ent2 = entries[e + 2];
-            if (e + 1 < end) {
-                uint32_t idx = ent1 & 0x7fffffffu;
-                p1 = idx < n ? bases[idx] : tail_bases[idx - n];
-            }
-            xyzz_madd(acc, p0, (ent0 >> 31) != 0);
+            if (e + 2 < end) ent2 = acc_entry<DIRECT>(entries, e + 2);
+            if (e + 1 < end) p1 = acc_base<DIRECT>(bases, n, tail_bases, ent1);
+            xyzz_madd(acc, p0, !DIRECT && (ent0 >> 31) != 0);
             e++;
         }
     }
 }
 
 // Static mapping (one thread per bucket) kept for A/B measurements: halo_set_tuning(ctx, "acc_static", 1).
+template <bool DIRECT>
 __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_static(const affine_t* __restrict__ bases, uint32_t n,
                                                                                 const affine_t* __restrict__ tail_bases,
                                                                                 const uint32_t* __restrict__ offsets,
@@ -290,23 +322,17 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_static(
     xyzz_t acc;
     xyzz_set_inf(acc);
     // software pipeline: the entry two steps ahead and the base one step ahead are in flight during each mixed add
-    uint32_t ent1 = beg < end ? entries[beg] : 0;
-    uint32_t ent2 = beg + 1 < end ? entries[beg + 1] : 0;
+    uint32_t ent1 = beg < end ? acc_entry<DIRECT>(entries, beg) : 0;
+    uint32_t ent2 = beg + 1 < end ? acc_entry<DIRECT>(entries, beg + 1) : 0;
     affine_t p1;
-    {
-        uint32_t idx = ent1 & 0x7fffffffu;
-        if (beg < end) p1 = idx < n ? bases[idx] : tail_bases[idx - n];
-    }
+    if (beg < end) p1 = acc_base<DIRECT>(bases, n, tail_bases, ent1);
     for (uint32_t e = beg; e < end; e++) {
         const uint32_t ent0 = ent1;
         const affine_t p0 = p1;
         ent1 = ent2;
-        if (e + 2 < end) ent2 = entries[e + 2];
-        if (e + 1 < end) {
-            uint32_t idx = ent1 & 0x7fffffffu;
-            p1 = idx < n ? bases[idx] : tail_bases[idx - n];
-        }
-        xyzz_madd(acc, p0, (ent0 >> 31) != 0);
+        if (e + 2 < end) ent2 = acc_entry<DIRECT>(entries, e + 2);
+        if (e + 1 < end) p1 = acc_base<DIRECT>(bases, n, tail_bases, ent1);
+        xyzz_madd(acc, p0, !DIRECT && (ent0 >> 31) != 0);
     }
     buckets[b] = acc;
 }
@@ -351,6 +377,7 @@ __global__ void __launch_bounds__(256) k_split_plan(const uint32_t* __restrict__
     }
 }
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_split(const affine_t* __restrict__ bases, uint32_t n,
                                                                                const affine_t* __restrict__ tail_bases,
                                                                                const uint32_t* __restrict__ entries,
@@ -390,10 +417,9 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_split(c
         }
         if (__all_sync(0xffffffffu, exhausted)) break;
         if (e < end) {
-            uint32_t ent = entries[e];
-            uint32_t idx = ent & 0x7fffffffu;
-            affine_t p = idx < n ? bases[idx] : tail_bases[idx - n];
-            xyzz_madd(acc, p, (ent >> 31) != 0);
+            uint32_t ent = acc_entry<DIRECT>(entries, e);
+            affine_t p = acc_base<DIRECT>(bases, n, tail_bases, ent);
+            xyzz_madd(acc, p, !DIRECT && (ent >> 31) != 0);
             e++;
         }
     }
@@ -563,9 +589,22 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
     cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
     const uint32_t NB = plan.NB;
     const int nwin = plan.fixed ? 1 : plan.W;
+    const uint64_t total_entries_max = (uint64_t)ntot * plan.W;
+    // pair-tree passes (msm_pairs.cu): worthwhile once the per-pass fixed costs (7 launches and one ~0.1 ms inversion
+    // latency) are small against the additions saved; bucket segments are then padded to multiples of 2^P slots
+    int P = 0;
+    if (ctx->tune_pair_passes >= 0)
+        P = ctx->tune_pair_passes;
+    else if (total_entries_max >= ((uint64_t)1 << 25) && total_entries_max >= (uint64_t)NB * 64)
+        P = 4;
+    if (P > 8) P = 8;
+    const uint32_t rmask = (1u << P) - 1u;
+    uint64_t slots_max = total_entries_max + (uint64_t)rmask * NB;
+    slots_max = (slots_max + rmask) & ~(uint64_t)rmask;
+    if (slots_max >= 0xfffffff0ull) throw CudaError{cudaErrorInvalidValue, "MSM too large for 32-bit slot indices", __FILE__, __LINE__};
     ws.counts.reserve((size_t)(NB + 1) * 4);
     ws.offsets.reserve((size_t)(NB + 1) * 4);
-    ws.entries.reserve((size_t)ntot * plan.W * 4);
+    ws.entries.reserve((size_t)slots_max * 4);
     ws.buckets.reserve((size_t)NB * sizeof(xyzz_t));
     ws.scan_tmp.reserve(4096 * 4);
     ws.task_partial.reserve((size_t)(2 * plan.red_slabs + 3) * nwin * sizeof(xyzz_t));
@@ -587,21 +626,40 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
     const int TPB = 256;
     uint32_t grid = (ntot + TPB - 1) / TPB;
     k_digits<false><<<grid, TPB, 0, st>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
-                                          in.fixed_first, counts, nullptr, nullptr);
+                                          in.fixed_first, counts, nullptr);
     mark(1);
-    exclusive_scan(counts, offsets, NB, ws.scan_tmp.as<uint32_t>(), st, &ctx->kernel_launches);
-    HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, st));
+    exclusive_scan(counts, offsets, NB, rmask, ws.scan_tmp.as<uint32_t>(), st, &ctx->kernel_launches);
+    if (P) {  // pad slots of every bucket segment stand for the point at infinity
+        k_fill_pads<<<(NB + 255) / 256, 256, 0, st>>>(counts, offsets, NB, entries);
+        ctx->kernel_launches++;
+    }
+    // the histogram array becomes the write cursor of every bucket; its spare slot [NB] the claim counter of k_accumulate
+    HALO_CUDA(cudaMemcpyAsync(counts, offsets, (size_t)NB * 4, cudaMemcpyDeviceToDevice, st));
+    HALO_CUDA(cudaMemsetAsync(counts + NB, 0, 4, st));
     mark(2);
     k_digits<true><<<grid, TPB, 0, st>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
-                                         in.fixed_first, counts, offsets, entries);
+                                         in.fixed_first, counts, entries);
     mark(3);
-    // FIXED: every entry indexes the table, there is no tail
+    // P > 0: the first P levels of every bucket's sum as flat pairwise affine additions (msm_pairs.cu); the XYZZ kernels
+    // below then see bucket b as the slots [offsets[b] >> P, offsets[b + 1] >> P) of the returned array.
+    const affine_t* acc_bases = in.bases;
+    const uint32_t* acc_offsets = offsets;
+    uint32_t acc_n = plan.fixed ? 0x7fffffffu : n;
+    uint64_t acc_entries_max = total_entries_max;
+    if (P) {
+        acc_bases = pair_tree_enqueue(ctx, ws, st, in, entries, offsets + NB, slots_max, P);
+        ws.cursor.reserve((size_t)(NB + 1) * 4);
+        k_shift_offsets<<<(NB + 1 + 255) / 256, 256, 0, st>>>(offsets, NB + 1, P, ws.cursor.as<uint32_t>());
+        ctx->kernel_launches++;
+        acc_offsets = ws.cursor.as<uint32_t>();
+        acc_n = 0;
+        acc_entries_max = slots_max >> P;
+    }
     // oversized-bucket threshold: 4x the mean fill, at least 1024 entries (uniform scalars never reach it)
-    const uint64_t total_entries_max = (uint64_t)ntot * plan.W;
-    uint32_t split_len = (uint32_t)(4 * (total_entries_max / NB + 1));
+    uint32_t split_len = (uint32_t)(4 * (acc_entries_max / NB + 1));
     if (split_len < 1024) split_len = 1024;
-    const uint32_t max_split_tasks = (uint32_t)(total_entries_max / split_len + 1) * 2 + 16;  // sum ceil(cnt/L) <= E/L + #split
-    const uint32_t max_split_buckets = (uint32_t)(total_entries_max / split_len + 1);
+    const uint32_t max_split_tasks = (uint32_t)(acc_entries_max / split_len + 1) * 2 + 16;  // sum ceil(cnt/L) <= E/L + #split
+    const uint32_t max_split_buckets = (uint32_t)(acc_entries_max / split_len + 1);
     ws.split_ctrl.reserve(16);
     ws.split_tasks.reserve((size_t)max_split_tasks * sizeof(SplitTask));
     ws.split_buckets.reserve((size_t)max_split_buckets * sizeof(SplitBucket));
@@ -610,27 +668,39 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
     HALO_CUDA(cudaMemsetAsync(split_ctrl, 0, 16, st));
     // thread-per-bucket is ~8 % faster when buckets are deep and evenly filled (variable base, large n); lane-level
     // claiming wins everywhere else (measured: profiles/r01_accumulate_static_vs_dynamic.txt)
-    const bool deep = !plan.fixed && (uint64_t)ntot * plan.W >= (uint64_t)NB * 256;
+    const bool deep = !P && !plan.fixed && (uint64_t)ntot * plan.W >= (uint64_t)NB * 256;
     if (ctx->tune_acc_static == 1 || (ctx->tune_acc_static == 0 && deep)) {
-        k_accumulate_static<<<(NB + 127) / 128, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, offsets, entries,
-                                                             NB, buckets, split_len);
+        if (P)
+            k_accumulate_static<true><<<(NB + 127) / 128, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB,
+                                                                       buckets, split_len);
+        else
+            k_accumulate_static<false><<<(NB + 127) / 128, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB,
+                                                                        buckets, split_len);
     } else {
         // persistent lanes: enough CTAs to fill the machine, capped by the amount of work
         uint32_t want_blocks = (NB + 127) / 128;
         uint32_t max_blocks = (uint32_t)ctx->sm_count * (ctx->tune_acc_blocks_per_sm ? ctx->tune_acc_blocks_per_sm : HALO_ACC_MIN_BLOCKS);
         uint32_t blocks = want_blocks < max_blocks ? want_blocks : max_blocks;
         uint32_t* next_bucket = counts + NB;  // spare slot at the end of the counter array (zeroed above)
-        k_accumulate<<<blocks, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, offsets, entries, NB, buckets,
-                                             next_bucket, split_len);
+        if (P)
+            k_accumulate<true><<<blocks, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB, buckets, next_bucket,
+                                                       split_len);
+        else
+            k_accumulate<false><<<blocks, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB, buckets, next_bucket,
+                                                        split_len);
     }
     {
-        k_split_plan<<<(NB + 255) / 256, 256, 0, st>>>(offsets, NB, split_len, max_split_tasks, max_split_buckets, split_ctrl,
+        k_split_plan<<<(NB + 255) / 256, 256, 0, st>>>(acc_offsets, NB, split_len, max_split_tasks, max_split_buckets, split_ctrl,
                                                        ws.split_tasks.as<SplitTask>(), ws.split_buckets.as<SplitBucket>());
         uint32_t sblocks = (uint32_t)ctx->sm_count * HALO_ACC_MIN_BLOCKS;
         uint32_t cap = (max_split_tasks + 127) / 128;
         if (sblocks > cap) sblocks = cap;
-        k_accumulate_split<<<sblocks, 128, 0, st>>>(in.bases, plan.fixed ? 0x7fffffffu : n, in.tail_bases, entries,
-                                                    ws.split_tasks.as<SplitTask>(), split_ctrl, ws.split_partials.as<xyzz_t>());
+        if (P)
+            k_accumulate_split<true><<<sblocks, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, entries, ws.split_tasks.as<SplitTask>(),
+                                                              split_ctrl, ws.split_partials.as<xyzz_t>());
+        else
+            k_accumulate_split<false><<<sblocks, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, entries, ws.split_tasks.as<SplitTask>(),
+                                                               split_ctrl, ws.split_partials.as<xyzz_t>());
         uint32_t mblocks = (max_split_buckets + 3) / 4;
         if (mblocks > (uint32_t)ctx->sm_count * 4) mblocks = (uint32_t)ctx->sm_count * 4;
         k_merge_split<<<mblocks, 128, 0, st>>>(ws.split_buckets.as<SplitBucket>(), split_ctrl, ws.split_partials.as<xyzz_t>(), buckets);

@@ -19,6 +19,9 @@ struct MsmInput {
 MsmPlan msm_make_fixed_plan(uint64_t n, int force_c);
 // Device part of one MSM: 3 partial points per window into d_out (see msm.cu).
 void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out, int lane = 0);
+// First `passes` levels of the bucket sums as flat pairwise affine additions with batched inversion (msm_pairs.cu).
+const affine_t* pair_tree_enqueue(halo_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const MsmInput& in, const uint32_t* entries,
+                                  const uint32_t* total_slots, uint64_t slots_max, int passes);
 // Builds the table of precomputed multiples for the resident generators (FIXED-base mode).
 void msm_precompute_tables(halo_ctx* ctx, int force_c);
 // MSM over resident generators G_first.., FIXED-base when available.

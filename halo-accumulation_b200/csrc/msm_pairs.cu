@@ -1,0 +1,300 @@
+// msm_pairs.cu -- K2b: the first levels of the bucket accumulation as a tree of pairwise AFFINE additions with
+// batched inversion (part of the Pippenger MSM behind group.rs:18-26; see msm.cu for the pipeline around it).
+//
+// The bucket-sorted entry list is laid out so that every bucket's segment starts at a multiple of 2^P slots and is
+// padded with "infinity" slots up to the next multiple (msm.cu rounds the histogram before the scan).  One tree pass
+// then is a flat, bucket-oblivious map over an array of slots:   out[q] = in[2q] + in[2q+1]   -- pairs never straddle
+// buckets, no per-pass offsets or searches, and after P passes bucket b owns the slots [off_b >> P, off_{b+1} >> P),
+// which the XYZZ kernel of msm.cu finishes (plus its splitting of oversized buckets, so degenerate scalar
+// distributions need nothing special here).
+//
+// An affine addition costs one inversion; the inversions of a whole pass are shared (Montgomery's trick) through a
+// hierarchy that never serialises more than a handful of multiplications per thread:
+//   k_pair_fwd    per thread K pairs: den_q (x2 - x1, or 2 y1 for a doubling), running product -> prefix[q], total -> T0[t]
+//   k_prod_up     T_{j+1}[u] = product of KU values of T_j, prefixes kept                            (until <= 65536 values)
+//   k_inv         one Fermat inversion per surviving value, all in parallel
+//   k_prod_down   inverse totals back down: T_j[i] <- 1 / T_j[i]
+//   k_pair_bwd    per pair: 1/den from the thread's inverse total and prefix[q], then lambda, x3, y3 -> out[q]
+// 5M + 1S per addition (+ 3/K + 3/(K KU) .. for the hierarchy) instead of the 8M + 2S of a mixed XYZZ addition.
+// The price is memory traffic (operands are read twice, prefixes written and read once: ~320 B per addition instead of
+// a 64-byte gather), which HBM3e carries while the integer pipe stays the bound.
+//
+// Exactness: infinity operands, P + P (tangent) and P + (-P) are classified identically by the forward and backward
+// kernels (same function, same inputs) and never contribute a zero denominator, so duplicate and cancelling bases --
+// legal inputs of msm_unchecked -- give the same group element as the XYZZ path.
+#include "common.cuh"
+#include "msm.cuh"
+
+namespace halo {
+
+constexpr int PT_K = 16;   // pairs per thread in k_pair_fwd / k_pair_bwd
+constexpr int PT_KU = 16;  // fan-in of the product hierarchy
+constexpr uint32_t PT_INV_MAX = 65536;
+constexpr uint32_t PT_SENTINEL = 0xffffffffu;  // entry that stands for the point at infinity (padding)
+
+enum : int { PT_SKIP = 0, PT_ADD = 1, PT_DBL = 2 };
+
+// Infinity inside the intermediate arrays: x = 2^256 - 1 (not a canonical residue), so the forward pass can classify a
+// pair from the x coordinates alone.
+__device__ __forceinline__ bool pt_x_is_inf(const fq_t& x) { return x.v[7] == 0xffffffffu; }
+__device__ __forceinline__ void pt_set_inf(affine_t& p) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        p.x.v[i] = 0xffffffffu;
+        p.y.v[i] = 0u;
+    }
+}
+
+// One operand of pass 0: table / base gather through the entry (index | sign << 31), sign applied.
+__device__ __forceinline__ void pt_gather(affine_t& p, bool& inf, uint32_t ent, const affine_t* __restrict__ bases, uint32_t n,
+                                          const affine_t* __restrict__ tail_bases) {
+    if (ent == PT_SENTINEL) {
+        inf = true;
+        affine_set_inf(p);
+        return;
+    }
+    const uint32_t idx = ent & 0x7fffffffu;
+    p = idx < n ? bases[idx] : tail_bases[idx - n];
+    inf = affine_is_inf(p);
+    if (ent >> 31) fp_neg(p.y, p.y);
+}
+
+// Classification shared by both directions.  Needs y only when the x coordinates coincide.
+//   PT_ADD: den = bx - ax.   PT_DBL: den = 2 ay (ay != 0).   PT_SKIP: no inversion; the result is inf, a or b.
+__device__ __forceinline__ int pt_classify(fq_t& den, bool ainf, bool binf, const fq_t& ax, const fq_t& bx, const fq_t& ay,
+                                           const fq_t& by) {
+    if (ainf || binf) return PT_SKIP;
+    fp_sub(den, bx, ax);
+    if (!fp_is_zero(den)) return PT_ADD;
+    if (fp_eq(ay, by) && !fp_is_zero(ay)) {
+        fp_dbl(den, ay);
+        return PT_DBL;
+    }
+    return PT_SKIP;  // a = -b (or a 2-torsion point of an off-curve input): the sum is infinity
+}
+
+// pair index of thread-local step s: warps own 32 * PT_K consecutive pairs, lanes interleave (coalesced 128-byte pairs)
+__device__ __forceinline__ uint32_t pt_pair_index(uint32_t gwarp, int s, uint32_t lane) { return (gwarp * PT_K + s) * 32u + lane; }
+
+// ---- forward ---------------------------------------------------------------------------------------------------------
+template <bool PASS0>
+__global__ void __launch_bounds__(128) k_pair_fwd(const uint32_t* __restrict__ entries, const affine_t* __restrict__ bases, uint32_t n,
+                                                  const affine_t* __restrict__ tail_bases, const affine_t* __restrict__ in,
+                                                  const uint32_t* __restrict__ total_slots, int pass, fq_t* __restrict__ prefix,
+                                                  fq_t* __restrict__ totals) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gwarp = tid >> 5, lane = tid & 31u;
+    const uint32_t Q = *total_slots >> (pass + 1);
+    fq_t run;
+    fp_one(run);
+    if (pt_pair_index(gwarp, 0, 0) < Q) {
+#pragma unroll 2
+        for (int s = 0; s < PT_K; s++) {
+            const uint32_t q = pt_pair_index(gwarp, s, lane);
+            if (q >= Q) break;
+            fq_t ax, bx, ay, by, den;
+            bool ainf, binf;
+            if (PASS0) {
+                const uint2 e = reinterpret_cast<const uint2*>(entries)[q];
+                affine_t a, b;
+                pt_gather(a, ainf, e.x, bases, n, tail_bases);
+                pt_gather(b, binf, e.y, bases, n, tail_bases);
+                ax = a.x;
+                ay = a.y;
+                bx = b.x;
+                by = b.y;
+            } else {
+                ax = in[2 * (size_t)q].x;
+                bx = in[2 * (size_t)q + 1].x;
+                ainf = pt_x_is_inf(ax);
+                binf = pt_x_is_inf(bx);
+                if (!ainf && !binf && fp_eq(ax, bx)) {
+                    ay = in[2 * (size_t)q].y;
+                    by = in[2 * (size_t)q + 1].y;
+                } else {
+                    fp_zero(ay);
+                    fp_zero(by);
+                }
+            }
+            const int mode = pt_classify(den, ainf, binf, ax, bx, ay, by);
+            if (mode != PT_SKIP) {
+                prefix[q] = run;
+                fp_mul(run, run, den);
+            }
+        }
+    }
+    totals[tid] = run;
+}
+
+// ---- product hierarchy -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_prod_up(const fq_t* __restrict__ vals, uint32_t n, fq_t* __restrict__ pre,
+                                                 fq_t* __restrict__ totals) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gwarp = tid >> 5, lane = tid & 31u;
+    fq_t run;
+    fp_one(run);
+#pragma unroll 1
+    for (int i = 0; i < PT_KU; i++) {
+        const uint32_t idx = (gwarp * PT_KU + i) * 32u + lane;
+        if (idx >= n) break;
+        pre[idx] = run;
+        fq_t v = vals[idx];
+        fp_mul(run, run, v);
+    }
+    totals[tid] = run;
+}
+__global__ void __launch_bounds__(128) k_inv(fq_t* __restrict__ vals, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fq_t v = vals[i], r;
+    fp_inv(r, v);
+    vals[i] = r;
+}
+// vals[i] <- 1 / vals[i], given the inverse of each thread's product in tot_inv
+__global__ void __launch_bounds__(128) k_prod_down(fq_t* __restrict__ vals, uint32_t n, const fq_t* __restrict__ pre,
+                                                   const fq_t* __restrict__ tot_inv) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gwarp = tid >> 5, lane = tid & 31u;
+    fq_t inv = tot_inv[tid];
+#pragma unroll 1
+    for (int i = PT_KU - 1; i >= 0; i--) {
+        const uint32_t idx = (gwarp * PT_KU + i) * 32u + lane;
+        if (idx >= n) continue;
+        fq_t v = vals[idx], p = pre[idx], o;
+        fp_mul(o, inv, p);
+        fp_mul(inv, inv, v);
+        vals[idx] = o;
+    }
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------------------
+template <bool PASS0>
+__global__ void __launch_bounds__(128, 4) k_pair_bwd(const uint32_t* __restrict__ entries, const affine_t* __restrict__ bases,
+                                                     uint32_t n, const affine_t* __restrict__ tail_bases,
+                                                     const affine_t* __restrict__ in, const uint32_t* __restrict__ total_slots,
+                                                     int pass, const fq_t* __restrict__ prefix, const fq_t* __restrict__ tot_inv,
+                                                     affine_t* __restrict__ out) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gwarp = tid >> 5, lane = tid & 31u;
+    const uint32_t Q = *total_slots >> (pass + 1);
+    if (pt_pair_index(gwarp, 0, 0) >= Q) return;
+    fq_t invtot = tot_inv[tid];
+#pragma unroll 1
+    for (int s = PT_K - 1; s >= 0; s--) {
+        const uint32_t q = pt_pair_index(gwarp, s, lane);
+        if (q >= Q) continue;
+        affine_t a, b;
+        bool ainf, binf;
+        if (PASS0) {
+            const uint2 e = reinterpret_cast<const uint2*>(entries)[q];
+            pt_gather(a, ainf, e.x, bases, n, tail_bases);
+            pt_gather(b, binf, e.y, bases, n, tail_bases);
+        } else {
+            a = in[2 * (size_t)q];
+            b = in[2 * (size_t)q + 1];
+            ainf = pt_x_is_inf(a.x);
+            binf = pt_x_is_inf(b.x);
+        }
+        fq_t den;
+        const int mode = pt_classify(den, ainf, binf, a.x, b.x, a.y, b.y);
+        affine_t r;
+        if (mode == PT_SKIP) {
+            if (ainf && binf)
+                pt_set_inf(r);
+            else if (ainf)
+                r = b;
+            else if (binf)
+                r = a;
+            else
+                pt_set_inf(r);  // a = -b
+        } else {
+            fq_t inv, pre = prefix[q], num, lam, t;
+            fp_mul(inv, invtot, pre);
+            fp_mul(invtot, invtot, den);
+            if (mode == PT_ADD) {
+                fp_sub(num, b.y, a.y);
+            } else {  // tangent: 3 x^2 / (2 y)
+                fp_sqr(t, a.x);
+                fp_dbl(num, t);
+                fp_add(num, num, t);
+            }
+            fp_mul(lam, num, inv);
+            fp_sqr(t, lam);
+            fp_sub(t, t, a.x);
+            fp_sub(r.x, t, b.x);
+            fp_sub(t, a.x, r.x);
+            fp_mul(t, lam, t);
+            fp_sub(r.y, t, a.y);
+        }
+        out[q] = r;
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------------
+static inline uint32_t ceil_div(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// Runs `passes` tree passes over the padded entry list (slots_max = host upper bound of the padded slot count, a
+// multiple of 2^passes; the exact count is *total_slots on the device).  Returns the array of slots after the last pass.
+const affine_t* pair_tree_enqueue(halo_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const MsmInput& in, const uint32_t* entries,
+                                  const uint32_t* total_slots, uint64_t slots_max, int passes) {
+    const uint64_t Q0 = slots_max >> 1;
+    ws.pt_a.reserve(Q0 * sizeof(affine_t));
+    ws.pt_b.reserve((Q0 >> 1) * sizeof(affine_t) + sizeof(affine_t));
+    ws.pt_prefix.reserve(Q0 * sizeof(fq_t));
+    // hierarchy geometry of pass 0 (the largest): level sizes n0 > n1 > .. until <= PT_INV_MAX
+    auto level_sizes = [](uint64_t Q, uint32_t* sizes, uint32_t* grids) {
+        int L = 0;
+        uint32_t blocks = ceil_div(ceil_div(Q, 32u * PT_K), 4);
+        if (blocks == 0) blocks = 1;
+        sizes[L] = blocks * 128u;
+        grids[L] = blocks;
+        while (sizes[L] > PT_INV_MAX) {
+            uint32_t b2 = ceil_div(ceil_div(sizes[L], 32u * PT_KU), 4);
+            sizes[L + 1] = b2 * 128u;
+            grids[L + 1] = b2;
+            L++;
+        }
+        return L + 1;
+    };
+    uint32_t sizes[8], grids[8];
+    int L = level_sizes(Q0, sizes, grids);
+    size_t lv_total = 0;
+    for (int j = 0; j < L; j++) lv_total += (size_t)sizes[j] * 2;  // values + prefixes per level
+    ws.pt_levels.reserve(lv_total * sizeof(fq_t));
+
+    const affine_t* src = nullptr;
+    const uint32_t nb = in.n;
+    for (int p = 0; p < passes; p++) {
+        const uint64_t Q = slots_max >> (p + 1);
+        L = level_sizes(Q, sizes, grids);
+        fq_t* lv = ws.pt_levels.as<fq_t>();
+        fq_t* vals[8];
+        fq_t* pres[8];
+        for (int j = 0; j < L; j++) {
+            vals[j] = lv;
+            pres[j] = lv + sizes[j];
+            lv += (size_t)sizes[j] * 2;
+        }
+        affine_t* dst = (p & 1) ? ws.pt_b.as<affine_t>() : ws.pt_a.as<affine_t>();
+        fq_t* prefix = ws.pt_prefix.as<fq_t>();
+        if (p == 0)
+            k_pair_fwd<true><<<grids[0], 128, 0, st>>>(entries, in.bases, in.fixed_stride ? 0x7fffffffu : nb, in.tail_bases, nullptr,
+                                                       total_slots, p, prefix, vals[0]);
+        else
+            k_pair_fwd<false><<<grids[0], 128, 0, st>>>(nullptr, nullptr, 0, nullptr, src, total_slots, p, prefix, vals[0]);
+        for (int j = 0; j + 1 < L; j++) k_prod_up<<<grids[j + 1], 128, 0, st>>>(vals[j], sizes[j], pres[j], vals[j + 1]);
+        k_inv<<<ceil_div(sizes[L - 1], 128), 128, 0, st>>>(vals[L - 1], sizes[L - 1]);
+        for (int j = L - 2; j >= 0; j--) k_prod_down<<<grids[j + 1], 128, 0, st>>>(vals[j], sizes[j], pres[j], vals[j + 1]);
+        if (p == 0)
+            k_pair_bwd<true><<<grids[0], 128, 0, st>>>(entries, in.bases, in.fixed_stride ? 0x7fffffffu : nb, in.tail_bases, nullptr,
+                                                       total_slots, p, prefix, vals[0], dst);
+        else
+            k_pair_bwd<false><<<grids[0], 128, 0, st>>>(nullptr, nullptr, 0, nullptr, src, total_slots, p, prefix, vals[0], dst);
+        ctx->kernel_launches += 2 + 2 * (uint64_t)(L - 1) + 1;
+        src = dst;
+    }
+    HALO_CUDA(cudaGetLastError());
+    return src;
+}
+
+}  // namespace halo

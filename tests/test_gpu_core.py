@@ -311,3 +311,97 @@ def test_msm_2_22_fixed_and_variable_vs_oracle(halo, oracle):
         assert O.pt_to_affine(c.msm_gens_collect(t))[0].tobytes() == exp.tobytes()
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("passes", [1, 2, 4, 6])
+@pytest.mark.parametrize("fixed", [False, True])
+def test_msm_pair_tree_passes(ctx, oracle, passes, fixed):
+    """K2b (msm_pairs.cu): the first levels of the bucket sums as pairwise affine additions with batched inversion,
+    forced on at sizes the oracle checks in seconds; ragged sizes, every window width class, both base modes."""
+    O = oracle
+    n_gens = 1 << 13
+    ctx.derive_generators(n_gens)
+    try:
+        if fixed:
+            ctx.precompute_generators(11)
+        ctx.set_fixed_base(fixed)
+        ctx.set_tuning("pair_passes", passes)
+        gs = ctx.get_generators(0, n_gens)
+        for n, off, seed in [(n_gens, 0, 1), (5000, 100, 2), (1, 7, 3), (2, 0, 4), (33, 0, 5), (1023, 1000, 6)]:
+            sc = O.random_scalars(n, seed)
+            assert O.pt_eq(ctx.msm_gens(sc, off=off), O.msm_affine(gs[off:off + n], sc, threads=8)), (n, off)
+        edge = {
+            "zeros": np.zeros((n_gens, 4), dtype=np.uint64),
+            "ones": np.tile(O.to_mont([1])[0], (n_gens, 1)),
+            "r_minus_1": np.tile(O.to_mont([R_MOD - 1])[0], (n_gens, 1)),
+            "same_big": np.tile(O.random_scalars(1, 5)[0], (n_gens, 1)),
+            "small": O.to_mont([i % 7 for i in range(n_gens)]),
+            "half": O.to_mont([(1 << 254) + i for i in range(n_gens)]),
+        }
+        for name, sc in edge.items():
+            assert O.pt_eq(ctx.msm_gens(sc), O.msm_affine(gs, sc, threads=8)), name
+    finally:
+        ctx.set_tuning("pair_passes", -1)
+        ctx.set_fixed_base(True)
+        ctx.derive_generators(1 << 16)
+
+
+@pytest.mark.parametrize("passes", [1, 3, 5])
+def test_msm_pair_tree_duplicates_cancellations_infinity(ctx, oracle, passes):
+    """Pairs the affine formulas cannot add generically: P + P (tangent), P + (-P) (infinity), infinity operands.
+    Duplicate bases with equal scalars meet in the same bucket; negated scalars meet with opposite signs."""
+    O = oracle
+    n = 2048
+    gs = ctx.get_generators(100, n).copy()
+    sc = O.random_scalars(n, 33)
+    gs[1::2] = gs[0::2]                      # every base twice, adjacent
+    sc[1:1024:2] = sc[0:1024:2]              # first half: identical pairs -> doublings at the first level
+    negs = ctx.test_fp_op(1, 5, sc[1024::2])  # second half: s and -s on the same base -> cancellation
+    sc[1025::2] = negs
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[[5, 6, 77, 1500, 2047]] = 1
+    ctx.set_tuning("pair_passes", passes)
+    try:
+        for c in (4, 8, 12):
+            ctx.set_msm_window(c)
+            assert O.pt_eq(ctx.msm(gs, sc, inf), O.msm_affine(gs, sc, inf=inf, threads=8)), c
+            # all bases equal, all scalars equal: one bucket per window holds n copies of the same point
+            same_g = np.tile(gs[3], (n, 1))
+            same_s = np.tile(sc[3], (n, 1))
+            assert O.pt_eq(ctx.msm(same_g, same_s), O.msm_affine(same_g, same_s, threads=8)), c
+            # everything cancels
+            half = n // 2
+            g2 = np.concatenate([gs[:half], gs[:half]])
+            s2 = np.concatenate([sc[:half], ctx.test_fp_op(1, 5, sc[:half])])
+            assert O.pt_to_affine(ctx.msm(g2, s2))[1], c
+    finally:
+        ctx.set_msm_window(0)
+        ctx.set_tuning("pair_passes", -1)
+
+
+def test_msm_pair_tree_oversized_buckets(ctx, oracle):
+    """Degenerate digit distributions through the pair tree: the flat passes shrink every bucket 2^P-fold and the XYZZ
+    tail's bucket splitting handles what is left."""
+    O = oracle
+    n = 1 << 16
+    ctx.derive_generators(n)
+    try:
+        ctx.precompute_generators(0)
+        ctx.set_tuning("pair_passes", 4)
+        gs = ctx.get_generators(0, n)
+        big = O.random_scalars(1, 5)[0]
+        cases = {
+            "all_equal": np.tile(big, (n, 1)),
+            "two_values": np.where((np.arange(n) % 3 == 0)[:, None], big[None, :], O.random_scalars(1, 6)[0][None, :]),
+            "half_uniform_half_equal": np.concatenate([O.random_scalars(n // 2, 7), np.tile(big, (n // 2, 1))]),
+            "uniform": O.random_scalars(n, 8),
+        }
+        for fixed in (True, False):
+            ctx.set_fixed_base(fixed)
+            for name, sc in cases.items():
+                sc = np.ascontiguousarray(sc, dtype=np.uint64)
+                assert O.pt_eq(ctx.msm_gens(sc), O.msm_affine(gs, sc, threads=8)), (fixed, name)
+    finally:
+        ctx.set_tuning("pair_passes", -1)
+        ctx.set_fixed_base(True)
+        ctx.derive_generators(1 << 16)
