@@ -11,6 +11,10 @@ cs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 Ps = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 4]
 ctx = H.Context(0, 1 << max(lgs))
 ctx.set_profiling(True)
+import os
+for kv in os.environ.get("TUNE", "").split(","):
+    if kv:
+        k_, v_ = kv.split("="); ctx.set_tuning(k_, int(v_))
 for lg in lgs:
     n = 1 << lg
     ctx.derive_generators(n)
@@ -30,4 +34,4 @@ for lg in lgs:
                 t = time.perf_counter(); r = ctx.msm_gens_resident(d.data_ptr(), n); wall = (time.perf_counter() - t) * 1e3
                 tm = ctx.last_msm_timings()
                 if best is None or tm["total"] < best[1]["total"]: best = (wall, tm)
-            emit(lg=lg, c=c, P=P, ok=bool(H.points_equal(r, ref)), wall_ms=best[0], **best[1])
+            emit(lg=lg, c=c, P=P, tune=os.environ.get("TUNE", ""), ok=bool(H.points_equal(r, ref)), wall_ms=best[0], **best[1])
