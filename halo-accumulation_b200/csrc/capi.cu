@@ -112,7 +112,8 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     ctx->stage_bases.release();
     ctx->stage_misc.release();
     ctx->poly_dev.release();
-    for (halo::DevBuf* b : {&ctx->ipa_G, &ctx->ipa_cs, &ctx->ipa_zs, &ctx->ipa_pbar, &ctx->ipa_tail, &ctx->ipa_frozen}) b->release();
+    for (halo::DevBuf* b : {&ctx->ipa_G, &ctx->ipa_cs, &ctx->ipa_zs, &ctx->ipa_pbar, &ctx->ipa_tail, &ctx->ipa_frozen,
+                           &ctx->ipa_sums, &ctx->ipa_den, &ctx->ipa_inv_scratch, &ctx->ipa_bx}) b->release();
     for (MsmWorkspace* wsp : {&ctx->ws, &ctx->ws2}) {
     MsmWorkspace& ws = *wsp;
     for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,
@@ -150,6 +151,7 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     if (!strcmp(key, "acc_static")) ctx->tune_acc_static = value;
     else if (!strcmp(key, "acc_blocks_per_sm")) ctx->tune_acc_blocks_per_sm = value;
     else if (!strcmp(key, "pair_passes")) ctx->tune_pair_passes = value;
+    else if (!strcmp(key, "ipa_defer_rounds")) ctx->tune_ipa_defer = value;
     else return fail(ctx, HALO_EINVAL, "halo_set_tuning: unknown key");
     return HALO_OK;
 }

@@ -117,6 +117,7 @@ struct halo_ctx {
     // buffers of the (single) in-flight PCDL opening, kept across openings: cudaMalloc / cudaFree of 100+ MB per open
     // costs tens of milliseconds
     halo::DevBuf ipa_G, ipa_cs, ipa_zs, ipa_pbar, ipa_tail, ipa_frozen;
+    halo::DevBuf ipa_sums, ipa_den, ipa_inv_scratch, ipa_bx;  // generator fold: XYZZ sums, ZZ * ZZZ and the batched inversion's hierarchy
     bool ipa_busy = false;
     // asynchronous MSM pipeline (halo_msm_gens_submit / _collect): two in-flight slots, H2D on its own stream so the copy
     // of call k+1 overlaps the kernels of call k
@@ -134,6 +135,7 @@ struct halo_ctx {
     size_t pinned_cap = 0;
     int force_c = 0;
     int tune_acc_static = 0, tune_acc_blocks_per_sm = 0;
+    int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
     int tune_pair_passes = -1;  // -1: automatic; 0: XYZZ accumulation only; P > 0: force P pair-tree passes
     uint64_t kernel_launches = 0;
     halo::Timings last;

@@ -44,8 +44,12 @@ __device__ __constant__ uint32_t c_beta_mont[8] = {0x9e65eac8u, 0xfbdfd7aau, 0xe
                                                    0x3785b99au, 0xd59892a3u, 0x585e8789u, 0x2a27fb62u};
 
 // K4 point part: G[j] <- affine(G[j] + xi * G[j + m]) with xi = k1 + k2 lambda.  One thread per output element; the
-// joint digit loop is uniform across the grid (same xi for every element of a round).
-__global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_points(affine_t* __restrict__ G, uint64_t m, GlvDigits dg) {
+// joint digit loop is uniform across the grid (same xi for every element of a round).  The sum is left in XYZZ
+// coordinates with den[j] = ZZ * ZZZ (1 for infinity); the normalisation shares its inversions across the whole
+// round (batch_invert: 3 multiplications per element instead of a 255-squaring Fermat chain each) and k_fold_finish
+// writes the affine point back (K7).
+__global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_points(const affine_t* __restrict__ G, uint64_t m, GlvDigits dg,
+                                                                          xyzz_t* __restrict__ sums, fq_t* __restrict__ den) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     affine_t hi = G[j + m];
@@ -68,9 +72,99 @@ __global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_points(affin
     }
     affine_t lo = G[j];
     xyzz_madd(acc, lo, false);
+    sums[j] = acc;
+    fq_t d;
+    if (xyzz_is_inf(acc))
+        fp_one(d);
+    else
+        fp_mul(d, acc.zz, acc.zzz);
+    den[j] = d;
+}
+// x = X / ZZ = X * ZZZ * inv, y = Y / ZZZ = Y * ZZ * inv with inv = 1 / (ZZ * ZZZ)
+__global__ void __launch_bounds__(128) k_fold_finish(const xyzz_t* __restrict__ sums, const fq_t* __restrict__ inv, uint64_t m,
+                                                     affine_t* __restrict__ G) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    xyzz_t p = sums[j];
     affine_t out;
-    xyzz_to_affine(out, acc);
+    if (xyzz_is_inf(p)) {
+        affine_set_inf(out);
+    } else {
+        fq_t i = inv[j], t;
+        fp_mul(t, i, p.zzz);
+        fp_mul(out.x, p.x, t);
+        fp_mul(t, i, p.zz);
+        fp_mul(out.y, p.y, t);
+    }
     G[j] = out;
+}
+
+// ---- deferred head: several fold rounds in one joint pass ---------------------------------------------------------------
+// Folding round by round pays ~129 doublings per element per round.  When the first D rounds are deferred (their L / R
+// are MSMs over the untouched generators with per-index coefficients, like the frozen tail below), the generator vector
+// after round D - 1 is, for j < n / 2^D,
+//     G^(D)_j = sum_{t < 2^D} s_t G_{j + off_t},   s_t = prod_k xi_k^{bit_k(t)},   off_t = sum_k bit_k(t) n / 2^(k+1)
+// (pcdl.rs:216-218 unrolled D times), a 2^D-term multi-scalar multiplication with SHARED scalars: one joint
+// double-and-add (Straus) pays the 129 doublings once per output instead of once per term.  The host decomposes every
+// s_t by GLV, merges the signed NAF digits of all 2 (2^D - 1) half-scalars into one operation list (uniform across the
+// grid, so the loop is divergence free) and uploads it; beta x of every term is staged in global memory once.
+constexpr int FOLD_MAX_DEFER = 4;
+constexpr int FOLD_MAX_OPS = 3072;
+struct FoldOps {
+    uint8_t code[FOLD_MAX_OPS];  // 0xff: double; else (stream | sign << 7), stream = 2 (t - 1) + half
+    int n_ops;
+};
+__device__ __constant__ FoldOps c_fold_ops;
+
+__global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_multi(const affine_t* __restrict__ G0, uint64_t n, int D,
+                                                                         fq_t* __restrict__ bx, xyzz_t* __restrict__ sums,
+                                                                         fq_t* __restrict__ den) {
+    const uint64_t m = n >> D;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int T = 1 << D;
+    {
+        fq_t beta;
+#pragma unroll
+        for (int i = 0; i < 8; i++) beta.v[i] = c_beta_mont[i];
+#pragma unroll 1
+        for (int t = 1; t < T; t++) {
+            uint64_t off = 0;
+            for (int k = 0; k < D; k++)
+                if ((t >> k) & 1) off += n >> (k + 1);
+            fq_t x = G0[j + off].x, r;
+            fp_mul(r, x, beta);
+            bx[(uint64_t)(t - 1) * m + j] = r;
+        }
+    }
+    xyzz_t acc;
+    xyzz_set_inf(acc);
+    const int n_ops = c_fold_ops.n_ops;
+#pragma unroll 1
+    for (int o = 0; o < n_ops; o++) {
+        const uint32_t code = c_fold_ops.code[o];
+        if (code == 0xffu) {
+            xyzz_dbl(acc, acc);
+        } else {
+            const int stream = code & 0x7f, t = (stream >> 1) + 1;
+            uint64_t off = 0;
+            for (int k = 0; k < D; k++)
+                if ((t >> k) & 1) off += n >> (k + 1);
+            affine_t p;
+            p.y = G0[j + off].y;
+            p.x = (stream & 1) ? bx[(uint64_t)(t - 1) * m + j] : G0[j + off].x;
+            xyzz_madd(acc, p, (code >> 7) != 0);
+        }
+    }
+    affine_t lo = G0[j];
+    xyzz_madd(acc, lo, false);
+    sums[j] = acc;
+    fq_t d;
+    if (xyzz_is_inf(acc))
+        fp_one(d);
+    else
+        fp_mul(d, acc.zz, acc.zzz);
+    den[j] = d;
 }
 
 // ---- frozen tail: once the vectors are short the generators stop being folded -------------------------------------
@@ -217,6 +311,49 @@ static void make_glv(const fr_t& xi, GlvDigits& dg) {
 
 }  // namespace halo
 
+namespace halo {
+// Materialises G^(D) from the untouched generators after D deferred rounds (see k_fold_multi).
+static void fold_multi(halo_ctx* ctx, halo_ipa* st) {
+    const int D = st->defer, T = 1 << D;
+    const uint64_t n = st->n, m = n >> D;
+    // s_t = prod_k xi_k^{bit_k(t)}
+    std::vector<fr_t> coef(T);
+    fp_one(coef[0]);
+    for (int t = 1; t < T; t++) {
+        int k = 31 - __builtin_clz((unsigned)t);  // highest set bit: s_t = s_{t - 2^k} * xi_k
+        fp_mul(coef[t], coef[t ^ (1 << k)], st->defer_xis[k]);
+    }
+    std::vector<GlvDigits> dg(T);
+    int top = -1;
+    for (int t = 1; t < T; t++) {
+        make_glv(coef[t], dg[t]);
+        if (dg[t].top > top) top = dg[t].top;
+    }
+    static FoldOps ops;  // one opening per context at a time; the copy below is staged before the call returns
+    int no = 0;
+    for (int i = top; i >= 0; i--) {
+        ops.code[no++] = 0xff;
+        for (int t = 1; t < T; t++) {
+            if (dg[t].d1[i]) ops.code[no++] = (uint8_t)((2 * (t - 1)) | (dg[t].d1[i] < 0 ? 0x80 : 0));
+            if (dg[t].d2[i]) ops.code[no++] = (uint8_t)((2 * (t - 1) + 1) | (dg[t].d2[i] < 0 ? 0x80 : 0));
+        }
+    }
+    if (no > FOLD_MAX_OPS) throw CudaError{cudaErrorInvalidValue, "fold_multi: operation list too long", __FILE__, __LINE__};
+    ops.n_ops = no;
+    HALO_CUDA(cudaMemcpyToSymbolAsync(c_fold_ops, &ops, sizeof ops, 0, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->ipa_bx.reserve((size_t)(T - 1) * m * sizeof(fq_t));
+    ctx->ipa_sums.reserve(m * sizeof(xyzz_t));
+    ctx->ipa_den.reserve(m * sizeof(fq_t));
+    k_fold_multi<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->gens.as<affine_t>(), n, D, ctx->ipa_bx.as<fq_t>(),
+                                                                       ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>());
+    batch_invert(ctx, ctx->stream, ctx->ipa_den.as<fq_t>(), (uint32_t)m, ctx->ipa_inv_scratch);
+    k_fold_finish<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>(), m,
+                                                                        ctx->ipa_G.as<affine_t>());
+    ctx->kernel_launches += 2;
+    HALO_CUDA(cudaGetLastError());
+}
+}  // namespace halo
+
 extern "C" int halo_test_glv_decompose(const uint64_t xi[4], int8_t d1[136], int8_t d2[136], int* top) {
     fr_t x;
     memcpy(&x, xi, 32);
@@ -262,6 +399,11 @@ static int ipa_begin_impl(halo_ctx* ctx, const uint64_t* coeffs, bool resident, 
         HALO_CUDA(cudaSetDevice(ctx->device));
         st->n = st->cur = n;
         while (((uint64_t)1 << st->lg_n) < n) st->lg_n++;
+        // deferred head (k_fold_multi): pays when the L / R of the deferred rounds can take the FIXED-base path
+        st->fixed_ok = ctx->use_fixed && ctx->pre_n == ctx->n_gens && ctx->gens_pre.p && n >= (1u << 17) && n * 8 >= ctx->pre_n;
+        st->defer = ctx->tune_ipa_defer >= 0 ? ctx->tune_ipa_defer : (st->fixed_ok ? 3 : 0);
+        if (st->defer > FOLD_MAX_DEFER) st->defer = FOLD_MAX_DEFER;
+        if (st->defer > (int)st->lg_n) st->defer = (int)st->lg_n;
         memcpy(&st->z, z, 32);
         ctx->ipa_G.reserve(n * sizeof(affine_t));
         ctx->ipa_cs.reserve(n * sizeof(fr_t));
@@ -353,6 +495,7 @@ int halo_ipa_set_hprime(halo_ipa* st, const uint64_t Hprime_jac[12]) {
     xyzz_to_affine(a, x);
     HALO_CUDA(cudaMemcpyAsync(ctx->ipa_tail.p, &a, sizeof a, cudaMemcpyHostToDevice, ctx->stream));
     HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    st->hprime = a;
     st->have_hprime = true;
     IPA_CATCH
 }
@@ -372,8 +515,9 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
     fr_t* scal = reinterpret_cast<fr_t*>(reinterpret_cast<char*>(ctx->ipa_tail.p) + sizeof(affine_t));
     vec_dot(ctx, c + m, z, m, scal + 2, scal);          // dot_l = <c_r, z_l>
     vec_dot(ctx, c, z + m, m, scal + 2, scal + 1);      // dot_r = <c_l, z_r>
-    if (!st->frozen && st->cur <= IPA_FREEZE_LEN) {     // freeze the generator vector (see k_frozen_scalars)
-        st->frozen = true;
+    if (!st->frozen && ((st->defer > 0 && st->round == 0) || st->cur <= IPA_FREEZE_LEN)) {  // freeze the generator vector
+        st->frozen = true;                                                                  // (see k_frozen_scalars)
+        st->deferred = st->cur > IPA_FREEZE_LEN;  // a head freeze is undone by k_fold_multi after `defer` rounds
         st->M0 = (uint32_t)st->cur;
         ctx->ipa_frozen.reserve((size_t)3 * st->M0 * sizeof(fr_t));
         k_fill_one<<<(st->M0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ipa_frozen.as<fr_t>(), st->M0);
@@ -390,20 +534,43 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
         in[0].scalars = tL;
         in[1].bases = G;
         in[1].scalars = tR;
+        if (st->deferred && st->fixed_ok) {  // G is still GS[0..n): shared bucket set over the precomputed multiples
+            for (int k = 0; k < 2; k++) {
+                in[k].bases = ctx->gens_pre.as<affine_t>();
+                in[k].fixed_stride = (uint32_t)ctx->pre_n;
+                in[k].fixed_first = 0;
+            }
+        }
     } else {
         in[0].bases = G;       // L = <c_r, g_l> + dot_l H'
         in[0].scalars = c + m;
         in[1].bases = G + m;   // R = <c_l, g_r> + dot_r H'
         in[1].scalars = c;
     }
+    const bool host_tail = in[0].fixed_stride != 0;  // the FIXED-base path has no tail: dot * H' is added on the host
+    fr_t dots[2];
     for (int k = 0; k < 2; k++) {
         in[k].n = st->frozen ? st->M0 : (uint32_t)m;
-        in[k].tail_bases = Hp;
-        in[k].tail_scalars = scal + k;
-        in[k].n_tail = 1;
+        if (!host_tail) {
+            in[k].tail_bases = Hp;
+            in[k].tail_scalars = scal + k;
+            in[k].n_tail = 1;
+        }
     }
+    if (host_tail) HALO_CUDA(cudaMemcpyAsync(dots, scal, sizeof dots, cudaMemcpyDeviceToHost, ctx->stream));
     xyzz_t out[2];
     msm_batch(ctx, in, 2, out);
+    if (host_tail) {
+        xyzz_t hp;
+        xyzz_from_affine(hp, st->hprime);
+        for (int k = 0; k < 2; k++) {
+            uint32_t kc[8];
+            fp_to_canon(kc, dots[k]);
+            xyzz_t t;
+            xyzz_mul_canon(t, hp, kc);
+            xyzz_add(out[k], t);
+        }
+    }
     jac_t j;
     xyzz_to_jac(j, out[0]);
     memcpy(L_jac, &j, 96);
@@ -424,12 +591,20 @@ int halo_ipa_round_fold(halo_ipa* st, const uint64_t xi[4], const uint64_t xi_in
     fr_t x, xinv;
     memcpy(&x, xi, 32);
     memcpy(&xinv, xi_inv, 32);
+    if (st->deferred) st->defer_xis.push_back(x);
     if (st->frozen) {
         k_frozen_fold_s<<<(st->M0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ipa_frozen.as<fr_t>(), st->M0, (uint32_t)st->cur, x);
     } else {
         GlvDigits dg;
         make_glv(x, dg);
-        k_fold_points<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_G.as<affine_t>(), m, dg);
+        ctx->ipa_sums.reserve(m * sizeof(xyzz_t));
+        ctx->ipa_den.reserve(m * sizeof(fq_t));
+        k_fold_points<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_G.as<affine_t>(), m, dg, ctx->ipa_sums.as<xyzz_t>(),
+                                                                            ctx->ipa_den.as<fq_t>());
+        batch_invert(ctx, ctx->stream, ctx->ipa_den.as<fq_t>(), (uint32_t)m, ctx->ipa_inv_scratch);
+        k_fold_finish<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>(), m,
+                                                                            ctx->ipa_G.as<affine_t>());
+        ctx->kernel_launches++;
     }
     ctx->kernel_launches++;
     HALO_CUDA(cudaGetLastError());
@@ -437,6 +612,10 @@ int halo_ipa_round_fold(halo_ipa* st, const uint64_t xi[4], const uint64_t xi_in
     st->cur = m;
     st->round++;
     st->lr_done = false;
+    if (st->deferred && (int)st->round == st->defer && st->cur > 1) {
+        fold_multi(ctx, st);  // G^(defer) in one joint pass; the rounds continue on the folded vector
+        st->frozen = st->deferred = false;
+    }
     IPA_CATCH
 }
 

@@ -1,5 +1,7 @@
 // ipa.cuh -- device state of one PCDL opening (pcdl.rs:183-231).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 struct halo_ipa {
@@ -17,4 +19,10 @@ struct halo_ipa {
     bool have_pbar = false;
     bool frozen = false;  // generator vector frozen at M0 elements (ctx->ipa_frozen holds s, tL, tR)
     uint32_t M0 = 0;
+    // deferred head: the first `defer` rounds leave the generators untouched (L / R over GS itself with per-index
+    // coefficients, fixed-base tables when present); k_fold_multi then materialises G^(defer) in one joint pass
+    int defer = 0;
+    bool deferred = false, fixed_ok = false;
+    halo::affine_t hprime;  // affine H' on the host (the FIXED-base L / R add dot * H' there)
+    std::vector<halo::fr_t> defer_xis;
 };

@@ -22,6 +22,8 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
 // First `passes` levels of the bucket sums as flat pairwise affine additions with batched inversion (msm_pairs.cu).
 const affine_t* pair_tree_enqueue(halo_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const MsmInput& in, const uint32_t* entries,
                                   const uint32_t* total_slots, uint64_t slots_max, int passes);
+// vals[i] <- 1 / vals[i] for n non-zero elements of Fq, in place (Montgomery's trick over a product hierarchy, msm_pairs.cu)
+void batch_invert(halo_ctx* ctx, cudaStream_t st, fq_t* vals, uint32_t n, DevBuf& scratch);
 // Builds the table of precomputed multiples for the resident generators (FIXED-base mode).
 void msm_precompute_tables(halo_ctx* ctx, int force_c);
 // MSM over resident generators G_first.., FIXED-base when available.

@@ -297,4 +297,40 @@ const affine_t* pair_tree_enqueue(halo_ctx* ctx, MsmWorkspace& ws, cudaStream_t 
     return src;
 }
 
+// In-place inversion of n non-zero field elements through the same product hierarchy (3 multiplications per element
+// plus one Fermat inversion per ~256 .. 65536 elements instead of one per element).  `scratch` grows as needed.
+void batch_invert(halo_ctx* ctx, cudaStream_t st, fq_t* vals, uint32_t n, DevBuf& scratch) {
+    if (n == 0) return;
+    uint32_t sizes[8], grids[8];
+    int L = 0;
+    sizes[0] = n;
+    grids[0] = 0;
+    while (sizes[L] > PT_INV_MAX) {
+        uint32_t b2 = ceil_div(ceil_div(sizes[L], 32u * PT_KU), 4);
+        sizes[L + 1] = b2 * 128u;
+        grids[L + 1] = b2;
+        L++;
+    }
+    L++;
+    size_t total = 0;
+    for (int j = 0; j < L; j++) total += (size_t)sizes[j] * (j == 0 ? 1 : 2);  // level 0: prefixes only (values are `vals`)
+    scratch.reserve(total * sizeof(fq_t));
+    fq_t* lv = scratch.as<fq_t>();
+    fq_t* v[8];
+    fq_t* pr[8];
+    v[0] = vals;
+    pr[0] = lv;
+    lv += sizes[0];
+    for (int j = 1; j < L; j++) {
+        v[j] = lv;
+        pr[j] = lv + sizes[j];
+        lv += (size_t)sizes[j] * 2;
+    }
+    for (int j = 0; j + 1 < L; j++) k_prod_up<<<grids[j + 1], 128, 0, st>>>(v[j], sizes[j], pr[j], v[j + 1]);
+    k_inv<<<ceil_div(sizes[L - 1], 128), 128, 0, st>>>(v[L - 1], sizes[L - 1]);
+    for (int j = L - 2; j >= 0; j--) k_prod_down<<<grids[j + 1], 128, 0, st>>>(v[j], sizes[j], pr[j], v[j + 1]);
+    ctx->kernel_launches += 2 * (uint64_t)(L - 1) + 1;
+    HALO_CUDA(cudaGetLastError());
+}
+
 }  // namespace halo

@@ -299,3 +299,49 @@ def test_open_and_full_check_2_20(ctx, oracle):
         assert e.value.code == O.pcdl_check(Cm, d, z, v, O.EvalProof.from_buffer_copy(bytes(bad)), threads=16)
     finally:
         ctx.derive_generators(1 << 16)
+
+
+@pytest.mark.parametrize("n,defer", [(2, 1), (4, 2), (16, 4), (64, 3), (1024, 1), (1024, 2), (1024, 3), (1 << 14, 3), (1 << 14, 4)])
+def test_open_deferred_head_rounds(env, n, defer):
+    """pcdl.rs:216-218 unrolled: the first `defer` rounds leave the generators untouched (L / R as MSMs over GS with
+    per-index coefficients) and k_fold_multi materialises G^(defer) in one joint pass.  Same L, R, U, c as the oracle's
+    round-by-round fold, hiding and non-hiding."""
+    ctx, O, pcdl = env["ctx"], env["O"], env["pcdl"]
+    d = n - 1
+    p = O.random_scalars(max(1, n - n // 5), 4000 + n + defer)
+    z = O.random_scalars(1, 11)[0]
+    w, wb = O.random_scalars(2, 12)
+    q = O.random_scalars(max(1, p.shape[0] - 1), 13)
+    ctx.set_tuning("ipa_defer_rounds", defer)
+    try:
+        Cm = pcdl.commit(ctx, p, d)
+        _same_proof(O, pcdl.open(ctx, p, Cm, d, z), O.pcdl_open(p, Cm, d, z, threads=8))
+        if n > 2:
+            Cw = pcdl.commit(ctx, p, d, w)
+            _same_proof(O, pcdl.open(ctx, p, Cw, d, z, w, q, wb), O.pcdl_open(p, Cw, d, z, w, q, wb, threads=8))
+    finally:
+        ctx.set_tuning("ipa_defer_rounds", -1)
+
+
+def test_open_deferred_head_fixed_base_2_17(ctx, oracle):
+    """The automatic policy: with FIXED-base tables covering the opening, three rounds are deferred and their L / R take
+    the shared-bucket-set path (dot * H' added on the host).  n = 2^17 is the smallest size it triggers at; the oracle
+    re-opens by the reference's round-by-round algorithm."""
+    from halo_accumulation_b200 import pcdl
+
+    O = oracle
+    n = 1 << 17
+    d = n - 1
+    ctx.derive_generators(n)
+    try:
+        ctx.precompute_generators(0)
+        S, Hh = ctx.get_SH()
+        O.set_params(S, Hh, ctx.get_generators(0, n))
+        p = O.random_scalars(n - 777, 21)
+        z = O.random_scalars(1, 22)[0]
+        Cm = pcdl.commit(ctx, p, d)
+        _same_proof(O, pcdl.open(ctx, p, Cm, d, z), O.pcdl_open(p, Cm, d, z, threads=16))
+    finally:
+        ctx.derive_generators(1 << 16)
+        S, Hh = ctx.get_SH()
+        O.set_params(S, Hh, ctx.get_generators(0, 1 << 16))
