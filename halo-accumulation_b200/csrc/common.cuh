@@ -135,6 +135,8 @@ struct halo_ctx {
     size_t pinned_cap = 0;
     int force_c = 0;
     int tune_acc_static = 0, tune_acc_blocks_per_sm = 0;
+    bool force_two_lanes = false;  // run a pair of large MSMs (deferred IPA rounds) on the two lanes as well
+    int tune_ipa_two_lanes = 1, tune_ipa_freeze_len = 0;
     int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
     int tune_pair_passes = -1;  // -1: automatic; 0: XYZZ accumulation only; P > 0: force P pair-tree passes
     uint64_t kernel_launches = 0;

@@ -12,6 +12,7 @@
 #include "ipa.cuh"
 
 #include <cstring>
+#include <functional>
 
 #include "../../include/halo_b200.h"
 #include "msm.cuh"
@@ -515,9 +516,10 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
     fr_t* scal = reinterpret_cast<fr_t*>(reinterpret_cast<char*>(ctx->ipa_tail.p) + sizeof(affine_t));
     vec_dot(ctx, c + m, z, m, scal + 2, scal);          // dot_l = <c_r, z_l>
     vec_dot(ctx, c, z + m, m, scal + 2, scal + 1);      // dot_r = <c_l, z_r>
-    if (!st->frozen && ((st->defer > 0 && st->round == 0) || st->cur <= IPA_FREEZE_LEN)) {  // freeze the generator vector
+    const uint64_t freeze_len = ctx->tune_ipa_freeze_len > 0 ? (uint64_t)ctx->tune_ipa_freeze_len : IPA_FREEZE_LEN;
+    if (!st->frozen && ((st->defer > 0 && st->round == 0) || st->cur <= freeze_len)) {  // freeze the generator vector
         st->frozen = true;                                                                  // (see k_frozen_scalars)
-        st->deferred = st->cur > IPA_FREEZE_LEN;  // a head freeze is undone by k_fold_multi after `defer` rounds
+        st->deferred = st->cur > freeze_len;  // a head freeze is undone by k_fold_multi after `defer` rounds
         st->M0 = (uint32_t)st->cur;
         ctx->ipa_frozen.reserve((size_t)3 * st->M0 * sizeof(fr_t));
         k_fill_one<<<(st->M0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ipa_frozen.as<fr_t>(), st->M0);
@@ -557,20 +559,25 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
             in[k].n_tail = 1;
         }
     }
-    if (host_tail) HALO_CUDA(cudaMemcpyAsync(dots, scal, sizeof dots, cudaMemcpyDeviceToHost, ctx->stream));
-    xyzz_t out[2];
-    msm_batch(ctx, in, 2, out);
-    if (host_tail) {
+    xyzz_t out[2], tails[2];
+    std::function<void()> tail_fn = [&]() {  // dot_l H', dot_r H' on the host while the MSM kernels run
         xyzz_t hp;
         xyzz_from_affine(hp, st->hprime);
         for (int k = 0; k < 2; k++) {
             uint32_t kc[8];
             fp_to_canon(kc, dots[k]);
-            xyzz_t t;
-            xyzz_mul_canon(t, hp, kc);
-            xyzz_add(out[k], t);
+            xyzz_mul_canon(tails[k], hp, kc);
         }
+    };
+    if (host_tail) {
+        HALO_CUDA(cudaMemcpyAsync(dots, scal, sizeof dots, cudaMemcpyDeviceToHost, ctx->stream));
+        HALO_CUDA(cudaStreamSynchronize(ctx->stream));  // two dot products: microseconds
     }
+    ctx->force_two_lanes = host_tail && ctx->tune_ipa_two_lanes != 0;
+    msm_batch(ctx, in, 2, out, host_tail ? &tail_fn : nullptr);
+    ctx->force_two_lanes = false;
+    if (host_tail)
+        for (int k = 0; k < 2; k++) xyzz_add(out[k], tails[k]);
     jac_t j;
     xyzz_to_jac(j, out[0]);
     memcpy(L_jac, &j, 96);

@@ -14,6 +14,8 @@
 // and selects the precomputed multiple instead, so the bucket reduction and the Horner doublings are paid once, not W
 // times, and the window can be as wide as the bucket memory allows.
 // Integer pipe bound (IMAD); see DESIGN.md for the roofline accounting.
+#include <functional>
+
 #include "common.cuh"
 #include "msm.cuh"
 
@@ -756,7 +758,7 @@ void msm_finish_host(const xyzz_t* parts, const MsmPlan& plan, xyzz_t& out) {
 
 // Enqueue `count` MSMs back to back on the context stream (they share the workspace, so they serialise on the
 // stream), then one D2H of all partial sums, one synchronisation, and the host finish per MSM.
-void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs) {
+void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, const std::function<void()>* while_running) {
     constexpr int MAXB = 4, SLOT = 3 * MSM_MAX_WINDOWS;
     if (count > MAXB) throw CudaError{cudaErrorInvalidValue, "msm_batch: count > 4", __FILE__, __LINE__};
     MsmPlan plans[MAXB];
@@ -771,7 +773,7 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs) {
     // two MSMs in a batch that are small enough to be latency bound run on two streams with separate workspaces
     bool two_lanes = false;
     if (count == 2 && ctx->stream2 && ins[0].n + ins[0].n_tail > 0 && ins[1].n + ins[1].n_tail > 0 &&
-        (uint64_t)ins[0].n + ins[1].n <= (1u << 19) && !ctx->profile) {
+        ((uint64_t)ins[0].n + ins[1].n <= (1u << 19) || ctx->force_two_lanes) && !ctx->profile) {
         two_lanes = true;
         HALO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));       // inputs produced on the main stream are complete
         HALO_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
@@ -790,6 +792,7 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs) {
         HALO_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
         HALO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later main-stream work (the fold) is ordered after lane 1
     }
+    if (while_running) (*while_running)();  // host work that overlaps the kernels enqueued above
     if (any) HALO_CUDA(cudaStreamSynchronize(ctx->stream));
     if (any && ctx->profile) {
         float t[5];

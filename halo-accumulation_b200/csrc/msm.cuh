@@ -1,5 +1,7 @@
 // msm.cuh -- internal interface of the MSM engine (msm.cu).
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 
 namespace halo {
@@ -29,7 +31,7 @@ void msm_precompute_tables(halo_ctx* ctx, int force_c);
 // MSM over resident generators G_first.., FIXED-base when available.
 void msm_gens_device(halo_ctx* ctx, const fr_t* d_scalars, uint64_t first, uint64_t n, xyzz_t& out);
 // Up to 4 MSMs enqueued back to back with a single synchronisation; results on the host.
-void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs);
+void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, const std::function<void()>* while_running = nullptr);
 void msm_finish_host(const xyzz_t* wsums, const MsmPlan& plan, xyzz_t& out);
 // Full MSM with device-resident inputs; synchronises the context stream and returns the point on the host.
 void msm_device(halo_ctx* ctx, const affine_t* d_bases, const fr_t* d_scalars, uint64_t n, xyzz_t& out);

@@ -9,6 +9,10 @@ n = 1 << lg
 ctx = H.Context(0, n)
 ctx.derive_generators(n); ctx.precompute_generators(0)
 lib = ctx._lib
+import os
+for kv in os.environ.get('TUNE', '').split(','):
+    if kv:
+        k_, v_ = kv.split('='); ctx.set_tuning(k_, int(v_))
 rng = np.random.Generator(np.random.PCG64(5))
 def rs(k):
     a = rng.integers(0, 1 << 64, size=(k, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 62) - 1); return a
@@ -34,5 +38,5 @@ for rep in range(2):
     assert lib.halo_ipa_finish(st, p64(U), p64(c)) == 0
     lib.halo_ipa_destroy(st)
     total = time.perf_counter() - t0
-print(json.dumps(dict(lg=lg, begin_ms=t_begin * 1e3, total_ms=total * 1e3, lr_ms=sum(r[2] for r in rows), fold_ms=sum(r[3] for r in rows))))
+print(json.dumps(dict(tune=os.environ.get('TUNE',''), lg=lg, begin_ms=t_begin * 1e3, total_ms=total * 1e3, lr_ms=sum(r[2] for r in rows), fold_ms=sum(r[3] for r in rows))))
 for r in rows: print("round %2d m=%8d lr=%8.3f ms fold=%8.3f ms" % r)
