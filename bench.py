@@ -12,8 +12,9 @@ N * 2^L-point MSM) and the partial results are combined with one all-gather per 
 `value`     : points/s, inputs resident in HBM, CUDA events on the library's stream, max over ranks.
 `e2e`       : same metric through the C ABI call halo_msm_gens with HOST (pinned) scalars: H2D of the step's scalars
               and D2H of the window sums inside the timed region.
-`roofline`  : integer pipe (IMAD) for the dominant kernel k_accumulate; peak measured in-run by the library's
-              IMAD microbenchmark (MEASURED_PEAKS.json carries no integer figure).
+`roofline`  : integer pipe (IMAD) for the dominant phase, the bucket accumulation (pair-tree passes k_pair_fwd / k_pair_bwd
+              and the XYZZ tail k_accumulate); peak measured in-run by the library's IMAD microbenchmark
+              (MEASURED_PEAKS.json carries no integer figure).
 `cpu_baseline` / `--impl reference`: the reference's arkworks algorithm restated in C (oracle/), timed on the host
               cores on a bounded sample of the same workload.  The reference itself is Rust and cannot run here.
 """
@@ -221,7 +222,7 @@ def run_ours(args):
         t = nxt
     barrier()
     e2e_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-    # ---- per-phase profile of the dominant kernel (k_accumulate), CUDA events on the library's stream ----
+    # ---- per-phase profile (dominant phase: bucket accumulation), CUDA events on the library's stream ----
     ctx.set_profiling(True)
     acc_ms = []
     for _ in range(max(3, min(args.steps, 5))):
@@ -250,7 +251,7 @@ def run_ours(args):
         achieved = alg_imad / (phases["accumulate"] * 1e-3) / 1e12
         traffic = None  # dram__bytes_read + dram__bytes_write of one k_accumulate launch, from the committed ncu capture
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_accumulate"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["accumulate_phase_pair_tree"]
             if tj["workload"] == f"pallas_msm_2^{args.log_n}_per_gpu" and tj["fixed_base_tables"] == (not args.no_precompute):
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
@@ -280,8 +281,9 @@ def run_ours(args):
                     "blocking_call": {"api": "halo_msm_gens", "value": total_points / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms}},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD32/s",
-                         "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r01_traffic.json)",
+            "roofline": {"bound": "imad", "kernel": "bucket accumulation phase: k_pair_fwd / k_pair_bwd x 4 tree passes (affine, batched inversion) + k_accumulate (XYZZ tail)", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD32/s",
+                         "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "DRAM bytes of the phase per MSM (ncu, profiles/r01_traffic.json); pass 0 of the tree (19 of 33 ms) is HBM bound on 128-byte random accesses at 3.6-4.0 TB/s, the rest integer-pipe bound",
+                         "hbm_gbs_phase": (traffic / (phases["accumulate"] * 1e-3) / 1e9) if traffic else None,
                          "peak_source": "measured in this run (libhalo_b200 mad.lo.u32 microbenchmark, 16 independent chains per thread, all SMs); MEASURED_PEAKS.json has no integer-pipe figure. IMAD.WIDE / IMAD.HI issue at half this rate (profiles/r01_imad_pipe_rates.jsonl)",
                          "algorithmic": f"{n} pts x {CANON_W} windows x 10 modmul x {IMAD_PER_MODMUL} IMAD32 per launch",
                          "launch_ms": phases["accumulate"], "phases_ms": phases,
