@@ -345,3 +345,48 @@ def test_open_deferred_head_fixed_base_2_17(ctx, oracle):
         ctx.derive_generators(1 << 16)
         S, Hh = ctx.get_SH()
         O.set_params(S, Hh, ctx.get_generators(0, 1 << 16))
+
+
+def test_kat_file_reproduced_on_the_gpu(env):
+    """The committed known-answer file (tests/golden/kat_pcdl_2_10.json, canonical arkworks encodings): commitments,
+    every L / R, U, c, the hiding proof and a full accumulation step computed on the GPU serialise to the same bytes."""
+    import importlib.util
+    import json
+    import os
+
+    ctx, O, pcdl, acc = env["ctx"], env["O"], env["pcdl"], env["acc"]
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_kat", os.path.join(here, "golden", "make_kat.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    kat = json.load(open(os.path.join(here, "golden", "kat_pcdl_2_10.json")))
+    n, d, deg = kat["n"], kat["d"], kat["poly_len"]
+    p, z, w = mk.xs("halo-b200-kat/p", deg), mk.xs("halo-b200-kat/z", 1)[0], mk.xs("halo-b200-kat/w", 1)[0]
+    pbar, wbar = mk.xs("halo-b200-kat/pbar", deg - 1), mk.xs("halo-b200-kat/wbar", 1)[0]
+    assert mk.fr_hex(p[0]) == kat["samples"]["p[0]"] and mk.fr_hex(z) == kat["samples"]["z"]
+    S, H = ctx.get_SH()
+    assert mk.pt_hex(S) == kat["params"]["S"] and mk.pt_hex(H) == kat["params"]["H"]
+    assert mk.pt_hex(O.affine_to_jac(ctx.get_generators(1023, 1))[0]) == kat["params"]["G_1023"]
+    from halo_accumulation_b200 import group
+
+    v = group.scalar_dot(ctx, p, group.construct_powers(ctx, z, deg))
+    assert mk.fr_hex(v) == kat["v = p(z)"]
+    assert mk.pt_hex(ctx.msm_gens(p)) == kat["msm <p, GS[0..poly_len)>"]
+    C0 = pcdl.commit(ctx, p, d)
+    assert mk.pt_hex(C0) == kat["non_hiding"]["C = commit(p, d, None)"]
+    assert mk.proof_dict(pcdl.open(ctx, p, C0, d, z)) == kat["non_hiding"]["proof = open(rng, p, C, d, z, None)"]
+    C1 = pcdl.commit(ctx, p, d, w)
+    assert mk.pt_hex(C1) == kat["hiding"]["C = commit(p, d, Some(w))"]
+    pi1 = pcdl.open(ctx, p, C1, d, z, w, pbar, wbar)
+    assert mk.proof_dict(pi1) == kat["hiding"]["proof"]
+    h, U = pcdl.succinct_check(ctx, C1, d, z, v, pi1)
+    assert [mk.fr_hex(x) for x in h.xis] == kat["hiding"]["succinct_check.h.xis"] and mk.pt_hex(U) == kat["hiding"]["succinct_check.U"]
+    inst = acc.new_instance(C1, d, z, v, pi1)
+    a = acc.prover(ctx, d, [inst], mk.xs("halo-b200-kat/h0", 2), mk.xs("halo-b200-kat/acc-w", 1)[0],
+                   mk.xs("halo-b200-kat/acc-pbar", n - 1), mk.xs("halo-b200-kat/acc-wbar", 1)[0])
+    acc.verifier(ctx, d, [inst], a)
+    acc.decider(ctx, a)
+    ka = kat["accumulator = acc::prover(rng, d, [instance])"]
+    assert mk.pt_hex(np.array(a.C_bar)) == ka["C_bar"] and mk.fr_hex(np.array(a.z)) == ka["z"] and mk.fr_hex(np.array(a.v)) == ka["v"]
+    assert mk.proof_dict(a.pi) == ka["pi"]
+    assert mk.pt_hex(np.array(a.U0)) == ka["pi_V.U0"] and mk.fr_hex(np.array(a.w)) == ka["pi_V.w"]

@@ -2,6 +2,7 @@
 tests/golden/consts_golden.npz), to the pure-Python restatement (oracle/pyref.py) and to the structural tests of
 the reference (pcdl.rs:351-438, :485-509; pedersen.rs:54-63; acc.rs:298-315)."""
 import hashlib
+import os
 import random
 
 import numpy as np
@@ -182,3 +183,16 @@ def test_acc_scheme(oracle):
         bad.v[0] ^= 1
         assert oracle.acc_verifier(d, qs, bad) == -17
     assert oracle.acc_decider(acc) == 0
+
+
+def test_kat_file_is_reproduced_by_the_oracle():
+    """tests/golden/kat_pcdl_2_10.json (known answers in the reference's canonical encodings, for third-party checks
+    against real arkworks) is exactly what the oracle computes today."""
+    import importlib.util
+    import json
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_kat", os.path.join(here, "golden", "make_kat.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    assert mk.build() == json.load(open(os.path.join(here, "golden", "kat_pcdl_2_10.json")))
