@@ -506,6 +506,59 @@ int halo_h_msm(halo_ctx* ctx, const uint64_t* xis, uint32_t lg_n, uint64_t out_j
     HALO_CATCH(ctx)
 }
 
+int halo_h_msm_with(halo_ctx* ctx, const uint64_t* xis, uint32_t lg_n, const uint64_t* bases_affine, const uint8_t* inf_flags,
+                    const uint64_t* scalars, uint64_t k, uint64_t out_h_jac[12], uint64_t out_small_jac[12]) {
+    if (!ctx || !xis || !out_h_jac || !out_small_jac || ((!bases_affine || !scalars) && k)) return HALO_EINVAL;
+    if (int rc = check_lg(ctx, lg_n, true)) return rc;
+    if (k > 4096) return fail(ctx, HALO_EINVAL, "halo_h_msm_with: the companion MSM is meant to be small (k <= 4096)");
+    HALO_TRY(ctx)
+    uint64_t n = (uint64_t)1 << lg_n;
+    ctx->stage_scalars.reserve(n * sizeof(fr_t));
+    fr_t one;
+    fp_one(one);
+    vec_h_expand(ctx, reinterpret_cast<const fr_t*>(xis), (int)lg_n, one, false, ctx->stage_scalars.as<fr_t>());
+    MsmInput in[2];
+    in[0].scalars = ctx->stage_scalars.as<fr_t>();
+    in[0].n = (uint32_t)n;
+    if (ctx->use_fixed && ctx->pre_n == ctx->n_gens && ctx->gens_pre.p && n >= (1u << 17) && n * 8 >= ctx->pre_n) {
+        in[0].bases = ctx->gens_pre.as<affine_t>();
+        in[0].fixed_stride = (uint32_t)ctx->pre_n;
+        in[0].fixed_first = 0;
+    } else {
+        in[0].bases = ctx->gens.as<affine_t>();
+    }
+    // companion: bases | scalars | infinity flags staged in stage_misc
+    const size_t kk = k ? k : 1;
+    ctx->stage_misc.reserve(kk * (sizeof(affine_t) + sizeof(fr_t) + 1));
+    affine_t* d_b = ctx->stage_misc.as<affine_t>();
+    fr_t* d_s = reinterpret_cast<fr_t*>(d_b + kk);
+    uint8_t* d_i = reinterpret_cast<uint8_t*>(d_s + kk);
+    if (k) {
+        HALO_CUDA(cudaMemcpyAsync(d_b, bases_affine, k * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+        HALO_CUDA(cudaMemcpyAsync(d_s, scalars, k * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (inf_flags) {
+            HALO_CUDA(cudaMemcpyAsync(d_i, inf_flags, k, cudaMemcpyHostToDevice, ctx->stream));
+            k_mark_infinity<<<(unsigned)((k + 255) / 256), 256, 0, ctx->stream>>>(d_b, d_i, k);
+            ctx->kernel_launches++;
+        }
+    }
+    in[1].bases = d_b;
+    in[1].scalars = d_s;
+    in[1].n = (uint32_t)k;
+    xyzz_t out[2];
+    ctx->force_two_lanes = k > 0;
+    try {
+        msm_batch(ctx, in, 2, out);
+    } catch (...) {
+        ctx->force_two_lanes = false;
+        throw;
+    }
+    ctx->force_two_lanes = false;
+    out_jac_from_xyzz(out[0], out_h_jac);
+    out_jac_from_xyzz(out[1], out_small_jac);
+    HALO_CATCH(ctx)
+}
+
 // out != NULL: coefficients to the host.  out == NULL: the polynomial stays on the device (ctx->poly_dev) and
 // *degree_out receives its degree (DensePolynomial::degree: index of the highest non-zero coefficient).
 static int h_lincomb_impl(halo_ctx* ctx, const uint64_t* h0, uint64_t n_h0, const uint64_t* alphas, const uint64_t* xis,

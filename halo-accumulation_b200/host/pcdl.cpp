@@ -136,8 +136,17 @@ static EvalProof open_impl(halo_ctx* ctx, const PolyView* p, uint64_t deg, const
     return pi;
 }
 
-std::pair<HPoly, PallasPoint> succinct_check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z,
-                                             const PallasScalar& v, const EvalProof& pi) {
+// Everything of succinct_check (pcdl.rs:252-314) up to its group equation, which is left as one small MSM:
+//   C_lg == c U + v' H'   <=>   C' + sum_k scalars[k] * aff[k] == 0
+struct SuccinctPrep {
+    HPoly h;
+    PallasPoint U, C_prime;
+    std::vector<affine_t> aff;
+    std::vector<uint8_t> inf;
+    std::vector<PallasScalar> scalars;
+};
+static SuccinctPrep succinct_prepare(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z, const PallasScalar& v,
+                                     const EvalProof& pi) {
     uint64_t n = d + 1;
     ensure(is_pow2(n), HALO_EINVAL, "d+1 is not a power of 2!");           // :261
     ensure(n <= halo_num_generators(ctx), HALO_EINVAL, "d was larger than D!");  // :262
@@ -187,22 +196,33 @@ std::pair<HPoly, PallasPoint> succinct_check(halo_ctx* ctx, const PallasPoint& C
     PallasScalar v_prime = pi.c * h.eval(z);        // :304
     scalars.push_back(xis[0] * v - xis[0] * v_prime);  // v H' - v' H' with H' = xi_0 H  (:285, :288, :308)
     scalars.push_back(-pi.c);                          // - c U
+    return SuccinctPrep{std::move(h), pi.U, C_prime, std::move(aff), std::move(inf), std::move(scalars)};
+}
+
+std::pair<HPoly, PallasPoint> succinct_check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z,
+                                             const PallasScalar& v, const EvalProof& pi) {
+    SuccinctPrep sp = succinct_prepare(ctx, C, d, z, v, pi);
     uint64_t out[12];
-    check_rc(ctx, halo_msm(ctx, reinterpret_cast<const uint64_t*>(aff.data()), inf.data(),
-                           reinterpret_cast<const uint64_t*>(scalars.data()), aff.size(), out));
-    PallasPoint lhs = C_prime + point_load(out);
+    check_rc(ctx, halo_msm(ctx, reinterpret_cast<const uint64_t*>(sp.aff.data()), sp.inf.data(),
+                           reinterpret_cast<const uint64_t*>(sp.scalars.data()), sp.aff.size(), out));
+    PallasPoint lhs = sp.C_prime + point_load(out);
     ensure(xyzz_is_inf(lhs.p), HALO_REJECT_SUCCINCT, "C_(log_n) != CM.Commit_Sigma(c || v')");  // :307-310
-    return {h, pi.U};                                                                           // :313
+    return {sp.h, sp.U};                                                                        // :313
 }
 
 void check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z, const PallasScalar& v,
            const EvalProof& pi) {
-    auto hu = succinct_check(ctx, C, d, z, v, pi);  // :332
-    const HPoly& h = hu.first;
-    // comm = pedersen::commit(None, GS[0..d+1], h.get_poly().coeffs) (:338): expansion + MSM fused on the device
-    uint64_t out[12];
-    check_rc(ctx, halo_h_msm(ctx, reinterpret_cast<const uint64_t*>(h.xis.data()), (uint32_t)h.xis.size() - 1, out));
-    ensure(hu.second == point_load(out), HALO_REJECT_U, "U != CM.Commit(ck, h_vec)");  // :339
+    // succinct_check (:332) and comm = pedersen::commit(None, GS[0..d+1], h.get_poly().coeffs) (:338).  The challenges
+    // (hence h) need only the transcript, so the small MSM of the succinct check and the expansion + MSM <G, h> run
+    // concurrently on the device; the two `ensure!`s are evaluated in the reference's order.
+    SuccinctPrep sp = succinct_prepare(ctx, C, d, z, v, pi);
+    uint64_t out_h[12], out_s[12];
+    check_rc(ctx, halo_h_msm_with(ctx, reinterpret_cast<const uint64_t*>(sp.h.xis.data()), (uint32_t)sp.h.xis.size() - 1,
+                                  reinterpret_cast<const uint64_t*>(sp.aff.data()), sp.inf.data(),
+                                  reinterpret_cast<const uint64_t*>(sp.scalars.data()), sp.aff.size(), out_h, out_s));
+    PallasPoint lhs = sp.C_prime + point_load(out_s);
+    ensure(xyzz_is_inf(lhs.p), HALO_REJECT_SUCCINCT, "C_(log_n) != CM.Commit_Sigma(c || v')");  // :307-310
+    ensure(sp.U == point_load(out_h), HALO_REJECT_U, "U != CM.Commit(ck, h_vec)");                // :339
 }
 
 EvalProof proof_from_c(const halo_eval_proof& p) {

@@ -127,6 +127,12 @@ int halo_h_expand(halo_ctx *ctx, const uint64_t *xis /*[lg_n+1][4]*/, uint32_t l
 /* U' = <GS[0..n), coeffs(h)>: expansion and MSM without the coefficients ever leaving the device.
  * Replaces pcdl.rs:338 (`pedersen::commit(None, &GS[0..n], &h.get_poly().coeffs)`), the decider's MSM. */
 int halo_h_msm(halo_ctx *ctx, const uint64_t *xis /*[lg_n+1][4]*/, uint32_t lg_n, uint64_t out_jac[12]);
+/* pcdl::check (pcdl.rs:323-342) in one call: <G, coeffs(h)> as above AND the k-point MSM that succinct_check's group
+ * equation reduces to (pcdl.rs:285-310: k = 2 lg n + 2 points L_i, R_i, H, U with host-computed scalars), run
+ * concurrently on two streams; the challenges need only the transcript, so neither waits for the other. */
+int halo_h_msm_with(halo_ctx *ctx, const uint64_t *xis /*[lg_n+1][4]*/, uint32_t lg_n, const uint64_t *bases_affine /*[k][8]*/,
+                    const uint8_t *inf_flags /*[k] or NULL*/, const uint64_t *scalars /*[k][4]*/, uint64_t k,
+                    uint64_t out_h_jac[12], uint64_t out_small_jac[12]);
 /* out = h_0 + sum_{i<m} alphas[i+1] * coeffs(h_i), zero-padded to n = 2^lg_n.
  * Replaces AccumulatedHPolys::get_poly, acc.rs:85-94. */
 int halo_h_lincomb(halo_ctx *ctx, const uint64_t *h0 /*[n_h0][4]*/, uint64_t n_h0, const uint64_t *alphas /*[m+1][4]*/,

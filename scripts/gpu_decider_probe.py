@@ -20,7 +20,7 @@ def best(f, reps=5):
     return b
 h, U = pcdl.succinct_check(ctx, Cm, d, z, v, pi)
 out = np.zeros(12, dtype=np.uint64)
-ctx.set_profiling(True)
+ctx.set_profiling(bool(int(__import__("os").environ.get("PROF", "0"))))
 res = dict(lg=lg, check_ms=best(lambda: pcdl.check(ctx, Cm, d, z, v, pi)), succinct_ms=best(lambda: pcdl.succinct_check(ctx, Cm, d, z, v, pi)),
            h_msm_ms=best(lambda: ctx._chk(ctx._lib.halo_h_msm(ctx._h, p64(h.xis), lg, p64(out)))))
 res["h_msm_phases"] = ctx.last_msm_timings()
