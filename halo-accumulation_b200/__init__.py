@@ -201,6 +201,11 @@ class Context:
         self._chk(self._lib.halo_test_vec_bench(self._h, int(kind), C.c_uint64(n), C.byref(ms)))
         return ms.value
 
+    def test_gather_throughput(self, table_bytes, blocks, threads, iters, nbytes=64):
+        ms = C.c_float()
+        self._chk(self._lib.halo_test_gather_throughput(self._h, C.c_uint64(table_bytes), blocks, threads, iters, nbytes, C.byref(ms)))
+        return ms.value
+
     def test_imad_throughput(self, kind, blocks, threads, iters):
         ms, ck = C.c_float(), C.c_uint64()
         self._chk(self._lib.halo_test_imad_throughput(self._h, kind, blocks, threads, iters, C.byref(ms), C.byref(ck)))

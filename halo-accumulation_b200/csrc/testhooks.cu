@@ -51,6 +51,41 @@ __global__ void k_add_chain(const jac_t* pts, uint64_t n, int dbls, jac_t* out) 
     *out = j;
 }
 
+
+// Random 64-byte gathers (the access pattern of the bucket accumulation: one affine base per entry) from a table far
+// larger than the L2: every thread walks `iters` pseudo-random 64-byte-aligned slots and xors what it reads.
+__global__ void __launch_bounds__(256) k_gather_tp(const uint4* __restrict__ table, uint64_t slots, int iters, int bytes, uint32_t* sink) {
+    uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9e3779b97f4a7c15ull + 0x1234567ull;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < iters; i += 4) {  // four independent gathers in flight per thread
+        const uint4* p[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            x ^= x << 13;
+            x ^= x >> 7;
+            x ^= x << 17;
+            p[k] = table + __umul64hi(x, slots) * 4;  // uniform in [0, slots)
+        }
+        uint4 v[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            v[k][0] = p[k][0];
+            if (bytes >= 32) v[k][1] = p[k][1];
+            if (bytes >= 64) {
+                v[k][2] = p[k][2];
+                v[k][3] = p[k][3];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            acc.x ^= v[k][0].x; acc.y ^= v[k][0].y; acc.z ^= v[k][0].z; acc.w ^= v[k][0].w;
+            if (bytes >= 32) { acc.x ^= v[k][1].x; acc.y ^= v[k][1].y; acc.z ^= v[k][1].z; acc.w ^= v[k][1].w; }
+            if (bytes >= 64) { acc.x ^= v[k][2].x ^ v[k][3].x; acc.y ^= v[k][2].y ^ v[k][3].y; acc.z ^= v[k][2].z ^ v[k][3].z; acc.w ^= v[k][2].w ^ v[k][3].w; }
+        }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x5a5a5a5au) sink[0] = acc.x;
+}
+
 template <int ILP, int V>
 __global__ void __launch_bounds__(512) k_fp_mul_tp(int iters, uint32_t* sink) {
     fq_t x[ILP], y;
@@ -255,6 +290,36 @@ int halo_test_fp_mul_throughput(halo_ctx* ctx, int blocks, int threads, int iter
     if (checksum) *checksum = h[1];
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    sink.release();
+    T_CATCH(ctx)
+}
+
+int halo_test_gather_throughput(halo_ctx* ctx, uint64_t table_bytes, int blocks, int threads, int iters, int bytes, float* ms) {
+    if (!ctx || !ms || table_bytes < 4096 || threads > 256) return HALO_EINVAL;
+    T_TRY(ctx)
+    DevBuf table, sink;
+    table.reserve(table_bytes);
+    sink.reserve(16);
+    HALO_CUDA(cudaMemsetAsync(table.p, 0x3c, table_bytes, ctx->stream));
+    cudaEvent_t e0, e1;
+    HALO_CUDA(cudaEventCreate(&e0));
+    HALO_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        HALO_CUDA(cudaEventRecord(e0, ctx->stream));
+        k_gather_tp<<<blocks, threads, 0, ctx->stream>>>(table.as<uint4>(), table_bytes / 64, iters, bytes, sink.as<uint32_t>());
+        HALO_CUDA(cudaEventRecord(e1, ctx->stream));
+        HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+        float t;
+        HALO_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        if (rep > 0 && t < best) best = t;
+    }
+    ctx->kernel_launches += 3;
+    HALO_CUDA(cudaGetLastError());
+    *ms = best;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    table.release();
     sink.release();
     T_CATCH(ctx)
 }

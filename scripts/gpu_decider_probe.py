@@ -6,7 +6,12 @@ from halo_accumulation_b200 import pcdl, group
 from halo_accumulation_b200._capi import p64
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 n, d = 1 << lg, (1 << lg) - 1
-ctx = H.Context(0, n); ctx.derive_generators(n); ctx.precompute_generators(0)
+ctx = H.Context(0, n)
+import os
+for kv in os.environ.get('TUNE', '').split(','):
+    if kv:
+        k_, v_ = kv.split('='); ctx.set_tuning(k_, int(v_))
+ctx.derive_generators(n); ctx.precompute_generators(0)
 rng = np.random.Generator(np.random.PCG64(5))
 def rs(k):
     a = rng.integers(0, 1 << 64, size=(k, 4), dtype=np.uint64); a[:, 3] &= np.uint64((1 << 62) - 1); return a
