@@ -59,6 +59,58 @@ __device__ __forceinline__ void pt_gather(affine_t& p, bool& inf, uint32_t ent, 
     if (ent >> 31) fp_neg(p.y, p.y);
 }
 
+// Warp-cooperative version for a whole warp step: lane l needs the operands named by its entry pair e = (e.x, e.y).
+// A lane loading its own 64-byte base issues 4 LDG.128 that each touch 32 different lines, and the load/store unit, not
+// HBM, becomes the limit (measured: 20 G gathers/s per-thread against 43 G/s when 4 adjacent lanes fetch one base with
+// ONE instruction, profiles/r01_random_gather_hbm.jsonl).  So 8 rounds of one LDG.128 per lane fetch the 64 bases of the
+// warp (round r: chunk l & 3 of the base of lane (r & 3) * 8 + (l >> 2); rounds 0-3 operand a, 4-7 operand b) and a
+// padded shared-memory tile transposes them back to their owners.  All 32 lanes must call it (padding lanes pass the
+// sentinel pair).
+constexpr int PT_SM_STRIDE = 5;  // uint4 per staged base: 64 B + 16 B pad (conflict-free 64-byte reads by 8 lanes)
+struct PairTile {
+    uint4 v[32][2][PT_SM_STRIDE];
+};
+__device__ __forceinline__ void pt_gather_pair_coop(affine_t& a, bool& ainf, affine_t& b, bool& binf, uint2 e,
+                                                    const affine_t* __restrict__ bases, uint32_t n,
+                                                    const affine_t* __restrict__ tail_bases, PairTile& tile, uint32_t lane) {
+    const uint32_t c = lane & 3u;
+    constexpr int BATCH = 8;  // loads in flight per lane
+#pragma unroll
+    for (int r0 = 0; r0 < 8; r0 += BATCH) {
+        uint4 v[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) {
+            const int r = r0 + k;
+            const int owner = (r & 3) * 8 + (int)(lane >> 2);
+            const uint32_t ent = __shfl_sync(0xffffffffu, r < 4 ? e.x : e.y, owner);
+            v[k] = make_uint4(0, 0, 0, 0);
+            if (ent != PT_SENTINEL) {
+                const uint32_t idx = ent & 0x7fffffffu;
+                const affine_t* p = idx < n ? bases + idx : tail_bases + (idx - n);
+                v[k] = __ldg(reinterpret_cast<const uint4*>(p) + c);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) {
+            const int r = r0 + k;
+            tile.v[(r & 3) * 8 + (lane >> 2)][r >> 2][c] = v[k];
+        }
+    }
+    __syncwarp();
+    uint4* ap = reinterpret_cast<uint4*>(&a);
+    uint4* bp = reinterpret_cast<uint4*>(&b);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        ap[k] = tile.v[lane][0][k];
+        bp[k] = tile.v[lane][1][k];
+    }
+    __syncwarp();
+    ainf = e.x == PT_SENTINEL || affine_is_inf(a);
+    binf = e.y == PT_SENTINEL || affine_is_inf(b);
+    if (e.x != PT_SENTINEL && (e.x >> 31)) fp_neg(a.y, a.y);
+    if (e.y != PT_SENTINEL && (e.y >> 31)) fp_neg(b.y, b.y);
+}
+
 // Classification shared by both directions.  Needs y only when the x coordinates coincide.
 //   PT_ADD: den = bx - ax.   PT_DBL: den = 2 ay (ay != 0).   PT_SKIP: no inversion; the result is inf, a or b.
 __device__ __forceinline__ int pt_classify(fq_t& den, bool ainf, bool binf, const fq_t& ax, const fq_t& bx, const fq_t& ay,
@@ -85,25 +137,29 @@ __global__ void __launch_bounds__(128) k_pair_fwd(const uint32_t* __restrict__ e
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gwarp = tid >> 5, lane = tid & 31u;
     const uint32_t Q = *total_slots >> (pass + 1);
+    __shared__ PairTile tiles[PASS0 ? 4 : 1];
+    PairTile& tile = tiles[PASS0 ? (threadIdx.x >> 5) : 0];
     fq_t run;
     fp_one(run);
     if (pt_pair_index(gwarp, 0, 0) < Q) {
 #pragma unroll 2
         for (int s = 0; s < PT_K; s++) {
+            if (pt_pair_index(gwarp, s, 0) >= Q) break;  // warp uniform
             const uint32_t q = pt_pair_index(gwarp, s, lane);
-            if (q >= Q) break;
+            const bool live = q < Q;
             fq_t ax, bx, ay, by, den;
             bool ainf, binf;
             if (PASS0) {
-                const uint2 e = reinterpret_cast<const uint2*>(entries)[q];
+                uint2 e = make_uint2(PT_SENTINEL, PT_SENTINEL);
+                if (live) e = reinterpret_cast<const uint2*>(entries)[q];
                 affine_t a, b;
-                pt_gather(a, ainf, e.x, bases, n, tail_bases);
-                pt_gather(b, binf, e.y, bases, n, tail_bases);
+                pt_gather_pair_coop(a, ainf, b, binf, e, bases, n, tail_bases, tile, lane);
                 ax = a.x;
                 ay = a.y;
                 bx = b.x;
                 by = b.y;
             } else {
+                if (!live) break;
                 ax = in[2 * (size_t)q].x;
                 bx = in[2 * (size_t)q + 1].x;
                 ainf = pt_x_is_inf(ax);
@@ -116,7 +172,7 @@ __global__ void __launch_bounds__(128) k_pair_fwd(const uint32_t* __restrict__ e
                     fp_zero(by);
                 }
             }
-            const int mode = pt_classify(den, ainf, binf, ax, bx, ay, by);
+            const int mode = live ? pt_classify(den, ainf, binf, ax, bx, ay, by) : PT_SKIP;
             if (mode != PT_SKIP) {
                 prefix[q] = run;
                 fp_mul(run, run, den);
@@ -186,6 +242,9 @@ __global__ void __launch_bounds__(128, 4) k_pair_bwd(const uint32_t* __restrict_
         affine_t a, b;
         bool ainf, binf;
         if (PASS0) {
+            // per-lane gathers: this kernel is bound by its 4M + 1S per pair, and the cooperative fetch of the forward
+            // kernel (shuffles, shared-memory transpose, 16 more registers) measured 9 % slower here; prefetching the
+            // next step's entries measured 1 % slower
             const uint2 e = reinterpret_cast<const uint2*>(entries)[q];
             pt_gather(a, ainf, e.x, bases, n, tail_bases);
             pt_gather(b, binf, e.y, bases, n, tail_bases);
