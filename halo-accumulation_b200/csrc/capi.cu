@@ -154,6 +154,7 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "ipa_defer_rounds")) ctx->tune_ipa_defer = value;
     else if (!strcmp(key, "ipa_two_lanes")) ctx->tune_ipa_two_lanes = value;
     else if (!strcmp(key, "ipa_freeze_len")) ctx->tune_ipa_freeze_len = value;
+    else if (!strcmp(key, "ipa_frozen_c")) ctx->tune_ipa_frozen_c = value;
     else return fail(ctx, HALO_EINVAL, "halo_set_tuning: unknown key");
     return HALO_OK;
 }

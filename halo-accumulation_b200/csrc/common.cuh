@@ -137,6 +137,7 @@ struct halo_ctx {
     int tune_acc_static = 0, tune_acc_blocks_per_sm = 0;
     bool force_two_lanes = false;  // run a pair of large MSMs (deferred IPA rounds) on the two lanes as well
     int tune_ipa_two_lanes = 1, tune_ipa_freeze_len = 0;
+    int tune_ipa_frozen_c = 10;  // window of the frozen-tail MSMs (8192 points, latency bound in the bucket reduction): 0.78 -> 0.71 ms per round vs c = 12
     int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
     int tune_pair_passes = -1;  // -1: automatic; 0: XYZZ accumulation only; P > 0: force P pair-tree passes
     uint64_t kernel_launches = 0;

@@ -559,6 +559,8 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
             in[k].n_tail = 1;
         }
     }
+    const int saved_c = ctx->force_c;
+    if (st->frozen && !st->deferred && ctx->tune_ipa_frozen_c > 0) ctx->force_c = ctx->tune_ipa_frozen_c;
     xyzz_t out[2], tails[2];
     std::function<void()> tail_fn = [&]() {  // dot_l H', dot_r H' on the host while the MSM kernels run
         xyzz_t hp;
@@ -576,6 +578,7 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
     ctx->force_two_lanes = host_tail && ctx->tune_ipa_two_lanes != 0;
     msm_batch(ctx, in, 2, out, host_tail ? &tail_fn : nullptr);
     ctx->force_two_lanes = false;
+    ctx->force_c = saved_c;
     if (host_tail)
         for (int k = 0; k < 2; k++) xyzz_add(out[k], tails[k]);
     jac_t j;
