@@ -113,7 +113,7 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     ctx->stage_misc.release();
     ctx->poly_dev.release();
     for (halo::DevBuf* b : {&ctx->ipa_G, &ctx->ipa_cs, &ctx->ipa_zs, &ctx->ipa_pbar, &ctx->ipa_tail, &ctx->ipa_frozen,
-                           &ctx->ipa_sums, &ctx->ipa_den, &ctx->ipa_inv_scratch, &ctx->ipa_bx}) b->release();
+                           &ctx->ipa_sums, &ctx->ipa_den, &ctx->ipa_inv_scratch, &ctx->ipa_bx, &ctx->ipa_diff, &ctx->ipa_den2}) b->release();
     for (MsmWorkspace* wsp : {&ctx->ws, &ctx->ws2}) {
     MsmWorkspace& ws = *wsp;
     for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,

@@ -117,7 +117,7 @@ struct halo_ctx {
     // buffers of the (single) in-flight PCDL opening, kept across openings: cudaMalloc / cudaFree of 100+ MB per open
     // costs tens of milliseconds
     halo::DevBuf ipa_G, ipa_cs, ipa_zs, ipa_pbar, ipa_tail, ipa_frozen;
-    halo::DevBuf ipa_sums, ipa_den, ipa_inv_scratch, ipa_bx;  // generator fold: XYZZ sums, ZZ * ZZZ and the batched inversion's hierarchy
+    halo::DevBuf ipa_sums, ipa_den, ipa_inv_scratch, ipa_bx, ipa_diff, ipa_den2;  // generator fold: XYZZ sums, ZZ * ZZZ and the batched inversion's hierarchy
     bool ipa_busy = false;
     // asynchronous MSM pipeline (halo_msm_gens_submit / _collect): two in-flight slots, H2D on its own stream so the copy
     // of call k+1 overlaps the kernels of call k

@@ -36,51 +36,19 @@ constexpr uint64_t IPA_FREEZE_LEN = HALO_IPA_FREEZE_LEN;
 // round is decomposed once on the host (Babai rounding against the reduced basis (a1, b1), (a2, b2) of the lattice
 // {(a, b): a + b lambda = 0 mod r}); the kernel then needs 129 doublings instead of 255.
 struct GlvDigits {
-    int8_t d1[136];  // signed NAF digits of k1 (sign folded in), LSB first
-    int8_t d2[136];  // signed NAF digits of k2
+    int8_t d1[136];  // joint-sparse-form digits of k1 (sign folded in), LSB first
+    int8_t d2[136];  // ... and of k2
     int16_t top;     // highest index with a non-zero digit in either (-1 if xi == 0)
 };
 
 __device__ __constant__ uint32_t c_beta_mont[8] = {0x9e65eac8u, 0xfbdfd7aau, 0xe50025fbu, 0x0cd4d654u,
                                                    0x3785b99au, 0xd59892a3u, 0x585e8789u, 0x2a27fb62u};
 
-// K4 point part: G[j] <- affine(G[j] + xi * G[j + m]) with xi = k1 + k2 lambda.  One thread per output element; the
-// joint digit loop is uniform across the grid (same xi for every element of a round).  The sum is left in XYZZ
-// coordinates with den[j] = ZZ * ZZZ (1 for infinity); the normalisation shares its inversions across the whole
-// round (batch_invert: 3 multiplications per element instead of a 255-squaring Fermat chain each) and k_fold_finish
-// writes the affine point back (K7).
-__global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_points(const affine_t* __restrict__ G, uint64_t m, GlvDigits dg,
-                                                                          xyzz_t* __restrict__ sums, fq_t* __restrict__ den) {
-    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    affine_t hi = G[j + m];
-    affine_t hip;  // phi(hi) = (beta x, y); infinity (0, 0) maps to itself
-    {
-        fq_t beta;
-#pragma unroll
-        for (int i = 0; i < 8; i++) beta.v[i] = c_beta_mont[i];
-        fp_mul(hip.x, hi.x, beta);
-        hip.y = hi.y;
-    }
-    xyzz_t acc;
-    xyzz_set_inf(acc);
-#pragma unroll 1
-    for (int i = dg.top; i >= 0; i--) {
-        xyzz_dbl(acc, acc);
-        int d1 = dg.d1[i], d2 = dg.d2[i];
-        if (d1 != 0) xyzz_madd(acc, hi, d1 < 0);
-        if (d2 != 0) xyzz_madd(acc, hip, d2 < 0);
-    }
-    affine_t lo = G[j];
-    xyzz_madd(acc, lo, false);
-    sums[j] = acc;
-    fq_t d;
-    if (xyzz_is_inf(acc))
-        fp_one(d);
-    else
-        fp_mul(d, acc.zz, acc.zzz);
-    den[j] = d;
-}
+// K4 point part: G[j] <- affine(G[j] + xi * G[j + m]) with xi = k1 + k2 lambda is the D = 1 case of k_fold_multi below
+// (joint digit loop uniform across the grid: same xi for every element of a round).  The sum is left in XYZZ coordinates
+// with den[j] = ZZ * ZZZ (1 for infinity); the normalisation shares its inversions across the whole round (batch_invert:
+// 3 multiplications per element instead of a 255-squaring Fermat chain each) and k_fold_finish writes the affine point
+// back (K7).
 // x = X / ZZ = X * ZZZ * inv, y = Y / ZZZ = Y * ZZ * inv with inv = 1 / (ZZ * ZZZ)
 __global__ void __launch_bounds__(128) k_fold_finish(const xyzz_t* __restrict__ sums, const fq_t* __restrict__ inv, uint64_t m,
                                                      affine_t* __restrict__ G) {
@@ -107,8 +75,9 @@ __global__ void __launch_bounds__(128) k_fold_finish(const xyzz_t* __restrict__ 
 //     G^(D)_j = sum_{t < 2^D} s_t G_{j + off_t},   s_t = prod_k xi_k^{bit_k(t)},   off_t = sum_k bit_k(t) n / 2^(k+1)
 // (pcdl.rs:216-218 unrolled D times), a 2^D-term multi-scalar multiplication with SHARED scalars: one joint
 // double-and-add (Straus) pays the 129 doublings once per output instead of once per term.  The host decomposes every
-// s_t by GLV, merges the signed NAF digits of all 2 (2^D - 1) half-scalars into one operation list (uniform across the
-// grid, so the loop is divergence free) and uploads it; beta x of every term is staged in global memory once.
+// s_t by GLV (k1, k2), writes each pair in joint sparse form (half of the positions carry an addition instead of two
+// thirds for separate NAFs; the combinations P +- phi(P) are one free point and one precomputed affine point per
+// term), merges all terms into one operation list (uniform across the grid, so the loop is divergence free) and uploads it.
 constexpr int FOLD_MAX_DEFER = 4;
 constexpr int FOLD_MAX_OPS = 3072;
 struct FoldOps {
@@ -117,27 +86,67 @@ struct FoldOps {
 };
 __device__ __constant__ FoldOps c_fold_ops;
 
+__device__ __forceinline__ uint64_t fold_term_offset(uint64_t n, int D, int t) {
+    uint64_t off = 0;
+    for (int k = 0; k < D; k++)
+        if ((t >> k) & 1) off += n >> (k + 1);
+    return off;
+}
+// Per term t >= 1 and output j: beta x (so phi(P) = (beta x, y)) and the denominator x - beta x of P - phi(P); the joint
+// sparse form below adds P, phi(P), P + phi(P) = (-(x + beta x), -y) [= -phi^2(P), free] or P - phi(P) [one affine
+// addition per term, inversions shared by batch_invert].
+__global__ void __launch_bounds__(128) k_fold_prep1(const affine_t* __restrict__ G0, uint64_t n, int D, fq_t* __restrict__ bx,
+                                                    fq_t* __restrict__ den) {
+    const uint64_t m = n >> D;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y + 1;
+    if (j >= m) return;
+    fq_t beta;
+#pragma unroll
+    for (int i = 0; i < 8; i++) beta.v[i] = c_beta_mont[i];
+    const affine_t p = G0[j + fold_term_offset(n, D, t)];
+    fq_t r, d;
+    fp_mul(r, p.x, beta);
+    fp_sub(d, p.x, r);
+    if (fp_is_zero(d)) fp_one(d);  // infinity, or x = 0 (then phi(P) = P and the difference is infinity): no inversion
+    bx[(uint64_t)(t - 1) * m + j] = r;
+    den[(uint64_t)(t - 1) * m + j] = d;
+}
+__global__ void __launch_bounds__(128) k_fold_prep2(const affine_t* __restrict__ G0, uint64_t n, int D, const fq_t* __restrict__ bx,
+                                                    const fq_t* __restrict__ inv, affine_t* __restrict__ diff) {
+    const uint64_t m = n >> D;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y + 1;
+    if (j >= m) return;
+    const affine_t p = G0[j + fold_term_offset(n, D, t)];
+    const fq_t b = bx[(uint64_t)(t - 1) * m + j];
+    affine_t out;
+    fq_t d;
+    fp_sub(d, p.x, b);
+    if (affine_is_inf(p) || fp_is_zero(d)) {
+        affine_set_inf(out);
+    } else {  // (x, y) + (beta x, -y): lambda = (-y - y) / (beta x - x) = 2 y / (x - beta x)
+        fq_t lam, t1;
+        fp_dbl(t1, p.y);
+        fp_mul(lam, t1, inv[(uint64_t)(t - 1) * m + j]);
+        fp_sqr(t1, lam);
+        fp_sub(t1, t1, p.x);
+        fp_sub(out.x, t1, b);
+        fp_sub(t1, p.x, out.x);
+        fp_mul(t1, lam, t1);
+        fp_sub(out.y, t1, p.y);
+    }
+    diff[(uint64_t)(t - 1) * m + j] = out;
+}
+
+// op code: 0xff = double; else (t - 1) | kind << 4 | sign << 7 with kind 0: P_t, 1: phi(P_t), 2: P_t + phi(P_t), 3: P_t - phi(P_t)
 __global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_multi(const affine_t* __restrict__ G0, uint64_t n, int D,
-                                                                         fq_t* __restrict__ bx, xyzz_t* __restrict__ sums,
-                                                                         fq_t* __restrict__ den) {
+                                                                         const fq_t* __restrict__ bx,
+                                                                         const affine_t* __restrict__ diff,
+                                                                         xyzz_t* __restrict__ sums, fq_t* __restrict__ den) {
     const uint64_t m = n >> D;
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
-    const int T = 1 << D;
-    {
-        fq_t beta;
-#pragma unroll
-        for (int i = 0; i < 8; i++) beta.v[i] = c_beta_mont[i];
-#pragma unroll 1
-        for (int t = 1; t < T; t++) {
-            uint64_t off = 0;
-            for (int k = 0; k < D; k++)
-                if ((t >> k) & 1) off += n >> (k + 1);
-            fq_t x = G0[j + off].x, r;
-            fp_mul(r, x, beta);
-            bx[(uint64_t)(t - 1) * m + j] = r;
-        }
-    }
     xyzz_t acc;
     xyzz_set_inf(acc);
     const int n_ops = c_fold_ops.n_ops;
@@ -147,14 +156,27 @@ __global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_multi(const 
         if (code == 0xffu) {
             xyzz_dbl(acc, acc);
         } else {
-            const int stream = code & 0x7f, t = (stream >> 1) + 1;
-            uint64_t off = 0;
-            for (int k = 0; k < D; k++)
-                if ((t >> k) & 1) off += n >> (k + 1);
+            const int t = (int)(code & 0xf) + 1, kind = (code >> 4) & 3;
+            bool neg = (code >> 7) != 0;
+            const uint64_t slot = (uint64_t)(t - 1) * m + j;
             affine_t p;
-            p.y = G0[j + off].y;
-            p.x = (stream & 1) ? bx[(uint64_t)(t - 1) * m + j] : G0[j + off].x;
-            xyzz_madd(acc, p, (code >> 7) != 0);
+            if (kind == 3) {
+                p = diff[slot];
+            } else {
+                p = G0[j + fold_term_offset(n, D, t)];
+                if (kind != 0 && !affine_is_inf(p)) {
+                    const fq_t b = bx[slot];
+                    if (kind == 1) {
+                        p.x = b;
+                    } else {  // P + phi(P) = (-(x + beta x), -y)
+                        fq_t sx;
+                        fp_add(sx, p.x, b);
+                        fp_neg(p.x, sx);
+                        neg = !neg;
+                    }
+                }
+            }
+            xyzz_madd(acc, p, neg);
         }
     }
     affine_t lo = G0[j];
@@ -255,32 +277,10 @@ static const uint64_t A2[3] = {0x0c7c095a00000001ull, 0x93cd3a2c8198e269ull, 0x0
 static const uint64_t G1[5] = {0x4a95a2d972171db4ull, 0x61afdea68480fa55ull, 0x32c49e4bffffffffull, 0x279a745902a2654eull, 0x1ull};
 static const uint64_t G2[5] = {0xc689c5879f98a4deull, 0x61afdea683e7688aull, 0xff2b871c00000003ull, 0x279a745903c12455ull, 0x1ull};
 
-// |k| as NAF digits (LSB first) with overall sign; returns the index of the top non-zero digit or -1
-static int naf(const uint64_t mag[3], bool negative, int8_t* out, int len) {
-    uint64_t k[3] = {mag[0], mag[1], mag[2]};
-    int top = -1;
-    for (int i = 0; i < len; i++) {
-        int d = 0;
-        if (k[0] & 1u) {
-            d = 2 - (int)(k[0] & 3u);
-            if (d < 0) {
-                for (int l = 0; l < 3; l++)
-                    if (++k[l] != 0) break;
-            } else {
-                k[0] -= 1;
-            }
-            top = i;
-        }
-        out[i] = (int8_t)(negative ? -d : d);
-        k[0] = (k[0] >> 1) | (k[1] << 63);
-        k[1] = (k[1] >> 1) | (k[2] << 63);
-        k[2] >>= 1;
-    }
-    return top;
-}
 }  // namespace glv
 
-static void make_glv(const fr_t& xi, GlvDigits& dg) {
+// xi = k1 + k2 lambda: magnitudes (< 2^130, three limbs) and signs
+static void glv_split(const fr_t& xi, uint64_t k1m[3], bool& n1, uint64_t k2m[3], bool& n2) {
     using namespace glv;
     uint32_t kc[8];
     fp_to_canon(kc, xi);
@@ -301,33 +301,68 @@ static void make_glv(const fr_t& xi, GlvDigits& dg) {
     mul(t1, c1, 3, B1N, 2);
     mul(t2, c2, 3, A1, 2);
     sub5(k2, t1, t2);
-    bool n1 = (k1[4] >> 63) != 0, n2 = (k2[4] >> 63) != 0;
+    n1 = (k1[4] >> 63) != 0;
+    n2 = (k2[4] >> 63) != 0;
     if (n1) neg5(k1, k1);
     if (n2) neg5(k2, k2);
+    for (int i = 0; i < 3; i++) {
+        k1m[i] = k1[i];
+        k2m[i] = k2[i];
+    }
+}
+
+// Joint sparse form (Solinas) of (|k1|, |k2|), signs folded in: at most one of any two consecutive positions is
+// non-zero in both rows on average half of the positions carry an addition, against two thirds for two separate NAFs.
+static void make_glv_jsf(const fr_t& xi, GlvDigits& dg) {
+    uint64_t k[2][3];
+    bool neg[2];
+    glv_split(xi, k[0], neg[0], k[1], neg[1]);
     for (int i = 0; i < 136; i++) dg.d1[i] = dg.d2[i] = 0;
-    int top1 = naf(k1, n1, dg.d1, 134);
-    int top2 = naf(k2, n2, dg.d2, 134);
-    dg.top = (int16_t)(top1 > top2 ? top1 : top2);
+    int d[2] = {0, 0}, top = -1;
+    auto nz = [&](int r) { return (k[r][0] | k[r][1] | k[r][2]) != 0 || d[r] != 0; };
+    for (int pos = 0; pos < 136 && (nz(0) || nz(1)); pos++) {
+        int l[2], u[2];
+        for (int r = 0; r < 2; r++) l[r] = (int)((k[r][0] & 7u) + (unsigned)d[r]) & 7;
+        for (int r = 0; r < 2; r++) {
+            if ((l[r] & 1) == 0) {
+                u[r] = 0;
+            } else {
+                u[r] = (l[r] & 3) == 1 ? 1 : -1;
+                if ((l[r] == 3 || l[r] == 5) && (l[1 - r] & 3) == 2) u[r] = -u[r];
+            }
+        }
+        for (int r = 0; r < 2; r++) {
+            if (2 * d[r] == 1 + u[r]) d[r] = 1 - d[r];
+            k[r][0] = (k[r][0] >> 1) | (k[r][1] << 63);
+            k[r][1] = (k[r][1] >> 1) | (k[r][2] << 63);
+            k[r][2] >>= 1;
+        }
+        dg.d1[pos] = (int8_t)(neg[0] ? -u[0] : u[0]);
+        dg.d2[pos] = (int8_t)(neg[1] ? -u[1] : u[1]);
+        if (u[0] || u[1]) top = pos;
+    }
+    dg.top = (int16_t)top;
 }
 
 }  // namespace halo
 
 namespace halo {
 // Materialises G^(D) from the untouched generators after D deferred rounds (see k_fold_multi).
-static void fold_multi(halo_ctx* ctx, halo_ipa* st) {
-    const int D = st->defer, T = 1 << D;
-    const uint64_t n = st->n, m = n >> D;
+// src: the vector being folded (n elements), xis: the D challenges, oldest first.  D = 1 is the ordinary round.
+static void fold_multi(halo_ctx* ctx, const affine_t* src, uint64_t n, const fr_t* xis, int D) {
+    const int T = 1 << D;
+    const uint64_t m = n >> D;
     // s_t = prod_k xi_k^{bit_k(t)}
     std::vector<fr_t> coef(T);
     fp_one(coef[0]);
     for (int t = 1; t < T; t++) {
         int k = 31 - __builtin_clz((unsigned)t);  // highest set bit: s_t = s_{t - 2^k} * xi_k
-        fp_mul(coef[t], coef[t ^ (1 << k)], st->defer_xis[k]);
+        fp_mul(coef[t], coef[t ^ (1 << k)], xis[k]);
     }
     std::vector<GlvDigits> dg(T);
     int top = -1;
     for (int t = 1; t < T; t++) {
-        make_glv(coef[t], dg[t]);
+        make_glv_jsf(coef[t], dg[t]);
         if (dg[t].top > top) top = dg[t].top;
     }
     static FoldOps ops;  // one opening per context at a time; the copy below is staged before the call returns
@@ -335,31 +370,44 @@ static void fold_multi(halo_ctx* ctx, halo_ipa* st) {
     for (int i = top; i >= 0; i--) {
         ops.code[no++] = 0xff;
         for (int t = 1; t < T; t++) {
-            if (dg[t].d1[i]) ops.code[no++] = (uint8_t)((2 * (t - 1)) | (dg[t].d1[i] < 0 ? 0x80 : 0));
-            if (dg[t].d2[i]) ops.code[no++] = (uint8_t)((2 * (t - 1) + 1) | (dg[t].d2[i] < 0 ? 0x80 : 0));
+            const int d1 = dg[t].d1[i], d2 = dg[t].d2[i];
+            if (!d1 && !d2) continue;
+            int kind, neg;
+            if (d1 && !d2) kind = 0, neg = d1 < 0;
+            else if (!d1 && d2) kind = 1, neg = d2 < 0;
+            else if (d1 == d2) kind = 2, neg = d1 < 0;
+            else kind = 3, neg = d1 < 0;  // d1 = -d2: +-(P - phi(P))
+            ops.code[no++] = (uint8_t)((t - 1) | (kind << 4) | (neg ? 0x80 : 0));
         }
     }
     if (no > FOLD_MAX_OPS) throw CudaError{cudaErrorInvalidValue, "fold_multi: operation list too long", __FILE__, __LINE__};
     ops.n_ops = no;
     HALO_CUDA(cudaMemcpyToSymbolAsync(c_fold_ops, &ops, sizeof ops, 0, cudaMemcpyHostToDevice, ctx->stream));
     ctx->ipa_bx.reserve((size_t)(T - 1) * m * sizeof(fq_t));
+    ctx->ipa_diff.reserve((size_t)(T - 1) * m * sizeof(affine_t));
+    ctx->ipa_den2.reserve((size_t)(T - 1) * m * sizeof(fq_t));
     ctx->ipa_sums.reserve(m * sizeof(xyzz_t));
     ctx->ipa_den.reserve(m * sizeof(fq_t));
-    k_fold_multi<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->gens.as<affine_t>(), n, D, ctx->ipa_bx.as<fq_t>(),
+    const affine_t* G0 = src;
+    const dim3 pgrid((unsigned)((m + 127) / 128), (unsigned)(T - 1));
+    k_fold_prep1<<<pgrid, 128, 0, ctx->stream>>>(G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_den2.as<fq_t>());
+    batch_invert(ctx, ctx->stream, ctx->ipa_den2.as<fq_t>(), (uint32_t)((T - 1) * m), ctx->ipa_inv_scratch);
+    k_fold_prep2<<<pgrid, 128, 0, ctx->stream>>>(G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_den2.as<fq_t>(), ctx->ipa_diff.as<affine_t>());
+    k_fold_multi<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_diff.as<affine_t>(),
                                                                        ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>());
     batch_invert(ctx, ctx->stream, ctx->ipa_den.as<fq_t>(), (uint32_t)m, ctx->ipa_inv_scratch);
     k_fold_finish<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>(), m,
                                                                         ctx->ipa_G.as<affine_t>());
-    ctx->kernel_launches += 2;
+    ctx->kernel_launches += 4;
     HALO_CUDA(cudaGetLastError());
 }
 }  // namespace halo
 
-extern "C" int halo_test_glv_decompose(const uint64_t xi[4], int8_t d1[136], int8_t d2[136], int* top) {
+extern "C" int halo_test_glv_decompose_jsf(const uint64_t xi[4], int8_t d1[136], int8_t d2[136], int* top) {
     fr_t x;
     memcpy(&x, xi, 32);
     GlvDigits dg;
-    make_glv(x, dg);
+    make_glv_jsf(x, dg);
     memcpy(d1, dg.d1, 136);
     memcpy(d2, dg.d2, 136);
     *top = dg.top;
@@ -605,16 +653,7 @@ int halo_ipa_round_fold(halo_ipa* st, const uint64_t xi[4], const uint64_t xi_in
     if (st->frozen) {
         k_frozen_fold_s<<<(st->M0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ipa_frozen.as<fr_t>(), st->M0, (uint32_t)st->cur, x);
     } else {
-        GlvDigits dg;
-        make_glv(x, dg);
-        ctx->ipa_sums.reserve(m * sizeof(xyzz_t));
-        ctx->ipa_den.reserve(m * sizeof(fq_t));
-        k_fold_points<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_G.as<affine_t>(), m, dg, ctx->ipa_sums.as<xyzz_t>(),
-                                                                            ctx->ipa_den.as<fq_t>());
-        batch_invert(ctx, ctx->stream, ctx->ipa_den.as<fq_t>(), (uint32_t)m, ctx->ipa_inv_scratch);
-        k_fold_finish<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>(), m,
-                                                                            ctx->ipa_G.as<affine_t>());
-        ctx->kernel_launches++;
+        fold_multi(ctx, ctx->ipa_G.as<affine_t>(), st->cur, &x, 1);  // G_j + xi G_{j+m}, joint-sparse-form digits of xi
     }
     ctx->kernel_launches++;
     HALO_CUDA(cudaGetLastError());
@@ -623,7 +662,7 @@ int halo_ipa_round_fold(halo_ipa* st, const uint64_t xi[4], const uint64_t xi_in
     st->round++;
     st->lr_done = false;
     if (st->deferred && (int)st->round == st->defer && st->cur > 1) {
-        fold_multi(ctx, st);  // G^(defer) in one joint pass; the rounds continue on the folded vector
+        fold_multi(ctx, ctx->gens.as<affine_t>(), st->n, st->defer_xis.data(), st->defer);  // G^(defer) in one joint pass
         st->frozen = st->deferred = false;
     }
     IPA_CATCH

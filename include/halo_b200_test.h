@@ -33,9 +33,9 @@ int halo_test_gather_throughput(halo_ctx *ctx, uint64_t table_bytes, int blocks,
  * one IPA round over 2 x n/2 outputs (pcdl.rs:221-223), 1 = h-expansion to 2^floor(lg n) coefficients (pcdl.rs:56-77),
  * 2 = dot product of two n-vectors (group.rs:13-15), 3 = powers of z (group.rs:29-37). */
 int halo_test_vec_bench(halo_ctx *ctx, int kind, uint64_t n, float *ms);
-/* Host-side GLV decomposition of a challenge used by the generator fold (K4): signed NAF digits of k1, k2 with
- * xi = k1 + k2 * lambda (mod r), LSB first.  Runs without a GPU. */
-int halo_test_glv_decompose(const uint64_t xi[4], int8_t d1[136], int8_t d2[136], int *top);
+/* Host-side GLV decomposition of a challenge used by the generator fold (K4): xi = k1 + k2 * lambda (mod r), written in
+ * joint sparse form (digits in {0, +-1}, LSB first; at most half of the positions non-zero on average).  Runs without a GPU. */
+int halo_test_glv_decompose_jsf(const uint64_t xi[4], int8_t d1[136], int8_t d2[136], int *top);
 #ifdef __cplusplus
 }
 #endif

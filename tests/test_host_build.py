@@ -165,25 +165,32 @@ def test_host_transcript_serialisation_vs_oracle(libs, oracle):
     assert out.tolist() == O.h_eval(xs, z).tolist()
 
 
-def test_glv_decomposition_of_fold_challenge(libs, oracle):
-    """K4 host side: xi = k1 + k2 * lambda (mod r) with |k1|, |k2| < 2^130, digits in signed NAF."""
+def test_glv_joint_sparse_form(libs, oracle):
+    """K4 host side (k_fold_multi's digits): xi = k1 + k2 * lambda (mod r) with |k1|, |k2| < 2^130, written in joint sparse form -- digits in {0, +-1}, the value is preserved,
+    and on average at most half of the positions carry an addition."""
     cuda, _ = libs
     LAMBDA = 0x397E65A7D7C1AD71AEE24B27E308F0A61259527EC1D4752E619D1840AF55F1B1
     BETA = 0x2D33357CB532458ED3552A23A8554E5005270D29D19FC7D27B7FD22F0201B547
     assert pow(LAMBDA, 3, PR.R) == 1 and pow(BETA, 3, PR.P) == 1
-    assert PR.pt_mul(PR.GEN, LAMBDA) == (BETA * PR.GEN[0] % PR.P, PR.GEN[1])  # phi(P) = lambda * P
-    rnd = random.Random(9)
-    vals = [0, 1, 2, PR.R - 1, PR.R - 2, LAMBDA, PR.R // 2, 1 << 254, (1 << 128) - 1, 1 << 128] + [rnd.randrange(PR.R) for _ in range(400)]
+    assert PR.pt_mul(PR.GEN, LAMBDA) == (BETA * PR.GEN[0] % PR.P, PR.GEN[1])  # phi(P) = (beta x, y) = lambda * P
+    rnd = random.Random(10)
+    vals = [0, 1, 2, 3, 5, PR.R - 1, PR.R - 2, LAMBDA, PR.R // 2, 1 << 254, (1 << 128) - 1, 1 << 128] + [rnd.randrange(PR.R) for _ in range(400)]
+    busy = total = 0
     for k in vals:
         xi = oracle.to_mont([k])[0]
         d1 = (C.c_int8 * 136)()
         d2 = (C.c_int8 * 136)()
         top = C.c_int()
-        assert cuda.halo_test_glv_decompose(oracle._p(xi), d1, d2, C.byref(top)) == 0
+        assert cuda.halo_test_glv_decompose_jsf(oracle._p(xi), d1, d2, C.byref(top)) == 0
         k1 = sum(int(d) << i for i, d in enumerate(d1))
         k2 = sum(int(d) << i for i, d in enumerate(d2))
         assert (k1 + k2 * LAMBDA - k) % PR.R == 0
-        assert abs(k1) < 1 << 130 and abs(k2) < 1 << 130 and top.value <= 131
-        for d in (d1, d2):  # non-adjacent form
-            assert all(not (d[i] and d[i + 1]) for i in range(135)) and all(-1 <= x <= 1 for x in d)
+        assert abs(k1) < 1 << 131 and abs(k2) < 1 << 131
+        assert all(-1 <= x <= 1 for x in d1) and all(-1 <= x <= 1 for x in d2) and top.value <= 132
         assert all(d1[i] == 0 and d2[i] == 0 for i in range(top.value + 1, 136))
+        # JSF property: of any three consecutive positions at least one is zero in both rows
+        assert all(any(d1[i + j] == 0 and d2[i + j] == 0 for j in range(3)) for i in range(133))
+        if k > (1 << 200):
+            busy += sum(1 for i in range(top.value + 1) if d1[i] or d2[i])
+            total += top.value + 1
+    assert busy / total < 0.55
