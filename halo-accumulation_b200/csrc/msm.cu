@@ -598,9 +598,9 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
     if (ctx->tune_pair_passes >= 0)
         P = ctx->tune_pair_passes;
     else if (total_entries_max >= ((uint64_t)1 << 25) && total_entries_max >= (uint64_t)NB * 64)
-        P = 4;  // measured (profiles/r01_pair_tree_sweep.jsonl): 2^24 FIXED 36.6 -> 32.9 ms, 2^22 11.2 -> 9.5 ms
+        P = 4;  // measured (profiles/r01_pair_tree_sweep.jsonl): 2^24 FIXED 36.6 -> 29.3 ms, 2^22 11.2 -> 8.6 ms
     else if (total_entries_max >= ((uint64_t)1 << 23) && total_entries_max >= (uint64_t)NB * 32)
-        P = 2;  // 2^20 FIXED: 3.07 -> 2.85 ms
+        P = 2;  // 2^20 FIXED: 3.07 -> 2.69 ms
     if (P > 8) P = 8;
     const uint32_t rmask = (1u << P) - 1u;
     uint64_t slots_max = total_entries_max + (uint64_t)rmask * NB;
