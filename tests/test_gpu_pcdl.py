@@ -297,6 +297,13 @@ def test_open_and_full_check_2_20(ctx, oracle):
             pcdl.check(ctx, Cm, d, z, v, bad)
         # (the flipped limb may take the point off the curve; both sides only need to reject at the same check)
         assert e.value.code == O.pcdl_check(Cm, d, z, v, O.EvalProof.from_buffer_copy(bytes(bad)), threads=16)
+        # hiding variant (deferred head rounds over the FIXED-base tables, blinding polynomial, w'): accepted by both
+        w, wb = O.random_scalars(2, 5)
+        q = O.random_scalars(p.shape[0] - 1, 6)
+        Cw = pcdl.commit(ctx, p, d, w)
+        piw = pcdl.open(ctx, p, Cw, d, z, w, q, wb)
+        pcdl.check(ctx, Cw, d, z, v, piw)
+        assert O.pcdl_check(Cw, d, z, v, O.EvalProof.from_buffer_copy(bytes(piw)), threads=16) == 0
     finally:
         ctx.derive_generators(1 << 16)
 
