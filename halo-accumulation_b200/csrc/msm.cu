@@ -16,6 +16,8 @@
 // Integer pipe bound (IMAD); see DESIGN.md for the roofline accounting.
 #include <functional>
 
+#include <thread>
+
 #include "common.cuh"
 #include "msm.cuh"
 
@@ -804,11 +806,20 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, cons
         ctx->last.reduce_ms = t[4];
         HALO_CUDA(cudaEventElapsedTime(&ctx->last.total_ms, ctx->ev[0], ctx->ev[5]));
     }
-    for (int k = 0; k < count; k++) {
+    // the Horner combination of a variable-base MSM is ~255 host doublings (~0.1 ms): the two results of an IPA round
+    // (L and R) are finished on two host threads
+    auto finish = [&](int k) {
         if (ins[k].n + ins[k].n_tail == 0)
             xyzz_set_inf(outs[k]);
         else
             msm_finish_host(h_parts + k * SLOT, plans[k], outs[k]);
+    };
+    if (count == 2 && ins[0].n + ins[0].n_tail > 0 && ins[1].n + ins[1].n_tail > 0 && !plans[0].fixed && !plans[1].fixed) {
+        std::thread other(finish, 1);
+        finish(0);
+        other.join();
+    } else {
+        for (int k = 0; k < count; k++) finish(k);
     }
 }
 
