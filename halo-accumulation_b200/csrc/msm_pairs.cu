@@ -224,8 +224,10 @@ __global__ void __launch_bounds__(128) k_prod_down(fq_t* __restrict__ vals, uint
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------------------
+// 7 CTAs per SM (72 registers, 24 bytes of spill): measured best of 4 (92 registers) .. 8 (64 registers): MSM 2^24
+// 36.16 / 35.71 (6) / 35.52 (7) / 36.41 ms (8)
 template <bool PASS0>
-__global__ void __launch_bounds__(128, 4) k_pair_bwd(const uint32_t* __restrict__ entries, const affine_t* __restrict__ bases,
+__global__ void __launch_bounds__(128, 7) k_pair_bwd(const uint32_t* __restrict__ entries, const affine_t* __restrict__ bases,
                                                      uint32_t n, const affine_t* __restrict__ tail_bases,
                                                      const affine_t* __restrict__ in, const uint32_t* __restrict__ total_slots,
                                                      int pass, const fq_t* __restrict__ prefix, const fq_t* __restrict__ tot_inv,
