@@ -309,6 +309,12 @@ def test_msm_2_22_fixed_and_variable_vs_oracle(halo, oracle):
         assert O.pt_to_affine(c.msm_gens(sc))[0].tobytes() == exp.tobytes()
         t = c.msm_gens_submit(sc)
         assert O.pt_to_affine(c.msm_gens_collect(t))[0].tobytes() == exp.tobytes()
+        # ragged slice at an offset: the automatic pair-tree passes on partially filled tiles and padded segments
+        m, off = n - 77777, 12345
+        exp2, _ = O.pt_to_affine(O.msm_affine(gs[off:off + m], sc[:m], threads=16))
+        assert O.pt_to_affine(c.msm_gens(sc[:m], off=off))[0].tobytes() == exp2.tobytes()
+        c.set_fixed_base(False)
+        assert O.pt_to_affine(c.msm_gens(sc[:m], off=off))[0].tobytes() == exp2.tobytes()
     finally:
         c.close()
 
