@@ -16,6 +16,7 @@
 // Integer pipe bound (IMAD); see DESIGN.md for the roofline accounting.
 #include <functional>
 
+#include <system_error>
 #include <thread>
 
 #include "common.cuh"
@@ -815,9 +816,18 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, cons
             msm_finish_host(h_parts + k * SLOT, plans[k], outs[k]);
     };
     if (count == 2 && ins[0].n + ins[0].n_tail > 0 && ins[1].n + ins[1].n_tail > 0 && !plans[0].fixed && !plans[1].fixed) {
-        std::thread other(finish, 1);
+        bool spawned = false;
+        std::thread other;
+        try {
+            other = std::thread(finish, 1);
+            spawned = true;
+        } catch (const std::system_error&) {  // no thread available: finish both here (nothing may unwind across the ABI)
+        }
         finish(0);
-        other.join();
+        if (spawned)
+            other.join();
+        else
+            finish(1);
     } else {
         for (int k = 0; k < count; k++) finish(k);
     }
