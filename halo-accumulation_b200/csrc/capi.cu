@@ -62,6 +62,9 @@ static void async_init(halo_ctx* ctx) {
     catch (const std::bad_alloc&) {                                                                            \
         return halo::set_error(ctx, HALO_ENOMEM, "out of host memory%s%s%d", "", "", 0);                        \
     }                                                                                                          \
+    catch (...) { /* nothing unwinds across the C ABI */                                                       \
+        return halo::set_error(ctx, HALO_ECUDA, "unexpected internal exception%s%s%d", "", "", 0);              \
+    }                                                                                                          \
     return HALO_OK;
 
 static int fail(halo_ctx* ctx, int code, const char* msg) {

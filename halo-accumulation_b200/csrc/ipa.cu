@@ -424,6 +424,10 @@ extern "C" int halo_test_glv_decompose_jsf(const uint64_t xi[4], int8_t d1[136],
         ctx->last_error = std::string("CUDA error: ") + cudaGetErrorString(e.err) + " (" + e.what + ")"; \
         return HALO_ECUDA;                                  \
     }                                                       \
+    catch (...) { /* nothing unwinds across the C ABI */    \
+        ctx->last_error = "unexpected internal exception";  \
+        return HALO_ECUDA;                                  \
+    }                                                       \
     return HALO_OK;
 
 static inline bool is_pow2(uint64_t n) { return n && !(n & (n - 1)); }
