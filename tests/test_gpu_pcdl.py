@@ -196,6 +196,28 @@ def test_pcdl_argument_errors(env):
         pcdl.commit(ctx, p, 3)            # degree exceeds d (pcdl.rs:103)
     with pytest.raises(H.HaloError):
         pcdl.commit(ctx, p, (1 << 17) - 1)  # d > D (pcdl.rs:104)
+    # halo_h_msm_with (pcdl::check in one call): equals halo_h_msm + halo_msm on the same inputs; argument errors
+    from halo_accumulation_b200._capi import p64
+
+    lib = ctx._lib
+    lg = 10
+    xis = O.random_scalars(lg + 1, 2)
+    k = 22
+    bases = ctx.get_generators(7, k).copy()
+    inf = np.zeros(k, dtype=np.uint8)
+    inf[3] = 1
+    sc = O.random_scalars(k, 3)
+    out_h, out_s, ref_h = (np.zeros(12, dtype=np.uint64) for _ in range(3))
+    assert lib.halo_h_msm_with(ctx._h, p64(xis), lg, p64(bases), inf.ctypes.data_as(C.POINTER(C.c_uint8)), p64(sc), C.c_uint64(k),
+                               p64(out_h), p64(out_s)) == 0
+    assert lib.halo_h_msm(ctx._h, p64(xis), lg, p64(ref_h)) == 0
+    assert O.pt_eq(out_h, ref_h) and O.pt_eq(out_s, ctx.msm(bases, sc, inf))
+    assert O.pt_eq(out_h, O.msm_affine(ctx.get_generators(0, 1 << lg), O.h_get_poly(xis), threads=8))
+    assert lib.halo_h_msm_with(ctx._h, p64(xis), lg, p64(bases), None, p64(sc), C.c_uint64(0), p64(out_h), p64(out_s)) == 0
+    assert O.pt_eq(out_h, ref_h) and O.pt_to_affine(out_s)[1]          # empty companion: infinity
+    assert lib.halo_h_msm_with(ctx._h, p64(xis), lg, None, None, p64(sc), C.c_uint64(k), p64(out_h), p64(out_s)) < 0
+    assert lib.halo_h_msm_with(ctx._h, p64(xis), 40, p64(bases), None, p64(sc), C.c_uint64(k), p64(out_h), p64(out_s)) < 0
+    assert lib.halo_h_msm_with(ctx._h, p64(xis), lg, p64(bases), None, p64(sc), C.c_uint64(5000), p64(out_h), p64(out_s)) < 0
 
 
 def _random_instance(env, d, seed):
