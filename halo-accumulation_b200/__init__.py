@@ -34,6 +34,14 @@ def points_equal(a, b):
     return bool(load().halo_points_equal(p64(a), p64(b)))
 
 
+def check_canaries():
+    """(overwritten, live): how many live device buffers had the 256-byte canary behind their end overwritten (test hook;
+    compute-sanitizer is not available on this pool)."""
+    live = C.c_int()
+    bad = load().halo_test_check_canaries(C.byref(live))
+    return int(bad), live.value
+
+
 class Context:
     """One CUDA device + resident public parameters (replaces consts.rs:23-68)."""
 

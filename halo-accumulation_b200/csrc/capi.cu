@@ -12,6 +12,12 @@ using namespace halo;
 
 namespace halo {
 
+// Registry behind DevBuf's canaries (one process-wide list; contexts are single-threaded like the reference).
+std::vector<DevBuf*>& devbuf_registry() {
+    static std::vector<DevBuf*> r;
+    return r;
+}
+
 __global__ void __launch_bounds__(256) k_mark_infinity(affine_t* __restrict__ bases, const uint8_t* __restrict__ inf, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && inf[i]) affine_set_inf(bases[i]);

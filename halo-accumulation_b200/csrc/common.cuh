@@ -34,22 +34,48 @@ struct CudaError {
         if (_e != cudaSuccess) throw halo::CudaError{_e, #expr, __FILE__, __LINE__}; \
     } while (0)
 
-// Device buffer that only grows; owned by a context, never handed across the ABI.
+// Device buffer that only grows; owned by a context, never handed across the ABI.  Every allocation carries a 256-byte
+// canary behind its end (compute-sanitizer is not available on this pool): halo_test_check_canaries() verifies that no
+// kernel wrote past any live buffer.
+struct DevBuf;
+std::vector<DevBuf*>& devbuf_registry();
 struct DevBuf {
+    static constexpr size_t CANARY = 256;
     void* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
     void reserve(size_t bytes) {
         if (bytes <= cap) return;
-        if (p) HALO_CUDA(cudaFree(p));
-        p = nullptr;
-        cap = 0;
-        HALO_CUDA(cudaMalloc(&p, bytes));
+        release();
+        HALO_CUDA(cudaMalloc(&p, bytes + CANARY));
         cap = bytes;
+        HALO_CUDA(cudaMemset(static_cast<char*>(p) + cap, 0xA5, CANARY));
+        devbuf_registry().push_back(this);
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            cudaFree(p);
+            auto& r = devbuf_registry();
+            for (size_t i = 0; i < r.size(); i++)
+                if (r[i] == this) {
+                    r[i] = r.back();
+                    r.pop_back();
+                    break;
+                }
+        }
         p = nullptr;
         cap = 0;
+    }
+    bool canary_ok() const {
+        if (!p) return true;
+        unsigned char h[CANARY];
+        if (cudaMemcpy(h, static_cast<const char*>(p) + cap, CANARY, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        for (size_t i = 0; i < CANARY; i++)
+            if (h[i] != 0xA5) return false;
+        return true;
     }
     template <class T>
     T* as() const {

@@ -319,6 +319,16 @@ int halo_test_fp_mul_throughput(halo_ctx* ctx, int blocks, int threads, int iter
     T_CATCH(ctx)
 }
 
+int halo_test_check_canaries(int* live_buffers) {
+    cudaDeviceSynchronize();
+    int bad = 0;
+    const auto& r = halo::devbuf_registry();
+    for (const halo::DevBuf* b : r)
+        if (!b->canary_ok()) bad++;
+    if (live_buffers) *live_buffers = (int)r.size();
+    return bad;
+}
+
 int halo_test_gather_throughput(halo_ctx* ctx, uint64_t table_bytes, int blocks, int threads, int iters, int bytes, float* ms) {
     if (!ctx || !ms || table_bytes < 4096 || threads > 256) return HALO_EINVAL;
     T_TRY(ctx)

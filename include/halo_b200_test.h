@@ -24,6 +24,9 @@ int halo_test_fp_mul_throughput(halo_ctx *ctx, int blocks, int threads, int iter
  * accumulator (nothing is loop invariant).  kind 0 = mad.lo.u32 (IMAD), 1 = mad.wide.u32 (IMAD.WIDE), 2 = mad.hi.u32
  * (IMAD.HI): ops = blocks * threads * iters * 16.  kinds 3-7: carry-chain forms, 8 (7: 16) ops per iteration. */
 int halo_test_imad_throughput(halo_ctx *ctx, int kind, int blocks, int threads, int iters, float *ms, uint64_t *checksum);
+/* Every device buffer of the library is allocated with a 256-byte canary behind its end.  Returns the number of live
+ * buffers whose canary was overwritten (0 = no kernel wrote past a buffer); *live_buffers = how many were checked. */
+int halo_test_check_canaries(int *live_buffers);
 /* Random-gather ceiling of HBM: blocks * threads threads each read `iters` pseudo-random 64-byte-aligned slots (16, 32 or
  * 64 bytes of each; bytes = -64: four adjacent lanes fetch one 64-byte slot with one instruction, blocks * threads / 4 *
  * iters gathers) of a table of `table_bytes` bytes; ms = best of 2 timed launches.  The denominator for the first

@@ -56,4 +56,6 @@ def ctx(halo):
     c = halo.Context(0, 1 << 20)
     c.derive_generators(1 << 16)
     yield c
+    bad, live = halo.check_canaries()  # no kernel of the whole session wrote past the end of a device buffer
     c.close()
+    assert bad == 0 and live > 10, (bad, live)

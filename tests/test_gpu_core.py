@@ -315,6 +315,8 @@ def test_msm_2_22_fixed_and_variable_vs_oracle(halo, oracle):
         assert O.pt_to_affine(c.msm_gens(sc[:m], off=off))[0].tobytes() == exp2.tobytes()
         c.set_fixed_base(False)
         assert O.pt_to_affine(c.msm_gens(sc[:m], off=off))[0].tobytes() == exp2.tobytes()
+        bad, live = halo.check_canaries()
+        assert bad == 0 and live > 10, (bad, live)
     finally:
         c.close()
 
