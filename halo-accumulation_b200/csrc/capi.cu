@@ -160,6 +160,7 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     if (!strcmp(key, "acc_static")) ctx->tune_acc_static = value;
     else if (!strcmp(key, "acc_blocks_per_sm")) ctx->tune_acc_blocks_per_sm = value;
     else if (!strcmp(key, "pair_passes")) ctx->tune_pair_passes = value;
+    else if (!strcmp(key, "split_blocking")) ctx->tune_split_blocking = value;
     else if (!strcmp(key, "ipa_defer_rounds")) ctx->tune_ipa_defer = value;
     else if (!strcmp(key, "ipa_two_lanes")) ctx->tune_ipa_two_lanes = value;
     else if (!strcmp(key, "ipa_freeze_len")) ctx->tune_ipa_freeze_len = value;
@@ -337,6 +338,28 @@ int halo_msm_gens_resident(halo_ctx* ctx, const void* d_scalars, uint64_t off, u
 int halo_msm_gens(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]) {
     if (!ctx || !out_jac || (!scalars && n)) return HALO_EINVAL;
     if (off + n > ctx->n_gens) return fail(ctx, HALO_ESTATE, "halo_msm_gens: range exceeds resident generators");
+    // Large calls are split into two point slices that go through the two pipeline slots: the host-to-device copy of the
+    // second slice overlaps the kernels of the first (2^24 scalars: 45.4 -> ~42 ms from pinned memory); the two partial
+    // sums are added on the host.
+    if (ctx->tune_split_blocking > 0 && n >= ((uint64_t)1 << ctx->tune_split_blocking) && !ctx->slots[0].active && !ctx->slots[1].active) {
+        const uint64_t h = n / 2;
+        int t0, t1;
+        uint64_t p0[12], p1[12];
+        int rc = halo_msm_gens_submit(ctx, scalars, off, h, &t0);
+        if (rc) return rc;
+        rc = halo_msm_gens_submit(ctx, scalars + 4 * h, off + h, n - h, &t1);
+        if (rc) {
+            halo_msm_gens_collect(ctx, t0, p0);
+            return rc;
+        }
+        rc = halo_msm_gens_collect(ctx, t0, p0);
+        int rc1 = halo_msm_gens_collect(ctx, t1, p1);
+        if (rc || rc1) return rc ? rc : rc1;
+        uint64_t both[24];
+        memcpy(both, p0, 96);
+        memcpy(both + 12, p1, 96);
+        return halo_points_sum(both, 2, out_jac);
+    }
     HALO_TRY(ctx)
     ctx->stage_scalars.reserve((n ? n : 1) * sizeof(fr_t));
     if (n) HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));

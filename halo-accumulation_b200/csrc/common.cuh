@@ -165,6 +165,7 @@ struct halo_ctx {
     int tune_ipa_two_lanes = 1, tune_ipa_freeze_len = 0;
     int tune_ipa_frozen_c = 10;  // window of the frozen-tail MSMs (8192 points, latency bound in the bucket reduction): 0.78 -> 0.71 ms per round vs c = 12
     int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
+    int tune_split_blocking = 23;  // halo_msm_gens: two half-size MSMs through the pipeline slots for n >= 2^this (0: never)
     int tune_pair_passes = -1;  // -1: automatic; 0: XYZZ accumulation only; P > 0: force P pair-tree passes
     uint64_t kernel_launches = 0;
     halo::Timings last;

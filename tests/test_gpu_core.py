@@ -282,6 +282,14 @@ def test_msm_pipelined_submit_collect(ctx, oracle):
         t = nxt
     for g, e in zip(got, exp):
         assert O.pt_eq(g, e)
+    # the blocking call splits large inputs over the two pipeline slots (copy of the second half overlaps the kernels of
+    # the first); forced here at a small size, odd length
+    ctx.set_tuning("split_blocking", 10)
+    try:
+        assert O.pt_eq(ctx.msm_gens(scs[0]), exp[0])
+        assert O.pt_eq(ctx.msm_gens(scs[1][:n - 3], off=3), O.msm_affine(gs[3:n], scs[1][:n - 3], threads=8))
+    finally:
+        ctx.set_tuning("split_blocking", 23)
     # a third submit without collecting is refused, not queued silently
     import halo_accumulation_b200 as H
     t0, t1 = ctx.msm_gens_submit(scs[0]), ctx.msm_gens_submit(scs[1])
