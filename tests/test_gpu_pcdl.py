@@ -419,3 +419,26 @@ def test_kat_file_reproduced_on_the_gpu(env):
     assert mk.pt_hex(np.array(a.C_bar)) == ka["C_bar"] and mk.fr_hex(np.array(a.z)) == ka["z"] and mk.fr_hex(np.array(a.v)) == ka["v"]
     assert mk.proof_dict(a.pi) == ka["pi"]
     assert mk.pt_hex(np.array(a.U0)) == ka["pi_V.U0"] and mk.fr_hex(np.array(a.w)) == ka["pi_V.w"]
+
+
+@pytest.mark.parametrize("passes", [2, 4])
+def test_open_with_pair_tree_in_the_round_msms(env, passes):
+    """The L / R MSMs of large openings take pair-tree passes (automatic from 2^23 entries) with the H' term riding as
+    a one-element tail: forced here at n = 2^12 and compared with the oracle's opening, with and without deferral."""
+    ctx, O, pcdl = env["ctx"], env["O"], env["pcdl"]
+    n = 1 << 12
+    d = n - 1
+    p = O.random_scalars(n - 5, 77)
+    z = O.random_scalars(1, 78)[0]
+    w, wb = O.random_scalars(2, 79)
+    q = O.random_scalars(n - 6, 80)
+    ref = O.pcdl_open(p, O.pcdl_commit(p, d, w, threads=8), d, z, w, q, wb, threads=8)
+    ctx.set_tuning("pair_passes", passes)
+    try:
+        for defer in (0, 2):
+            ctx.set_tuning("ipa_defer_rounds", defer)
+            Cw = pcdl.commit(ctx, p, d, w)
+            _same_proof(O, pcdl.open(ctx, p, Cw, d, z, w, q, wb), ref)
+    finally:
+        ctx.set_tuning("pair_passes", -1)
+        ctx.set_tuning("ipa_defer_rounds", -1)
