@@ -326,6 +326,17 @@ def test_open_and_full_check_2_20(ctx, oracle):
         piw = pcdl.open(ctx, p, Cw, d, z, w, q, wb)
         pcdl.check(ctx, Cw, d, z, v, piw)
         assert O.pcdl_check(Cw, d, z, v, O.EvalProof.from_buffer_copy(bytes(piw)), threads=16) == 0
+        # without the FIXED-base tables: no deferral, variable-base round MSMs (pair-tree passes with the H' tail at this
+        # size); same proof, since every L, R, U is the same group element
+        ctx.set_fixed_base(False)
+        try:
+            piv = pcdl.open(ctx, p, Cm, d, z)
+            for i in range(pi.lg_n):
+                assert O.pt_eq(np.array(piv.Ls[i]), np.array(pi.Ls[i])) and O.pt_eq(np.array(piv.Rs[i]), np.array(pi.Rs[i])), i
+            assert O.pt_eq(np.array(piv.U), np.array(pi.U)) and list(piv.c) == list(pi.c)
+            pcdl.check(ctx, Cm, d, z, v, piv)
+        finally:
+            ctx.set_fixed_base(True)
     finally:
         ctx.derive_generators(1 << 16)
 
