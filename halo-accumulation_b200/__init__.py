@@ -126,6 +126,12 @@ class Context:
         self._chk(self._lib.halo_msm_gens_submit(self._h, p64(s), C.c_uint64(off), C.c_uint64(s.shape[0]), C.byref(t)))
         return t.value, s
 
+    def msm_gens_submit_resident(self, d_ptr, n, off=0):
+        """Pipelined MSM over device-resident scalars (CUDA pointer); returns a ticket for msm_gens_collect."""
+        t = C.c_int()
+        self._chk(self._lib.halo_msm_gens_submit_resident(self._h, C.c_void_p(d_ptr), C.c_uint64(off), C.c_uint64(n), C.byref(t)))
+        return t.value, None
+
     def msm_gens_collect(self, ticket):
         out = np.zeros(12, dtype=np.uint64)
         self._chk(self._lib.halo_msm_gens_collect(self._h, int(ticket[0]), p64(out)))

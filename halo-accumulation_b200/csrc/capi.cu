@@ -49,7 +49,11 @@ namespace halo {
 static void async_init(halo_ctx* ctx) {
     if (ctx->copy_stream) return;
     HALO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    HALO_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    HALO_CUDA(cudaStreamCreateWithPriority(&ctx->sort_stream, cudaStreamNonBlocking, prio_hi));
     for (auto& s : ctx->slots) {
+        HALO_CUDA(cudaEventCreateWithFlags(&s.sorted, cudaEventDisableTiming));
         HALO_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
         HALO_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         HALO_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_parts), 3 * MSM_MAX_WINDOWS * sizeof(xyzz_t)));
@@ -138,11 +142,14 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& s : ctx->slots) {
         s.scalars.release();
+        for (DevBuf* b : {&s.sort_ws.counts, &s.sort_ws.offsets, &s.sort_ws.entries, &s.sort_ws.scan_tmp}) b->release();
+        if (s.sorted) cudaEventDestroy(s.sorted);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
         if (s.h_parts) cudaFreeHost(s.h_parts);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->sort_stream) cudaStreamDestroy(ctx->sort_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -161,6 +168,7 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "acc_blocks_per_sm")) ctx->tune_acc_blocks_per_sm = value;
     else if (!strcmp(key, "pair_passes")) ctx->tune_pair_passes = value;
     else if (!strcmp(key, "split_blocking")) ctx->tune_split_blocking = value;
+    else if (!strcmp(key, "sort_ahead")) ctx->tune_sort_ahead = value;
     else if (!strcmp(key, "ipa_defer_rounds")) ctx->tune_ipa_defer = value;
     else if (!strcmp(key, "ipa_two_lanes")) ctx->tune_ipa_two_lanes = value;
     else if (!strcmp(key, "ipa_freeze_len")) ctx->tune_ipa_freeze_len = value;
@@ -369,7 +377,9 @@ int halo_msm_gens(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t
     HALO_CATCH(ctx)
 }
 
-int halo_msm_gens_submit(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t n, int* ticket) {
+// Shared body of the two submit entry points: host scalars are copied on the copy stream first; device-resident
+// scalars (resident = true) are used in place and must stay untouched until the ticket is collected.
+static int submit_impl(halo_ctx* ctx, const uint64_t* scalars, bool resident, uint64_t off, uint64_t n, int* ticket) {
     if (!ctx || !ticket || (!scalars && n)) return HALO_EINVAL;
     if (off + n > ctx->n_gens) return fail(ctx, HALO_ESTATE, "halo_msm_gens_submit: range exceeds resident generators");
     HALO_TRY(ctx)
@@ -379,12 +389,21 @@ int halo_msm_gens_submit(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, u
     if (s.active) return fail(ctx, HALO_ESTATE, "halo_msm_gens_submit: both pipeline slots are in flight; collect one first");
     s.empty = n == 0;
     if (!s.empty) {
-        s.scalars.reserve(n * sizeof(fr_t));
-        HALO_CUDA(cudaMemcpyAsync(s.scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->copy_stream));
-        HALO_CUDA(cudaEventRecord(s.copied, ctx->copy_stream));
-        HALO_CUDA(cudaStreamWaitEvent(ctx->stream, s.copied, 0));
+        const bool ahead_on = ctx->tune_sort_ahead > 0 && n >= ((uint64_t)1 << 22);
+        // (delaying the sort until the HBM-bound pass-0 gathers of the MSM in front are over measured slower: the
+        // throttled sort then no longer fits under what is left of that MSM)
         MsmInput in;
-        in.scalars = s.scalars.as<fr_t>();
+        if (resident) {
+            in.scalars = reinterpret_cast<const fr_t*>(scalars);
+            // the caller's producer of the scalars ran on a stream we do not know: like halo_msm_gens_resident, the
+            // contract is that they are complete when this call is made
+        } else {
+            s.scalars.reserve(n * sizeof(fr_t));
+            HALO_CUDA(cudaMemcpyAsync(s.scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+            HALO_CUDA(cudaEventRecord(s.copied, ctx->copy_stream));
+            HALO_CUDA(cudaStreamWaitEvent(ahead_on ? ctx->sort_stream : ctx->stream, s.copied, 0));
+            in.scalars = s.scalars.as<fr_t>();
+        }
         in.n = (uint32_t)n;
         const bool fixed = ctx->use_fixed && ctx->pre_n == ctx->n_gens && ctx->gens_pre.p && n >= (1u << 17) && n * 8 >= ctx->pre_n;
         if (fixed) {
@@ -398,7 +417,10 @@ int halo_msm_gens_submit(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, u
         }
         ctx->ws.wsums.reserve((size_t)6 * 3 * MSM_MAX_WINDOWS * sizeof(xyzz_t));
         xyzz_t* d_parts = ctx->ws.wsums.as<xyzz_t>() + (size_t)(4 + si) * 3 * MSM_MAX_WINDOWS;  // slots 0-3 belong to msm_batch
-        msm_enqueue(ctx, in, s.plan, d_parts);
+        // the sort buffers of this slot were last read by the accumulation of the MSM two submits ago, which the caller
+        // has collected (slot free) -- so the sort may start as soon as the scalars have arrived
+        SortAhead ahead{&s.sort_ws, ctx->sort_stream, s.sorted, ctx->tune_sort_ahead};
+        msm_enqueue(ctx, in, s.plan, d_parts, 0, ahead_on ? &ahead : nullptr);
         const int nwin = s.plan.fixed ? 1 : s.plan.W;
         HALO_CUDA(cudaMemcpyAsync(s.h_parts, d_parts, (size_t)3 * nwin * sizeof(xyzz_t), cudaMemcpyDeviceToHost, ctx->stream));
         HALO_CUDA(cudaEventRecord(s.done, ctx->stream));
@@ -407,6 +429,14 @@ int halo_msm_gens_submit(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, u
     *ticket = si;
     ctx->next_slot = si ^ 1;
     HALO_CATCH(ctx)
+}
+
+int halo_msm_gens_submit(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t n, int* ticket) {
+    return submit_impl(ctx, scalars, false, off, n, ticket);
+}
+
+int halo_msm_gens_submit_resident(halo_ctx* ctx, const void* d_scalars, uint64_t off, uint64_t n, int* ticket) {
+    return submit_impl(ctx, reinterpret_cast<const uint64_t*>(d_scalars), true, off, n, ticket);
 }
 
 int halo_msm_gens_collect(halo_ctx* ctx, int ticket, uint64_t out_jac[12]) {

@@ -149,13 +149,14 @@ struct halo_ctx {
     // of call k+1 overlaps the kernels of call k
     struct AsyncSlot {
         halo::DevBuf scalars;
-        cudaEvent_t copied = nullptr, done = nullptr;
+        halo::MsmWorkspace sort_ws;  // counts / offsets / entries of this slot's counting sort (SortAhead)
+        cudaEvent_t copied = nullptr, done = nullptr, sorted = nullptr;
         halo::xyzz_t* h_parts = nullptr;  // pinned
         halo::MsmPlan plan;
         bool active = false;
         bool empty = false;
     } slots[2];
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, sort_stream = nullptr;  // sort_stream: highest priority
     int next_slot = 0;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
@@ -165,6 +166,7 @@ struct halo_ctx {
     int tune_ipa_two_lanes = 1, tune_ipa_freeze_len = 0;
     int tune_ipa_frozen_c = 10;  // window of the frozen-tail MSMs (8192 points, latency bound in the bucket reduction): 0.78 -> 0.71 ms per round vs c = 12
     int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
+    int tune_sort_ahead = 1;  // pipelined submit: CTAs per SM of the counting sort running beside the previous MSM (0: off)
     int tune_split_blocking = 23;  // halo_msm_gens: two half-size MSMs through the pipeline slots for n >= 2^this (0: never)
     int tune_pair_passes = -1;  // -1: automatic; 0: XYZZ accumulation only; P > 0: force P pair-tree passes
     uint64_t kernel_launches = 0;

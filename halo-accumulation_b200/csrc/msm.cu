@@ -85,8 +85,9 @@ __global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars
                                                 const fr_t* __restrict__ tail_scalars, uint32_t n_tail, const MsmWidths widths,
                                                 int W, uint32_t M, uint32_t fixed_stride, uint32_t fixed_first,
                                                 uint32_t* __restrict__ counts, uint32_t* __restrict__ entries) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n + n_tail) return;
+    // grid-stride: the launch normally covers every scalar with one thread; the pipelined path (SortAhead) runs the sort
+    // of the NEXT MSM with a few CTAs per SM beside the accumulation kernels of the current one
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n + n_tail; i += gridDim.x * blockDim.x) {
     fr_t s = i < n ? scalars[i] : tail_scalars[i - n];
     uint32_t k[8];
     fp_to_canon(k, s);  // arkworks `into_bigint`
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256) k_digits(const fr_t* __restrict__ scalars
                 entries[pos] = idx | (neg << 31);
             }
         }
+    }
     }
 }
 
@@ -585,13 +587,18 @@ void msm_precompute_tables(halo_ctx* ctx, int force_c) {
 // ------------------------------------------------------------------------------------------------
 // Device part of one MSM.  d_out receives 3 points per window (one "window" in FIXED mode): [E, A2, R2] with
 // window sum S = E + slab * (A2 - R2); a single-slab plan writes S into E and leaves A2 = R2 = infinity.
-void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out, int lane) {
+void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out, int lane, const SortAhead* ahead) {
     const uint32_t n = in.n;
     const uint32_t ntot = in.n + in.n_tail;
     // lane 0: the context's stream and workspace.  lane 1: a second stream and workspace, so two latency-bound MSMs of
     // one IPA round (L and R) overlap instead of queueing behind each other.
     MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
     cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
+    // SortAhead (pipelined submit): the counting sort runs on its own high-priority stream with its own buffers and a
+    // throttled grid, so it proceeds beside the accumulation kernels of the previous MSM (the sort is bound by L2 atomics
+    // and leaves the integer pipe idle; the accumulation is the opposite); the accumulation below waits for it.
+    MsmWorkspace& sws = ahead ? *ahead->ws : ws;
+    cudaStream_t sst = ahead ? ahead->stream : st;
     const uint32_t NB = plan.NB;
     const int nwin = plan.fixed ? 1 : plan.W;
     const uint64_t total_entries_max = (uint64_t)ntot * plan.W;
@@ -609,18 +616,18 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
     uint64_t slots_max = total_entries_max + (uint64_t)rmask * NB;
     slots_max = (slots_max + rmask) & ~(uint64_t)rmask;
     if (slots_max >= 0xfffffff0ull) throw CudaError{cudaErrorInvalidValue, "MSM too large for 32-bit slot indices", __FILE__, __LINE__};
-    ws.counts.reserve((size_t)(NB + 1) * 4);
-    ws.offsets.reserve((size_t)(NB + 1) * 4);
-    ws.entries.reserve((size_t)slots_max * 4);
+    sws.counts.reserve((size_t)(NB + 1) * 4);
+    sws.offsets.reserve((size_t)(NB + 1) * 4);
+    sws.entries.reserve((size_t)slots_max * 4);
     ws.buckets.reserve((size_t)NB * sizeof(xyzz_t));
-    ws.scan_tmp.reserve(4096 * 4);
+    sws.scan_tmp.reserve(4096 * 4);
     ws.task_partial.reserve((size_t)(2 * plan.red_slabs + 3) * nwin * sizeof(xyzz_t));
     if ((NB + SCAN_TILE - 1) / SCAN_TILE > 2048) throw CudaError{cudaErrorInvalidValue, "bucket count too large for scan", __FILE__, __LINE__};
     if (plan.red_slabs > (uint32_t)REDUCE_THREADS * 16) throw CudaError{cudaErrorInvalidValue, "too many reduction slabs", __FILE__, __LINE__};
 
-    uint32_t* counts = ws.counts.as<uint32_t>();
-    uint32_t* offsets = ws.offsets.as<uint32_t>();
-    uint32_t* entries = ws.entries.as<uint32_t>();
+    uint32_t* counts = sws.counts.as<uint32_t>();
+    uint32_t* offsets = sws.offsets.as<uint32_t>();
+    uint32_t* entries = sws.entries.as<uint32_t>();
     xyzz_t* buckets = ws.buckets.as<xyzz_t>();
     const bool prof = ctx->profile && lane == 0;
     auto mark = [&](int i) {
@@ -629,23 +636,31 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
     const uint32_t fstride = plan.fixed ? in.fixed_stride : 0;
 
     mark(0);
-    HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, st));
+    HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, sst));
     const int TPB = 256;
     uint32_t grid = (ntot + TPB - 1) / TPB;
-    k_digits<false><<<grid, TPB, 0, st>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
-                                          in.fixed_first, counts, nullptr);
+    if (ahead && ahead->ctas_per_sm > 0) {
+        const uint32_t cap = (uint32_t)ctx->sm_count * (uint32_t)ahead->ctas_per_sm;
+        if (grid > cap) grid = cap;
+    }
+    k_digits<false><<<grid, TPB, 0, sst>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
+                                           in.fixed_first, counts, nullptr);
     mark(1);
-    exclusive_scan(counts, offsets, NB, rmask, ws.scan_tmp.as<uint32_t>(), st, &ctx->kernel_launches);
+    exclusive_scan(counts, offsets, NB, rmask, sws.scan_tmp.as<uint32_t>(), sst, &ctx->kernel_launches);
     if (P) {  // pad slots of every bucket segment stand for the point at infinity
-        k_fill_pads<<<(NB + 255) / 256, 256, 0, st>>>(counts, offsets, NB, entries);
+        k_fill_pads<<<(NB + 255) / 256, 256, 0, sst>>>(counts, offsets, NB, entries);
         ctx->kernel_launches++;
     }
     // the histogram array becomes the write cursor of every bucket; its spare slot [NB] the claim counter of k_accumulate
-    HALO_CUDA(cudaMemcpyAsync(counts, offsets, (size_t)NB * 4, cudaMemcpyDeviceToDevice, st));
-    HALO_CUDA(cudaMemsetAsync(counts + NB, 0, 4, st));
+    HALO_CUDA(cudaMemcpyAsync(counts, offsets, (size_t)NB * 4, cudaMemcpyDeviceToDevice, sst));
+    HALO_CUDA(cudaMemsetAsync(counts + NB, 0, 4, sst));
     mark(2);
-    k_digits<true><<<grid, TPB, 0, st>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
-                                         in.fixed_first, counts, entries);
+    k_digits<true><<<grid, TPB, 0, sst>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
+                                          in.fixed_first, counts, entries);
+    if (ahead) {
+        HALO_CUDA(cudaEventRecord(ahead->sorted, sst));
+        HALO_CUDA(cudaStreamWaitEvent(st, ahead->sorted, 0));
+    }
     mark(3);
     // P > 0: the first P levels of every bucket's sum as flat pairwise affine additions (msm_pairs.cu); the XYZZ kernels
     // below then see bucket b as the slots [offsets[b] >> P, offsets[b + 1] >> P) of the returned array.

@@ -19,8 +19,15 @@ struct MsmInput {
     uint32_t fixed_first = 0;
 };
 MsmPlan msm_make_fixed_plan(uint64_t n, int force_c);
+// Counting sort of an MSM ahead of its accumulation: own stream (high priority), own sort buffers, throttled grid.
+struct SortAhead {
+    MsmWorkspace* ws;
+    cudaStream_t stream;
+    cudaEvent_t sorted;
+    int ctas_per_sm;  // 0: full grid
+};
 // Device part of one MSM: 3 partial points per window into d_out (see msm.cu).
-void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out, int lane = 0);
+void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out, int lane = 0, const SortAhead* ahead = nullptr);
 // First `passes` levels of the bucket sums as flat pairwise affine additions with batched inversion (msm_pairs.cu).
 const affine_t* pair_tree_enqueue(halo_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const MsmInput& in, const uint32_t* entries,
                                   const uint32_t* total_slots, uint64_t slots_max, int passes);

@@ -98,12 +98,16 @@ int halo_msm_jac(halo_ctx *ctx, const uint64_t *bases_jac /*[n][12]*/, const uin
                  uint64_t out_jac[12]);
 /* Pipelined form of halo_msm_gens for streams of commitments (an IVC chain, a batch of polynomials): submit enqueues
  * the host-to-device copy on a copy stream and the MSM behind it and returns at once; collect waits for that MSM and
- * finishes it.  Two tickets may be in flight, so the copy of call k+1 overlaps the kernels of call k.  `scalars` must
- * stay valid (and should be pinned) until the ticket is collected. */
+ * finishes it.  Two tickets may be in flight, so the copy of call k+1 overlaps the kernels of call k, and (n >= 2^22) the
+ * counting sort of call k+1 runs on a high-priority stream beside the bucket accumulation of call k (the sort is bound
+ * by L2 atomics, the accumulation by the integer pipe).  `scalars` must stay valid (and should be pinned) until the
+ * ticket is collected. */
 int halo_msm_gens_submit(halo_ctx *ctx, const uint64_t *scalars /*[n][4]*/, uint64_t off, uint64_t n, int *ticket);
 int halo_msm_gens_collect(halo_ctx *ctx, int ticket, uint64_t out_jac[12]);
-/* Device-resident variant for throughput measurement: d_scalars is a CUDA device pointer to n scalars. */
+/* Device-resident variants for throughput measurement: d_scalars is a CUDA device pointer to n scalars (complete when
+ * the call is made; for submit_resident untouched until the ticket is collected). */
 int halo_msm_gens_resident(halo_ctx *ctx, const void *d_scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]);
+int halo_msm_gens_submit_resident(halo_ctx *ctx, const void *d_scalars, uint64_t off, uint64_t n, int *ticket);
 
 /* Sum of g Jacobian points on the host, in index order: combines the per-GPU partial MSM results after the
  * single all-gather of the sharded MSM. */

@@ -282,6 +282,15 @@ def test_msm_pipelined_submit_collect(ctx, oracle):
         t = nxt
     for g, e in zip(got, exp):
         assert O.pt_eq(g, e)
+    # device-resident scalars through the same pipeline (halo_msm_gens_submit_resident)
+    import torch
+
+    d0 = torch.from_numpy(np.ascontiguousarray(scs[0]).view(np.int64)).cuda()
+    d1 = torch.from_numpy(np.ascontiguousarray(scs[1]).view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    ta = ctx.msm_gens_submit_resident(d0.data_ptr(), n)
+    tb = ctx.msm_gens_submit_resident(d1.data_ptr(), n)
+    assert O.pt_eq(ctx.msm_gens_collect(ta), exp[0]) and O.pt_eq(ctx.msm_gens_collect(tb), exp[1])
     # the blocking call splits large inputs over the two pipeline slots (copy of the second half overlaps the kernels of
     # the first); forced here at a small size, odd length
     ctx.set_tuning("split_blocking", 10)
@@ -317,6 +326,10 @@ def test_msm_2_22_fixed_and_variable_vs_oracle(halo, oracle):
         assert O.pt_to_affine(c.msm_gens(sc))[0].tobytes() == exp.tobytes()
         t = c.msm_gens_submit(sc)
         assert O.pt_to_affine(c.msm_gens_collect(t))[0].tobytes() == exp.tobytes()
+        # two in flight at a size where the counting sort of the second runs ahead beside the first's accumulation
+        t1, t2 = c.msm_gens_submit(sc), c.msm_gens_submit(sc)
+        assert O.pt_to_affine(c.msm_gens_collect(t1))[0].tobytes() == exp.tobytes()
+        assert O.pt_to_affine(c.msm_gens_collect(t2))[0].tobytes() == exp.tobytes()
         # ragged slice at an offset: the automatic pair-tree passes on partially filled tiles and padded segments
         m, off = n - 77777, 12345
         exp2, _ = O.pt_to_affine(O.msm_affine(gs[off:off + m], sc[:m], threads=16))
