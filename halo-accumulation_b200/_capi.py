@@ -40,6 +40,9 @@ def load():
     lib.halo_last_error.restype = C.c_char_p
     lib.halo_kernel_launches.argtypes = [C.c_void_p]
     lib.halo_kernel_launches.restype = C.c_uint64
+    lib.halo_curve_name.restype = C.c_char_p
+    if lib.halo_curve_name().decode() != _build.CURVE:
+        raise RuntimeError(f"{path} was built for {lib.halo_curve_name().decode()}, HALO_B200_CURVE asks for {_build.CURVE}")
     _lib = lib
     return lib
 

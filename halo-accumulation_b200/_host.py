@@ -67,7 +67,7 @@ def lib():
     global _lib
     if _lib is None:
         load()  # libhalo_b200.so first (RTLD_GLOBAL not needed: rpath $ORIGIN resolves the dependency)
-        path = os.path.join(_build.HERE, "lib", "libhalo_host.so")
+        path = _build.HOST_LIB
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: build it with __graft_entry__.build()")
         _lib = C.CDLL(path)

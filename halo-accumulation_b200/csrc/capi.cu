@@ -155,6 +155,7 @@ void halo_ctx_destroy(halo_ctx* ctx) {
 }
 
 const char* halo_last_error(halo_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+const char* halo_curve_name(void) { return HALO_CURVE_NAME; }
 uint64_t halo_kernel_launches(halo_ctx* ctx) { return ctx ? ctx->kernel_launches : 0; }
 uint64_t halo_num_generators(halo_ctx* ctx) { return ctx ? ctx->n_gens : 0; }
 int halo_set_msm_window(halo_ctx* ctx, int c) {

@@ -60,8 +60,20 @@ template <class P>
 struct alignas(16) fp_t {
     uint32_t v[8];
 };
-using fq_t = fp_t<FqParams>;
-using fr_t = fp_t<FrParams>;
+// The curve of this build.  Pallas (default): coordinates in Fq, scalars in Fr.  -DHALO_CURVE_VESTA swaps the roles:
+// Vesta is y^2 = x^3 + 5 over Pallas' scalar field with Pallas' base field as its scalar field (the Pasta cycle), so
+// every kernel, the host layer and the C ABI are the same sources with `fq_t` = coordinate field, `fr_t` = scalar field.
+#if defined(HALO_CURVE_VESTA)
+using BaseParams = FrParams;
+using ScalarParams = FqParams;
+#define HALO_CURVE_NAME "vesta"
+#else
+using BaseParams = FqParams;
+using ScalarParams = FrParams;
+#define HALO_CURVE_NAME "pallas"
+#endif
+using fq_t = fp_t<BaseParams>;    // coordinate field of the curve
+using fr_t = fp_t<ScalarParams>;  // scalar field of the curve
 
 template <class P>
 HALO_HD void fp_zero(fp_t<P>& r) {

@@ -41,8 +41,14 @@ struct GlvDigits {
     int16_t top;     // highest index with a non-zero digit in either (-1 if xi == 0)
 };
 
+// Constants of both curves come from tools/gen_glv_consts.py (which re-derives the Pallas set as a check).
+#if defined(HALO_CURVE_VESTA)
+__device__ __constant__ uint32_t c_beta_mont[8] = {0x7feeeee3u, 0x410e7d20u, 0xd8fa2279u, 0x6afdf14fu,
+                                                   0xeca4d4d7u, 0xfd3d8a04u, 0x77dba4efu, 0x2de2d607u};
+#else
 __device__ __constant__ uint32_t c_beta_mont[8] = {0x9e65eac8u, 0xfbdfd7aau, 0xe50025fbu, 0x0cd4d654u,
                                                    0x3785b99au, 0xd59892a3u, 0x585e8789u, 0x2a27fb62u};
+#endif
 
 // K4 point part: G[j] <- affine(G[j] + xi * G[j + m]) with xi = k1 + k2 lambda is the D = 1 case of k_fold_multi below
 // (joint digit loop uniform across the grid: same xi for every element of a round).  The sum is left in XYZZ coordinates
@@ -271,11 +277,19 @@ static void sub5(uint64_t* r, const uint64_t* a, const uint64_t* b) {
     add5(r, a, nb);
 }
 // basis and fixed-point reciprocals g_i = floor(|.| 2^384 / r) (tools: see DESIGN.md; checked by the open parity tests)
+#if defined(HALO_CURVE_VESTA)
+static const uint64_t A1[2] = {0x8cb1279300000001ull, 0x49e69d1640a89953ull};            // a1 = b2
+static const uint64_t B1N[2] = {0x7fcae1c700000000ull, 0x49e69d1640f04915ull};           // -b1
+static const uint64_t A2[3] = {0x0c7c095a00000001ull, 0x93cd3a2c8198e269ull, 0x0ull};    // a2
+static const uint64_t G1[5] = {0x841414c24bf99a82ull, 0x61afdea685cc1578ull, 0x32c49e4c00000003ull, 0x279a745902a2654eull, 0x1ull};
+static const uint64_t G2[5] = {0x0009789fdd747ae0ull, 0x61afdea6853283aeull, 0xff2b871bffffffffull, 0x279a745903c12455ull, 0x1ull};
+#else
 static const uint64_t A1[2] = {0x8cb1279300000000ull, 0x49e69d1640a89953ull};            // a1 = b2
 static const uint64_t B1N[2] = {0x7fcae1c700000001ull, 0x49e69d1640f04915ull};           // -b1
 static const uint64_t A2[3] = {0x0c7c095a00000001ull, 0x93cd3a2c8198e269ull, 0x0ull};    // a2
 static const uint64_t G1[5] = {0x4a95a2d972171db4ull, 0x61afdea68480fa55ull, 0x32c49e4bffffffffull, 0x279a745902a2654eull, 0x1ull};
 static const uint64_t G2[5] = {0xc689c5879f98a4deull, 0x61afdea683e7688aull, 0xff2b871c00000003ull, 0x279a745903c12455ull, 0x1ull};
+#endif
 
 }  // namespace glv
 

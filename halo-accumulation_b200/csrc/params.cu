@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) k_derive_points(const affine_t* __restric
         s[2 * j] = (uint32_t)dg[j];
         s[2 * j + 1] = (uint32_t)(dg[j] >> 32);
     }
-    fp_mod_limbs<FrParams>(m);
+    fp_mod_limbs<ScalarParams>(m);
     for (int it = 0; it < 3; it++) {
         uint32_t borrow = sub8(t, s, m);
 #pragma unroll

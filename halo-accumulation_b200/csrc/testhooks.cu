@@ -236,9 +236,9 @@ int halo_test_fp_op(halo_ctx* ctx, int which, int op, const uint64_t* a, const u
     }
     unsigned grid = (unsigned)((n + 127) / 128);
     if (which)
-        k_fp_op<FrParams><<<grid, 128, 0, ctx->stream>>>(op, da.as<fr_t>(), b ? db.as<fr_t>() : nullptr, dout.as<fr_t>(), n);
+        k_fp_op<ScalarParams><<<grid, 128, 0, ctx->stream>>>(op, da.as<fr_t>(), b ? db.as<fr_t>() : nullptr, dout.as<fr_t>(), n);
     else
-        k_fp_op<FqParams><<<grid, 128, 0, ctx->stream>>>(op, da.as<fq_t>(), b ? db.as<fq_t>() : nullptr, dout.as<fq_t>(), n);
+        k_fp_op<BaseParams><<<grid, 128, 0, ctx->stream>>>(op, da.as<fq_t>(), b ? db.as<fq_t>() : nullptr, dout.as<fq_t>(), n);
     ctx->kernel_launches++;
     HALO_CUDA(cudaGetLastError());
     HALO_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -230,7 +230,7 @@ public:
             s[2 * j] = (uint32_t)dg[j];
             s[2 * j + 1] = (uint32_t)(dg[j] >> 32);
         }
-        fp_mod_limbs<FrParams>(m);
+        fp_mod_limbs<ScalarParams>(m);
         for (int it = 0; it < 3; it++) {  // r > 2^254: at most three subtractions
             uint32_t borrow = sub8(t, s, m);
             for (int j = 0; j < 8; j++) s[j] = borrow ? s[j] : t[j];

@@ -49,6 +49,10 @@ typedef struct halo_ctx halo_ctx;
 int halo_ctx_create(int device, uint64_t max_n, halo_ctx **out);
 void halo_ctx_destroy(halo_ctx *ctx);
 const char *halo_last_error(halo_ctx *ctx);
+/* The curve this library was built for: "pallas" (libhalo_b200.so, the reference's `ark_pallas` types) or "vesta"
+ * (libhalo_b200_vesta.so: same sources and entry points with coordinate and scalar field swapped).
+ * A process that needs both halves of the Pasta cycle loads the two libraries with dlopen(RTLD_LOCAL). */
+const char *halo_curve_name(void);
 /* Count of this library's kernel launches on the context since creation (bench accounting). */
 uint64_t halo_kernel_launches(halo_ctx *ctx);
 /* Tuning / diagnostics: force the Pippenger window width (0 = automatic). */

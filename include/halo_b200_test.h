@@ -9,7 +9,7 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* Element-wise field op on the device: which = 0 (Fq) / 1 (Fr); op = 0 mul, 1 add, 2 sub, 3 sqr, 4 inv,
+/* Element-wise field op on the device: which = 0 (coordinate field Fq) / 1 (scalar field Fr) of the build's curve; op = 0 mul, 1 add, 2 sub, 3 sqr, 4 inv,
  * 5 neg, 6 to_canonical, 7 from_canonical.  a, b, out: host arrays of n elements (uint64_t[4] each). */
 int halo_test_fp_op(halo_ctx *ctx, int which, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n);
 /* Single device thread: sum_i (neg[i] ? -P_i : P_i) over affine points via mixed adds -> Jacobian. */

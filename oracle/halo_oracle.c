@@ -18,18 +18,37 @@ typedef uint64_t u64;
 typedef unsigned __int128 u128;
 typedef unsigned char u8;
 
-/* Pallas base field Fq: p = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001 */
+/* The two Pasta moduli.  Pallas (default): coordinates over p, scalars over r.  -DHALO_CURVE_VESTA builds the same
+ * restatement for Vesta, y^2 = x^3 + 5 over r with scalar field p: "fq" always names the coordinate
+ * field of the build's curve and "fr" its scalar field.
+ *   p = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001   (Pallas base field)
+ *   r = 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001   (Pallas scalar field) */
+#define PASTA_P0 0x992d30ed00000001ULL
+#define PASTA_P1 0x224698fc094cf91bULL
+#define PASTA_R0 0x8c46eb2100000001ULL
+#define PASTA_R1 0x224698fc0994a8ddULL
+#ifdef HALO_CURVE_VESTA
+#define BASE0 PASTA_R0
+#define BASE1 PASTA_R1
+#define SCAL0 PASTA_P0
+#define SCAL1 PASTA_P1
+#else
+#define BASE0 PASTA_P0
+#define BASE1 PASTA_P1
+#define SCAL0 PASTA_R0
+#define SCAL1 PASTA_R1
+#endif
+
 #define FP_NAME fq
-#define FP_MOD0 0x992d30ed00000001ULL
-#define FP_MOD1 0x224698fc094cf91bULL
+#define FP_MOD0 BASE0
+#define FP_MOD1 BASE1
 #define FP_MOD2 0x0000000000000000ULL
 #define FP_MOD3 0x4000000000000000ULL
 #include "fp_tmpl.h"
 
-/* Pallas scalar field Fr: r = 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001 */
 #define FP_NAME fr
-#define FP_MOD0 0x8c46eb2100000001ULL
-#define FP_MOD1 0x224698fc0994a8ddULL
+#define FP_MOD0 SCAL0
+#define FP_MOD1 SCAL1
 #define FP_MOD2 0x0000000000000000ULL
 #define FP_MOD3 0x4000000000000000ULL
 #include "fp_tmpl.h"

@@ -9,7 +9,11 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+# HALO_B200_CURVE=vesta selects the Vesta build of the restatement (same sources, the two Pasta moduli in swapped roles)
+CURVE = os.environ.get("HALO_B200_CURVE", "pallas")
+assert CURVE in ("pallas", "vesta"), CURVE
+_LIB_NAME = "liboracle.so" if CURVE == "pallas" else "liboracle_vesta.so"
+_LIB_PATH = os.path.join(_HERE, _LIB_NAME)
 MAX_LG = 32
 
 u64p = C.POINTER(C.c_uint64)
@@ -58,7 +62,7 @@ def build(force=False):
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
-    subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE, "-B", _LIB_NAME], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 
@@ -93,6 +97,8 @@ def _arr(x, shape=None):
 FQ, FR = 0, 1
 P_MOD = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001
 R_MOD = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
+if CURVE == "vesta":  # coordinate field (FQ) and scalar field (FR) of the build's curve
+    P_MOD, R_MOD = R_MOD, P_MOD
 _MODS = {FQ: P_MOD, FR: R_MOD}
 _MONT = 1 << 256
 _MASK = (1 << 64) - 1

@@ -6,9 +6,12 @@ Reference: code/src/{main.rs:18-45, group.rs, pcdl.rs:56-91}; arkworks conventio
 the published 0.5.0 crates (not in the reference tree).
 """
 import hashlib
+import os
 
 P = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001  # Pallas base field Fq
 R = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001  # Pallas scalar field Fr
+if os.environ.get("HALO_B200_CURVE", "pallas") == "vesta":  # Vesta: y^2 = x^3 + 5 over Pallas' Fr, scalars in Pallas' Fq
+    P, R = R, P
 MONT = 1 << 256
 B = 5
 GEN = (P - 1, 2)

@@ -25,8 +25,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 
-R_MOD = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kat_pcdl_2_10.json")
+R_MOD = O.R_MOD  # scalar field of the curve selected by HALO_B200_CURVE
+# HALO_B200_CURVE=vesta writes the same file for the Vesta instantiation (ark_vesta types in place of ark_pallas,
+# same derivation rule for S, H, G_i; nothing in the reference pins it: SURVEY 8(f).4)
+KAT_FILE = "kat_pcdl_2_10.json" if O.CURVE == "pallas" else "kat_pcdl_2_10_vesta.json"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), KAT_FILE)
 
 
 def x(tag, i):
@@ -65,7 +68,8 @@ def build():
     wbar = xs("halo-b200-kat/wbar", 1)[0]
     v = O.scalar_dot(p, O.construct_powers(z, deg))
     kat = {
-        "about": "known answers for rasmus-kirk/halo-accumulation, n = 2^10 (config 1); see tests/golden/make_kat.py",
+        "about": "known answers for rasmus-kirk/halo-accumulation, n = 2^10 (config 1); see tests/golden/make_kat.py"
+                 + ("" if O.CURVE == "pallas" else " -- VESTA instantiation (ark_vesta in place of ark_pallas)"),
         "n": n, "d": d, "poly_len": deg,
         "input_rule": "x(tag, i) = Fr::from_le_bytes_mod_order(Sha3_256(tag || u64_le(i)))",
         "inputs": {"p": "x('halo-b200-kat/p', i), i < poly_len", "z": "x('halo-b200-kat/z', 0)", "w": "x('halo-b200-kat/w', 0)",

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import pyref as PR
+from oracle.oracle import CURVE  # "pallas" unless HALO_B200_CURVE=vesta (tests/test_vesta.py re-runs this file that way)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -39,7 +40,9 @@ def test_cuda_library_exports_declared_symbols(libs):
 
 
 def test_library_contains_sm100a_code():
-    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "halo-accumulation_b200", "lib", "libhalo_b200.so")],
+    from halo_accumulation_b200 import _build
+
+    out = subprocess.run(["cuobjdump", "-lelf", _build.LIB],
                          capture_output=True, text=True).stdout
     assert "sm_100a" in out
 
@@ -74,7 +77,8 @@ def hostcheck():
     d = os.path.join(ROOT, "tests", "hostcheck")
     libs = {}
     for tag, flags in (("portable", ["-DHALO_FP_FORCE_PORTABLE"]), ("host64", [])):
-        so = os.path.join(d, f"libhostcheck_{tag}.so")
+        so = os.path.join(d, f"libhostcheck_{tag}{'' if CURVE == 'pallas' else '_vesta'}.so")
+        flags = flags + (["-DHALO_CURVE_VESTA"] if CURVE == "vesta" else [])
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", *flags, "-o", so,
                                os.path.join(d, "hostcheck.cpp")])
         libs[tag] = C.CDLL(so)
@@ -171,6 +175,8 @@ def test_glv_joint_sparse_form(libs, oracle):
     cuda, _ = libs
     LAMBDA = 0x397E65A7D7C1AD71AEE24B27E308F0A61259527EC1D4752E619D1840AF55F1B1
     BETA = 0x2D33357CB532458ED3552A23A8554E5005270D29D19FC7D27B7FD22F0201B547
+    if CURVE == "vesta":  # the fields swap roles, and so do the two cube roots (tools/gen_glv_consts.py)
+        LAMBDA, BETA = BETA, LAMBDA
     assert pow(LAMBDA, 3, PR.R) == 1 and pow(BETA, 3, PR.P) == 1
     assert PR.pt_mul(PR.GEN, LAMBDA) == (BETA * PR.GEN[0] % PR.P, PR.GEN[1])  # phi(P) = (beta x, y) = lambda * P
     rnd = random.Random(10)

@@ -9,6 +9,9 @@ import numpy as np
 import pytest
 
 from oracle import pyref as PR
+from oracle.oracle import CURVE
+
+pallas_only = pytest.mark.skipif(CURVE != "pallas", reason="pinned to the reference's Pallas constants (consts.rs, SURVEY appendix A)")
 
 
 def test_sha3_matches_hashlib(oracle):
@@ -17,6 +20,7 @@ def test_sha3_matches_hashlib(oracle):
         assert oracle.sha3_256(msg[:L]) == hashlib.sha3_256(msg[:L]).digest()
 
 
+@pallas_only
 def test_generators_match_consts_rs(oracle, golden):
     """All 16 386 golden points of the reference: S, H (Jacobian, up to projective equivalence) and GS (affine,
     Montgomery limbs, bit for bit)."""
@@ -30,6 +34,7 @@ def test_generators_match_consts_rs(oracle, golden):
         assert oracle.lib().orc_pt_on_curve_affine(oracle._p(np.ascontiguousarray(a)))
 
 
+@pallas_only
 def test_generator_kats_from_survey(oracle):
     """SURVEY.md appendix A.2 known answers (decoded from consts.rs, canonical big-endian hex)."""
     assert hashlib.sha3_256(PR.GENESIS + (2).to_bytes(8, "little")).hexdigest() == \
@@ -81,8 +86,9 @@ def test_u_check_kat(oracle):
     h = oracle.h_get_poly(xis)
     assert oracle.from_mont(h) == [1, 3, 2, 6, 1, 3, 2, 6]
     U = oracle.pedersen_commit(None, gs[:8], h)
-    assert oracle.pt_to_affine_ints(U) == (0x18CEF7A91C998EAB6266EAA5C7523A520B6F9B56AEFE02B7CB48B226B9C0530C,
-                                           0x2CC9CEE89D461087F1312759EFB678EC548F5CDA04F99A56429AE889CC2D7DA3)
+    if CURVE == "pallas":
+        assert oracle.pt_to_affine_ints(U) == (0x18CEF7A91C998EAB6266EAA5C7523A520B6F9B56AEFE02B7CB48B226B9C0530C,
+                                               0x2CC9CEE89D461087F1312759EFB678EC548F5CDA04F99A56429AE889CC2D7DA3)
     # fold direction / challenge indexing (pcdl.rs:399-423)
     cur = list(oracle.affine_to_jac(gs[:8]))
     for i in range(3):
@@ -90,8 +96,9 @@ def test_u_check_kat(oracle):
         cur = [oracle.pt_add(cur[j], oracle.pt_mul(cur[j + half], xis[i + 1])) for j in range(half)]
     assert oracle.pt_eq(cur[0], U)
     # compressed form under the restated arkworks rule (33 bytes, flags in the last byte; y > -y here)
-    assert oracle.pt_serialize_compressed(U).hex() == \
-        "0c53c0b926b248cbb702feae569b6f0b523a52c7a5ea6662ab8e991ca9f7ce18" + "80"
+    if CURVE == "pallas":
+        assert oracle.pt_serialize_compressed(U).hex() == \
+            "0c53c0b926b248cbb702feae569b6f0b523a52c7a5ea6662ab8e991ca9f7ce18" + "80"
     assert oracle.pt_serialize_compressed(oracle.pt_from_affine_ints(None)).hex() == "00" * 32 + "40"
 
 
@@ -195,4 +202,4 @@ def test_kat_file_is_reproduced_by_the_oracle():
     spec = importlib.util.spec_from_file_location("make_kat", os.path.join(here, "golden", "make_kat.py"))
     mk = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mk)
-    assert mk.build() == json.load(open(os.path.join(here, "golden", "kat_pcdl_2_10.json")))
+    assert mk.build() == json.load(open(os.path.join(here, "golden", mk.KAT_FILE)))
