@@ -5,6 +5,7 @@ Pallas MSMs, IPA folds and h-expansion behind PCDL / ASDL.  The submodules `grou
 and `acc` mirror the reference's Rust modules of the same names (code/src/*.rs) on top of it.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -96,6 +97,17 @@ class Context:
     def load_generators(self, S, H, gs):
         S, H, gs = arr(S, (12,)), arr(H, (12,)), arr(gs).reshape(-1, 8)
         self._chk(self._lib.halo_load_generators(self._h, p64(S), p64(H), p64(gs), C.c_uint64(gs.shape[0])))
+
+    def save_generators(self, path):
+        """Writes S, H and the resident generators to a generator store (flat file of the 64-byte device records)."""
+        self._chk(self._lib.halo_save_generators(self._h, os.fsencode(path)))
+
+    def load_generators_file(self, path, n=0):
+        """The first n generators of a store (0 = all) become the resident set; checksum and on-curve check included."""
+        self._chk(self._lib.halo_load_generators_file(self._h, os.fsencode(path), C.c_uint64(n)))
+
+    def num_generators(self):
+        return int(self._lib.halo_num_generators(self._h))
 
     def get_generators(self, off, n):
         out = np.zeros((n, 8), dtype=np.uint64)

@@ -11,7 +11,7 @@ from . import _build
 u64p = C.POINTER(C.c_uint64)
 u8p = C.POINTER(C.c_uint8)
 
-HALO_OK, HALO_EINVAL, HALO_ELEN, HALO_ECUDA, HALO_ENCCL, HALO_ENOMEM, HALO_ESTATE = 0, -1, -2, -3, -4, -5, -6
+HALO_OK, HALO_EINVAL, HALO_ELEN, HALO_ECUDA, HALO_ENCCL, HALO_ENOMEM, HALO_ESTATE, HALO_EIO = 0, -1, -2, -3, -4, -5, -6, -7
 
 
 class HaloError(RuntimeError):
@@ -41,6 +41,10 @@ def load():
     lib.halo_kernel_launches.argtypes = [C.c_void_p]
     lib.halo_kernel_launches.restype = C.c_uint64
     lib.halo_curve_name.restype = C.c_char_p
+    lib.halo_num_generators.argtypes = [C.c_void_p]
+    lib.halo_num_generators.restype = C.c_uint64
+    lib.halo_save_generators.argtypes = [C.c_void_p, C.c_char_p]
+    lib.halo_load_generators_file.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
     if lib.halo_curve_name().decode() != _build.CURVE:
         raise RuntimeError(f"{path} was built for {lib.halo_curve_name().decode()}, HALO_B200_CURVE asks for {_build.CURVE}")
     _lib = lib

@@ -304,6 +304,156 @@ int halo_load_generators(halo_ctx* ctx, const uint64_t S_jac[12], const uint64_t
     HALO_CATCH(ctx)
 }
 
+// ---- generator store ---------------------------------------------------------------------------------
+// The reference keeps its public parameters as generated source (main.rs:47-67 writes them, consts.rs holds 16 386 of
+// them, and report.md:2081-2086 names that as the limit on n).  Here they are a flat file of the device records:
+//   header (64 B): magic "HALOGEN1", curve name (8 B, zero padded), n, record size (64), checksum, 24 B reserved
+//   S, H           2 x 64 B Montgomery affine
+//   G_0 .. G_{n-1} n x 64 B Montgomery affine (x | y, little-endian limbs: the bytes of consts.rs' mk_aff! arguments)
+// Loading streams the file through two pinned buffers (the read of chunk k+1 overlaps the copy of chunk k), verifies
+// the checksum and checks on the device that every record is a canonical point on the curve.
+namespace {
+constexpr char STORE_MAGIC[8] = {'H', 'A', 'L', 'O', 'G', 'E', 'N', '1'};
+constexpr size_t STORE_CHUNK = 32u << 20;
+struct StoreHeader {
+    char magic[8];
+    char curve[8];
+    uint64_t n;
+    uint64_t record_bytes;
+    uint64_t checksum;
+    uint64_t reserved[3];
+};
+static_assert(sizeof(StoreHeader) == 64, "store header layout");
+// 64-bit multiply-rotate checksum over the u64 words of S, H and the records, in file order
+inline uint64_t store_mix(uint64_t h, const void* data, size_t bytes) {
+    const uint64_t* w = static_cast<const uint64_t*>(data);
+    for (size_t i = 0; i < bytes / 8; i++) {
+        h ^= w[i];
+        h *= 0x9e3779b97f4a7c15ull;
+        h = (h << 29) | (h >> 35);
+    }
+    return h;
+}
+struct FileCloser {
+    FILE* f;
+    ~FileCloser() {
+        if (f) fclose(f);
+    }
+};
+struct PinnedPair {
+    void* p[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    ~PinnedPair() {
+        for (int i = 0; i < 2; i++) {
+            if (p[i]) cudaFreeHost(p[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+    }
+};
+}  // namespace
+
+int halo_save_generators(halo_ctx* ctx, const char* path) {
+    if (!ctx || !path) return HALO_EINVAL;
+    if (ctx->n_gens == 0 || !ctx->have_SH) return fail(ctx, HALO_ESTATE, "halo_save_generators: no generators resident");
+    HALO_TRY(ctx)
+    FileCloser fc{fopen(path, "wb")};
+    if (!fc.f) return fail(ctx, HALO_EIO, "halo_save_generators: cannot open the file for writing");
+    StoreHeader hd = {};
+    memcpy(hd.magic, STORE_MAGIC, 8);
+    strncpy(hd.curve, HALO_CURVE_NAME, 8);
+    hd.n = ctx->n_gens;
+    hd.record_bytes = sizeof(affine_t);
+    affine_t sh[2] = {ctx->S, ctx->H};
+    uint64_t sum = store_mix(0, sh, sizeof sh);
+    if (fwrite(&hd, sizeof hd, 1, fc.f) != 1 || fwrite(sh, sizeof sh, 1, fc.f) != 1)
+        return fail(ctx, HALO_EIO, "halo_save_generators: write failed");
+    PinnedPair pp;
+    for (int i = 0; i < 2; i++) {
+        HALO_CUDA(cudaMallocHost(&pp.p[i], STORE_CHUNK));
+        HALO_CUDA(cudaEventCreateWithFlags(&pp.ev[i], cudaEventDisableTiming));
+    }
+    const size_t total = ctx->n_gens * sizeof(affine_t);
+    const char* src = ctx->gens.as<char>();
+    size_t issued = 0, written = 0;
+    int k = 0;
+    auto issue = [&](int b) {
+        size_t len = total - issued < STORE_CHUNK ? total - issued : STORE_CHUNK;
+        HALO_CUDA(cudaMemcpyAsync(pp.p[b], src + issued, len, cudaMemcpyDeviceToHost, ctx->stream));
+        HALO_CUDA(cudaEventRecord(pp.ev[b], ctx->stream));
+        issued += len;
+    };
+    if (issued < total) issue(0);
+    while (written < total) {  // the device-to-host copy of chunk k+1 runs while chunk k is hashed and written
+        int b = k & 1;
+        if (issued < total) issue(b ^ 1);
+        HALO_CUDA(cudaEventSynchronize(pp.ev[b]));
+        size_t len = total - written < STORE_CHUNK ? total - written : STORE_CHUNK;
+        sum = store_mix(sum, pp.p[b], len);
+        if (fwrite(pp.p[b], 1, len, fc.f) != len) return fail(ctx, HALO_EIO, "halo_save_generators: write failed");
+        written += len;
+        k++;
+    }
+    hd.checksum = sum;
+    if (fseek(fc.f, 0, SEEK_SET) != 0 || fwrite(&hd, sizeof hd, 1, fc.f) != 1 || fflush(fc.f) != 0)
+        return fail(ctx, HALO_EIO, "halo_save_generators: write failed");
+    HALO_CATCH(ctx)
+}
+
+int halo_load_generators_file(halo_ctx* ctx, const char* path, uint64_t n) {
+    if (!ctx || !path) return HALO_EINVAL;
+    HALO_TRY(ctx)
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) return fail(ctx, HALO_EIO, "halo_load_generators_file: cannot open the file");
+    StoreHeader hd;
+    affine_t sh[2];
+    if (fread(&hd, sizeof hd, 1, fc.f) != 1 || fread(sh, sizeof sh, 1, fc.f) != 1)
+        return fail(ctx, HALO_EIO, "halo_load_generators_file: truncated header");
+    char curve[8] = {};
+    strncpy(curve, HALO_CURVE_NAME, 8);
+    if (memcmp(hd.magic, STORE_MAGIC, 8) != 0 || hd.record_bytes != sizeof(affine_t))
+        return fail(ctx, HALO_EINVAL, "halo_load_generators_file: not a generator store");
+    if (memcmp(hd.curve, curve, 8) != 0)
+        return fail(ctx, HALO_EINVAL, "halo_load_generators_file: the store holds points of the other curve");
+    if (n == 0) n = hd.n;
+    if (n > hd.n) return fail(ctx, HALO_EINVAL, "halo_load_generators_file: the store holds fewer generators than requested");
+    if (n > ctx->max_n) return fail(ctx, HALO_EINVAL, "halo_load_generators_file: n exceeds max_n");
+    ctx->n_gens = 0;  // the resident set is replaced; a failure below leaves the context without generators
+    ctx->pre_n = 0;
+    ctx->gens.reserve(n * sizeof(affine_t));
+    PinnedPair pp;
+    for (int i = 0; i < 2; i++) {
+        HALO_CUDA(cudaMallocHost(&pp.p[i], STORE_CHUNK));
+        HALO_CUDA(cudaEventCreateWithFlags(&pp.ev[i], cudaEventDisableTiming));
+    }
+    // a prefix of the store is a valid parameter set (G_0..G_{n-1}); the checksum covers the whole file, so it is
+    // verified only when all of it is read -- the on-curve check below covers every record either way
+    const size_t total = n * sizeof(affine_t);
+    uint64_t sum = store_mix(0, sh, sizeof sh);
+    size_t done = 0;
+    for (int k = 0; done < total; k++) {
+        int b = k & 1;
+        if (k >= 2) HALO_CUDA(cudaEventSynchronize(pp.ev[b]));  // the copy out of this buffer two chunks ago
+        size_t len = total - done < STORE_CHUNK ? total - done : STORE_CHUNK;
+        if (fread(pp.p[b], 1, len, fc.f) != len) return fail(ctx, HALO_EIO, "halo_load_generators_file: truncated file");
+        sum = store_mix(sum, pp.p[b], len);
+        HALO_CUDA(cudaMemcpyAsync(ctx->gens.as<char>() + done, pp.p[b], len, cudaMemcpyHostToDevice, ctx->stream));
+        HALO_CUDA(cudaEventRecord(pp.ev[b], ctx->stream));
+        done += len;
+    }
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n == hd.n && sum != hd.checksum) return fail(ctx, HALO_EINVAL, "halo_load_generators_file: checksum mismatch");
+    ctx->stage_bases.reserve(sizeof sh);
+    HALO_CUDA(cudaMemcpyAsync(ctx->stage_bases.p, sh, sizeof sh, cudaMemcpyHostToDevice, ctx->stream));
+    if (params_count_off_curve(ctx, ctx->stage_bases.as<affine_t>(), 2) != 0 ||
+        params_count_off_curve(ctx, ctx->gens.as<affine_t>(), n) != 0)
+        return fail(ctx, HALO_EINVAL, "halo_load_generators_file: the store holds records that are not points on the curve");
+    ctx->S = sh[0];
+    ctx->H = sh[1];
+    ctx->have_SH = true;
+    ctx->n_gens = n;
+    HALO_CATCH(ctx)
+}
+
 int halo_get_generators(halo_ctx* ctx, uint64_t off, uint64_t n, uint64_t* out_affine) {
     if (!ctx || !out_affine) return HALO_EINVAL;
     if (off + n > ctx->n_gens) return fail(ctx, HALO_EINVAL, "halo_get_generators: range exceeds resident generators");

@@ -19,6 +19,7 @@ enum : int {
     E_NCCL = -4,
     E_NOMEM = -5,
     E_STATE = -6,
+    E_IO = -7,
 };
 
 struct CudaError {

@@ -79,6 +79,39 @@ __global__ void __launch_bounds__(128) k_derive_points(const affine_t* __restric
     out[i] = a;
 }
 
+// Generator store (capi.cu: halo_load_generators_file): a record is accepted only if it is a canonical Montgomery residue
+// pair on y^2 = x^3 + 5 (the point at infinity is not a generator).  bad[0] counts the records that are not.
+__global__ void __launch_bounds__(256) k_count_off_curve(const affine_t* __restrict__ pts, uint64_t n, unsigned long long* bad) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t p = pts[i];
+    uint32_t m[8], t[8];
+    fp_mod_limbs<BaseParams>(m);
+    bool ok = sub8(t, p.x.v, m) != 0 && sub8(t, p.y.v, m) != 0;  // both coordinates < modulus
+    fq_t lhs, rhs, five;
+    fp_sqr(lhs, p.y);
+    fp_sqr(rhs, p.x);
+    fp_mul(rhs, rhs, p.x);
+    fp_from_u32(five, 5);
+    fp_add(rhs, rhs, five);
+    ok = ok && fp_eq(lhs, rhs);
+    if (!ok) atomicAdd(bad, 1ull);
+}
+
+uint64_t params_count_off_curve(halo_ctx* ctx, const affine_t* d_pts, uint64_t n) {
+    if (n == 0) return 0;
+    ctx->stage_misc.reserve(256);
+    auto* d_bad = ctx->stage_misc.as<unsigned long long>();
+    HALO_CUDA(cudaMemsetAsync(d_bad, 0, 8, ctx->stream));
+    k_count_off_curve<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_pts, n, d_bad);
+    ctx->kernel_launches++;
+    HALO_CUDA(cudaGetLastError());
+    unsigned long long bad = 0;
+    HALO_CUDA(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HALO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return bad;
+}
+
 void params_ensure_table(halo_ctx* ctx) {
     if (ctx->fixed_table.p) return;
     HALO_CUDA(cudaMemcpyToSymbolAsync(c_genesis, GENESIS, 60, 0, cudaMemcpyHostToDevice, ctx->stream));

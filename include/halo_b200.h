@@ -41,6 +41,7 @@ extern "C" {
 #define HALO_ENCCL (-4)
 #define HALO_ENOMEM (-5)
 #define HALO_ESTATE (-6) /* call out of order (e.g. generators not loaded) */
+#define HALO_EIO (-7)    /* generator store: file cannot be opened / read / written */
 
 typedef struct halo_ctx halo_ctx;
 
@@ -81,6 +82,14 @@ int halo_set_fixed_base(halo_ctx *ctx, int on);
 /* Alternative: take the reference's own constants (consts::S, consts::H as Jacobian, consts::GS affine). */
 int halo_load_generators(halo_ctx *ctx, const uint64_t S_jac[12], const uint64_t H_jac[12],
                          const uint64_t *gs_affine /*[n][8]*/, uint64_t n);
+/* Generator store (the reference's analogue is main.rs:47-67 writing consts.rs / points.txt, and
+ * report.md:2081-2086 names the generated source as what limits n): S, H and the resident G_i as one flat file of
+ * 64-byte Montgomery affine records behind a 64-byte header (magic, curve, n, checksum).  `load` reads the first n
+ * generators of a store (0 = all of them) through pinned double buffers, verifies the checksum when the whole file is
+ * read, and checks ON THE DEVICE that every record is a canonical point on the curve; on failure the context is left
+ * without generators.  HALO_EIO: file problems; HALO_EINVAL: not a store, other curve, too short, corrupt. */
+int halo_save_generators(halo_ctx *ctx, const char *path);
+int halo_load_generators_file(halo_ctx *ctx, const char *path, uint64_t n);
 /* Reads generators back (tests / caching): out_affine[i] = G_{off+i}. */
 int halo_get_generators(halo_ctx *ctx, uint64_t off, uint64_t n, uint64_t *out_affine /*[n][8]*/);
 int halo_get_SH(halo_ctx *ctx, uint64_t S_jac[12], uint64_t H_jac[12]);

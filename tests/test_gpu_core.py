@@ -436,3 +436,51 @@ def test_msm_pair_tree_oversized_buckets(ctx, oracle):
         ctx.set_tuning("pair_passes", -1)
         ctx.set_fixed_base(True)
         ctx.derive_generators(1 << 16)
+
+
+def test_generator_store_round_trip(halo, ctx, oracle, tmp_path):
+    """save -> load gives the same resident parameters (and therefore the same MSM); a prefix of a store is a
+    valid parameter set; a corrupted record, a wrong checksum, the other curve's store and a short file are refused."""
+    O = oracle
+    n = 1 << 12
+    path = str(tmp_path / "gens.bin")
+    try:
+        ctx.derive_generators(n)
+        gs, (S, H) = ctx.get_generators(0, n), ctx.get_SH()
+        sc = O.random_scalars(n, 77)
+        exp = ctx.msm_gens(sc)
+        ctx.save_generators(path)
+        raw = open(path, "rb").read()
+        assert len(raw) == 64 + 128 + 64 * n and raw[:8] == b"HALOGEN1" and raw[8:8 + len(CURVE)] == CURVE.encode()
+        assert raw[192:192 + 64 * n] == gs.astype("<u8").tobytes()  # the records are the device bytes (consts.rs limbs)
+        ctx.derive_generators(16)  # forget them
+        ctx.load_generators_file(path)
+        assert np.array_equal(ctx.get_generators(0, n), gs)
+        S2, H2 = ctx.get_SH()
+        assert O.pt_eq(S2, S) and O.pt_eq(H2, H)
+        assert O.pt_eq(ctx.msm_gens(sc), exp) and O.pt_eq(exp, O.msm_affine(gs, sc, threads=8))
+        ctx.load_generators_file(path, 1000)  # ragged prefix
+        assert ctx.num_generators() == 1000 and np.array_equal(ctx.get_generators(0, 1000), gs[:1000])
+        # failures: every one leaves the context without generators and with a message
+        def refuse(data, code, n_req=0):
+            bad = str(tmp_path / "bad.bin")
+            open(bad, "wb").write(data)
+            with pytest.raises(halo.HaloError) as e:
+                ctx.load_generators_file(bad, n_req)
+            assert e.value.code == code, e.value
+            assert ctx.num_generators() == 0 or code == -7
+        flipped = bytearray(raw)
+        flipped[192 + 64 * 17 + 3] ^= 0x10  # one bit of G_17.x
+        refuse(bytes(flipped), -1)           # checksum
+        refuse(bytes(flipped), -1, n_req=64)  # prefix load: no checksum, the on-curve check catches it
+        other = bytearray(raw)
+        other[8:16] = (b"vesta" if CURVE == "pallas" else b"pallas").ljust(8, b"\0")
+        refuse(bytes(other), -1)
+        refuse(raw[:-64], -7)                # truncated
+        refuse(b"not a store" * 30, -1)
+        refuse(raw, -1, n_req=n + 1)         # more than the store holds
+        with pytest.raises(halo.HaloError) as e:
+            ctx.load_generators_file(str(tmp_path / "missing.bin"))
+        assert e.value.code == -7
+    finally:
+        ctx.derive_generators(1 << 16)
