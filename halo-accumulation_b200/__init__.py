@@ -43,6 +43,11 @@ def check_canaries():
     return int(bad), live.value
 
 
+class _MsmDesc(C.Structure):  # halo_msm_desc, include/halo_b200.h
+    _fields_ = [("bases_affine", C.POINTER(C.c_uint64)), ("inf_flags", u8p), ("scalars", C.POINTER(C.c_uint64)),
+                ("n", C.c_uint64), ("off", C.c_uint64)]
+
+
 class Context:
     """One CUDA device + resident public parameters (replaces consts.rs:23-68)."""
 
@@ -164,6 +169,28 @@ class Context:
             infp = inf_flags.ctypes.data_as(u8p)
         self._chk(self._lib.halo_msm(self._h, p64(b), infp, p64(s), C.c_uint64(n), p64(out)))
         return out
+
+    def msm_multi(self, problems):
+        """A batch of small independent MSMs with one host round trip (halo_msm_multi).  problems: list of
+        (bases_affine or None, scalars, inf_flags or None, off); None bases = resident generators from `off`."""
+        descs = (_MsmDesc * max(1, len(problems)))()
+        keep = []
+        for d, (b, sc, inf, off) in zip(descs, problems):
+            sc = arr(sc).reshape(-1, 4)
+            keep.append(sc)
+            d.scalars, d.n, d.off = p64(sc), sc.shape[0], off
+            if b is not None:
+                b = arr(b).reshape(-1, 8)
+                assert b.shape[0] == sc.shape[0]
+                keep.append(b)
+                d.bases_affine = p64(b)
+                if inf is not None:
+                    inf = np.ascontiguousarray(inf, dtype=np.uint8)
+                    keep.append(inf)
+                    d.inf_flags = inf.ctypes.data_as(u8p)
+        out = np.zeros((max(1, len(problems)), 12), dtype=np.uint64)
+        self._chk(self._lib.halo_msm_multi(self._h, descs, C.c_uint32(len(problems)), p64(out)))
+        return out[:len(problems)]
 
     def msm_jac(self, bases_jac, scalars):
         b, s = arr(bases_jac).reshape(-1, 12), arr(scalars).reshape(-1, 4)

@@ -773,6 +773,57 @@ int halo_h_msm_with(halo_ctx* ctx, const uint64_t* xis, uint32_t lg_n, const uin
     HALO_CATCH(ctx)
 }
 
+int halo_msm_multi(halo_ctx* ctx, const halo_msm_desc* descs, uint32_t count, uint64_t* out_jac) {
+    if (!ctx || (!descs && count) || (!out_jac && count)) return HALO_EINVAL;
+    size_t bytes = 0;
+    for (uint32_t k = 0; k < count; k++) {
+        const halo_msm_desc& d = descs[k];
+        if (d.n && !d.scalars) return HALO_EINVAL;
+        if (d.n > 4096) return fail(ctx, HALO_EINVAL, "halo_msm_multi: the MSMs of a batch are meant to be small (n <= 4096)");
+        if (!d.bases_affine && d.off + d.n > ctx->n_gens)
+            return fail(ctx, HALO_EINVAL, "halo_msm_multi: range exceeds the resident generators");
+        bytes += d.n * (sizeof(fr_t) + (d.bases_affine ? sizeof(affine_t) + 16 : 0)) + 64;
+    }
+    HALO_TRY(ctx)
+    // one staging area for the whole batch: per MSM  scalars | bases | infinity flags  (16-byte aligned pieces)
+    ctx->stage_misc.reserve(bytes ? bytes : 64);
+    char* cur = ctx->stage_misc.as<char>();
+    auto take = [&](size_t len) {
+        char* p = cur;
+        cur += (len + 15) & ~(size_t)15;
+        return p;
+    };
+    std::vector<MsmInput> ins(count);
+    for (uint32_t k = 0; k < count; k++) {
+        const halo_msm_desc& d = descs[k];
+        if (!d.n) continue;
+        fr_t* d_s = reinterpret_cast<fr_t*>(take(d.n * sizeof(fr_t)));
+        HALO_CUDA(cudaMemcpyAsync(d_s, d.scalars, d.n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        ins[k].scalars = d_s;
+        ins[k].n = (uint32_t)d.n;
+        if (d.bases_affine) {
+            affine_t* d_b = reinterpret_cast<affine_t*>(take(d.n * sizeof(affine_t)));
+            HALO_CUDA(cudaMemcpyAsync(d_b, d.bases_affine, d.n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+            if (d.inf_flags) {
+                uint8_t* d_i = reinterpret_cast<uint8_t*>(take(d.n));
+                HALO_CUDA(cudaMemcpyAsync(d_i, d.inf_flags, d.n, cudaMemcpyHostToDevice, ctx->stream));
+                k_mark_infinity<<<(unsigned)((d.n + 255) / 256), 256, 0, ctx->stream>>>(d_b, d_i, d.n);
+                ctx->kernel_launches++;
+            }
+            ins[k].bases = d_b;
+        } else {
+            ins[k].bases = ctx->gens.as<affine_t>() + d.off;
+        }
+    }
+    for (uint32_t k0 = 0; k0 < count; k0 += 4) {  // msm_batch: up to 4 MSMs on two lanes, one synchronisation
+        const int c = (int)(count - k0 < 4 ? count - k0 : 4);
+        xyzz_t out[4];
+        msm_batch(ctx, ins.data() + k0, c, out);
+        for (int k = 0; k < c; k++) out_jac_from_xyzz(out[k], out_jac + 12 * (k0 + k));
+    }
+    HALO_CATCH(ctx)
+}
+
 // out != NULL: coefficients to the host.  out == NULL: the polynomial stays on the device (ctx->poly_dev) and
 // *degree_out receives its degree (DensePolynomial::degree: index of the highest non-zero coefficient).
 static int h_lincomb_impl(halo_ctx* ctx, const uint64_t* h0, uint64_t n_h0, const uint64_t* alphas, const uint64_t* xis,

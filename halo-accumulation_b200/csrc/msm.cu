@@ -789,9 +789,15 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, cons
     xyzz_t* h_parts = reinterpret_cast<xyzz_t*>(ctx->pinned);
     bool any = false;
     // two MSMs in a batch that are small enough to be latency bound run on two streams with separate workspaces
+    // (a batch of 3 or 4 alternates between the two lanes)
     bool two_lanes = false;
-    if (count == 2 && ctx->stream2 && ins[0].n + ins[0].n_tail > 0 && ins[1].n + ins[1].n_tail > 0 &&
-        ((uint64_t)ins[0].n + ins[1].n <= (1u << 19) || ctx->force_two_lanes) && !ctx->profile) {
+    uint64_t n_sum = 0;
+    int n_live = 0;
+    for (int k = 0; k < count; k++) {
+        n_sum += ins[k].n;
+        n_live += ins[k].n + ins[k].n_tail > 0;
+    }
+    if (count >= 2 && n_live == count && ctx->stream2 && (n_sum <= (1u << 19) || ctx->force_two_lanes) && !ctx->profile) {
         two_lanes = true;
         HALO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));       // inputs produced on the main stream are complete
         HALO_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
@@ -799,7 +805,7 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, cons
     for (int k = 0; k < count; k++) {
         if (ins[k].n + ins[k].n_tail == 0) continue;
         plans[k] = ins[k].fixed_stride ? ctx->pre_plan : msm_make_plan(ins[k].n + ins[k].n_tail, ctx->force_c);
-        const int lane = two_lanes ? k : 0;
+        const int lane = two_lanes ? (k & 1) : 0;
         cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
         msm_enqueue(ctx, ins[k], plans[k], d_parts + k * SLOT, lane);
         const int nwin = plans[k].fixed ? 1 : plans[k].W;

@@ -93,14 +93,42 @@ static CommonOut common_subroutine(halo_ctx* ctx, uint64_t d, const std::vector<
     hs.h_0 = pi_V.h;
     hs.have_h0 = true;
     Us.push_back(pi_V.U);
-    // (3) U_0 == PCDL.Commit(h_0, d, None) (:152-155)
-    ensure(pi_V.U == pcdl::commit(ctx, pi_V.h, d, nullptr), HALO_REJECT_U0, "U_0 != PCDL.Commit_rho0(ck^(1)_PC, h_0; w = bot)");
-    // (4) (:158-170)
-    for (const auto& q : qs) {
-        auto hu = pcdl::succinct_check(ctx, q.C, q.d, q.z, q.v, q.pi);
-        hs.hs.push_back(hu.first);
-        Us.push_back(hu.second);
-        ensure(q.d == d, HALO_REJECT_D, "d_i != d");  // :169
+    // (3) and (4) need m + 1 small MSMs, none of which depends on another's result: one device round trip for all of
+    // them (pcdl::succinct_check_many), the `ensure!`s raised afterwards in the reference's order.  Input that the
+    // reference would panic on goes through the one-by-one path so that the first failure is the reference's.
+    bool batched = false;
+    if (m >= 1 && pi_V.h.size() <= 4096) {
+        try {
+            std::vector<pcdl::Query> queries;
+            for (const auto& q : qs) queries.push_back(pcdl::Query{&q.C, q.d, &q.z, &q.v, &q.pi});
+            PolyView h0(pi_V.h);
+            pcdl::SuccinctMany sm = pcdl::succinct_check_many(ctx, queries, &h0, d);
+            batched = true;
+            // (3) U_0 == PCDL.Commit(h_0, d, None) (:152-155)
+            ensure(pi_V.U == sm.commitment, HALO_REJECT_U0, "U_0 != PCDL.Commit_rho0(ck^(1)_PC, h_0; w = bot)");
+            // (4) (:158-170)
+            for (size_t i = 0; i < m; i++) {
+                ensure(sm.accept[i], HALO_REJECT_SUCCINCT, "C_(log_n) != CM.Commit_Sigma(c || v')");  // pcdl.rs:307-310
+                hs.hs.push_back(sm.hu[i].first);
+                Us.push_back(sm.hu[i].second);
+                ensure(qs[i].d == d, HALO_REJECT_D, "d_i != d");  // :169
+            }
+        } catch (const HaloFailure& e) {
+            if (batched || e.code <= HALO_REJECT_SUCCINCT) throw;  // a decision, already in the reference's order
+            hs.hs.clear();
+            Us.resize(1);
+        }
+    }
+    if (!batched) {
+        // (3) U_0 == PCDL.Commit(h_0, d, None) (:152-155)
+        ensure(pi_V.U == pcdl::commit(ctx, pi_V.h, d, nullptr), HALO_REJECT_U0, "U_0 != PCDL.Commit_rho0(ck^(1)_PC, h_0; w = bot)");
+        // (4) (:158-170)
+        for (const auto& q : qs) {
+            auto hu = pcdl::succinct_check(ctx, q.C, q.d, q.z, q.v, q.pi);
+            hs.hs.push_back(hu.first);
+            Us.push_back(hu.second);
+            ensure(q.d == d, HALO_REJECT_D, "d_i != d");  // :169
+        }
     }
     // (6) alpha = rho_1(hs) (:173)
     Transcript t;

@@ -210,6 +210,35 @@ std::pair<HPoly, PallasPoint> succinct_check(halo_ctx* ctx, const PallasPoint& C
     return {sp.h, sp.U};                                                                        // :313
 }
 
+SuccinctMany succinct_check_many(halo_ctx* ctx, const std::vector<Query>& qs, const PolyView* commit_p, uint64_t commit_d) {
+    std::vector<SuccinctPrep> preps;
+    preps.reserve(qs.size());
+    for (const Query& q : qs) preps.push_back(succinct_prepare(ctx, *q.C, q.d, *q.z, *q.v, *q.pi));
+    std::vector<halo_msm_desc> descs;
+    for (const SuccinctPrep& sp : preps)
+        descs.push_back(halo_msm_desc{reinterpret_cast<const uint64_t*>(sp.aff.data()), sp.inf.data(),
+                                      reinterpret_cast<const uint64_t*>(sp.scalars.data()), sp.aff.size(), 0});
+    if (commit_p) {  // pcdl::commit without hiding: <coeffs, GS[0..)> over the resident generators
+        uint64_t n = commit_d + 1;
+        ensure(is_pow2(n), HALO_EINVAL, "d+1 is not a power of 2");          // pcdl.rs:102
+        ensure(degree(*commit_p) <= commit_d, HALO_EINVAL, "p.degree() > d");  // pcdl.rs:103
+        ensure(n <= halo_num_generators(ctx), HALO_EINVAL, "d > D");          // pcdl.rs:104
+        uint64_t n_coeffs = commit_p->size() < n ? commit_p->size() : n;
+        ensure(n_coeffs <= 4096, HALO_EINVAL, "succinct_check_many: the commitment riding along must be short");
+        descs.push_back(halo_msm_desc{nullptr, nullptr, reinterpret_cast<const uint64_t*>(commit_p->data()), n_coeffs, 0});
+    }
+    std::vector<uint64_t> out(12 * descs.size() + 12);
+    check_rc(ctx, halo_msm_multi(ctx, descs.data(), (uint32_t)descs.size(), out.data()));
+    SuccinctMany r;
+    for (size_t i = 0; i < preps.size(); i++) {
+        PallasPoint lhs = preps[i].C_prime + point_load(&out[12 * i]);
+        r.accept.push_back(xyzz_is_inf(lhs.p));  // :307-310
+        r.hu.emplace_back(preps[i].h, preps[i].U);
+    }
+    if (commit_p) r.commitment = point_load(&out[12 * preps.size()]);
+    return r;
+}
+
 void check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z, const PallasScalar& v,
            const EvalProof& pi) {
     // succinct_check (:332) and comm = pedersen::commit(None, GS[0..d+1], h.get_poly().coeffs) (:338).  The challenges

@@ -37,6 +37,23 @@ EvalProof open_resident(halo_ctx* ctx, uint64_t deg, const PallasPoint& C, uint6
 // pcdl.rs:252-314; throws HaloFailure(HALO_REJECT_SUCCINCT) on reject
 std::pair<HPoly, PallasPoint> succinct_check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z,
                                              const PallasScalar& v, const EvalProof& pi);
+// the succinct checks of several instances (acc.rs:158-170) and one unhidden commitment (acc.rs:153) with a
+// single device round trip (halo_msm_multi).  Nothing is decided here: `accept[i]` is instance i's group equation
+// (pcdl.rs:307-310) and the caller raises the reference's `ensure!`s in the reference's order.  Malformed input throws
+// exactly as succinct_check / commit would, but possibly out of order -- callers fall back to the one-by-one path then.
+struct Query {
+    const PallasPoint* C;
+    uint64_t d;
+    const PallasScalar* z;
+    const PallasScalar* v;
+    const EvalProof* pi;
+};
+struct SuccinctMany {
+    std::vector<std::pair<HPoly, PallasPoint>> hu;  // what succinct_check returns per instance
+    std::vector<bool> accept;
+    PallasPoint commitment;                          // commit(commit_p, commit_d, None) when commit_p != nullptr
+};
+SuccinctMany succinct_check_many(halo_ctx* ctx, const std::vector<Query>& qs, const PolyView* commit_p, uint64_t commit_d);
 // pcdl.rs:323-342
 void check(halo_ctx* ctx, const PallasPoint& C, uint64_t d, const PallasScalar& z, const PallasScalar& v,
            const EvalProof& pi);

@@ -150,6 +150,20 @@ int halo_h_msm(halo_ctx *ctx, const uint64_t *xis /*[lg_n+1][4]*/, uint32_t lg_n
 int halo_h_msm_with(halo_ctx *ctx, const uint64_t *xis /*[lg_n+1][4]*/, uint32_t lg_n, const uint64_t *bases_affine /*[k][8]*/,
                     const uint8_t *inf_flags /*[k] or NULL*/, const uint64_t *scalars /*[k][4]*/, uint64_t k,
                     uint64_t out_h_jac[12], uint64_t out_small_jac[12]);
+/* A batch of small, independent MSMs with ONE host round trip: the accumulation verifier's
+ * common_subroutine (acc.rs:135-188) needs commit(h_0) (acc.rs:153) and, per instance q_i, the 2 lg n + 2 point MSM that
+ * succinct_check's group equation reduces to (pcdl.rs:285-310); none depends on another's result, so they are enqueued
+ * together (alternating between the context's two streams) and synchronised once.  Each result is kept separate: the
+ * reference checks every instance on its own, and so does the caller.
+ * bases_affine == NULL: the resident generators G_off .. G_{off+n-1}.  n <= 4096 per MSM.  out_jac: [count][12]. */
+typedef struct halo_msm_desc {
+    const uint64_t *bases_affine; /* [n][8] Montgomery affine, or NULL */
+    const uint8_t *inf_flags;     /* [n] or NULL (only with bases_affine) */
+    const uint64_t *scalars;      /* [n][4] */
+    uint64_t n;
+    uint64_t off;                 /* first resident generator when bases_affine == NULL */
+} halo_msm_desc;
+int halo_msm_multi(halo_ctx *ctx, const halo_msm_desc *descs, uint32_t count, uint64_t *out_jac /*[count][12]*/);
 /* out = h_0 + sum_{i<m} alphas[i+1] * coeffs(h_i), zero-padded to n = 2^lg_n.
  * Replaces AccumulatedHPolys::get_poly, acc.rs:85-94. */
 int halo_h_lincomb(halo_ctx *ctx, const uint64_t *h0 /*[n_h0][4]*/, uint64_t n_h0, const uint64_t *alphas /*[m+1][4]*/,

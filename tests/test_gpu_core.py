@@ -484,3 +484,38 @@ def test_generator_store_round_trip(halo, ctx, oracle, tmp_path):
         assert e.value.code == -7
     finally:
         ctx.derive_generators(1 << 16)
+
+
+def test_msm_multi_matches_single_calls_and_oracle(halo, ctx, oracle):
+    """halo_msm_multi: a batch of small independent MSMs -- caller-supplied bases with infinity flags and
+    duplicates, resident generators at an offset, an empty problem, more than four problems -- each result equal to the
+    oracle's and to the one-call-per-MSM path."""
+    O = oracle
+    gs = ctx.get_generators(0, 5000)
+    probs, exp = [], []
+    for k, n in enumerate([42, 2, 1, 4096, 0, 33, 3]):
+        sc = O.random_scalars(n, 300 + k) if n else np.zeros((0, 4), dtype=np.uint64)
+        if k % 2 == 0:  # own bases
+            b = gs[100 * k:100 * k + n].copy()
+            inf = np.zeros(n, dtype=np.uint8)
+            if n > 8:
+                b[5] = b[4]
+                inf[7] = 1
+            probs.append((b, sc, inf, 0))
+            exp.append(O.msm_affine(b, sc, inf=inf) if n else None)
+        else:           # resident generators G_off..
+            off = 17 * k
+            probs.append((None, sc, None, off))
+            exp.append(O.msm_affine(gs[off:off + n], sc) if n else None)
+    got = ctx.msm_multi(probs)
+    for (b, sc, inf, off), g, e in zip(probs, got, exp):
+        if e is None:
+            assert O.pt_eq(g, O.pt_from_affine_ints(None))
+            continue
+        assert O.pt_eq(g, e)
+        assert O.pt_eq(g, ctx.msm(b, sc, inf) if b is not None else ctx.msm_gens(sc, off))
+    assert len(ctx.msm_multi([])) == 0
+    with pytest.raises(halo.HaloError):  # not a small MSM
+        ctx.msm_multi([(None, O.random_scalars(4097, 1), None, 0)])
+    with pytest.raises(halo.HaloError):  # beyond the resident generators
+        ctx.msm_multi([(None, O.random_scalars(4, 1), None, ctx.num_generators() - 2)])

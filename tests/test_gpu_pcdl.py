@@ -455,3 +455,53 @@ def test_open_with_pair_tree_in_the_round_msms(env, passes):
     finally:
         ctx.set_tuning("pair_passes", -1)
         ctx.set_tuning("ipa_defer_rounds", -1)
+
+
+def test_verifier_batched_checks_keep_the_reference_order(env):
+    """common_subroutine runs commit(h_0) and every instance's succinct check in one device round trip (SURVEY 8(f).2);
+    the `ensure!`s must still fire in the reference's order (acc.rs:152-170): U_0 first, then per instance the succinct
+    check and d_i == d.  Every decision is compared with the oracle's on the same (corrupted) inputs."""
+    ctx, O, acc = env["ctx"], env["O"], env["acc"]
+    n, d = 64, 63
+    q1, q1o = _random_instance(env, d, 4100)
+    q2, q2o = _random_instance(env, d, 4200)
+    h0, (w, wb), qq = O.random_scalars(2, 4300), O.random_scalars(2, 4310), O.random_scalars(n - 1, 4320)
+    a = acc.prover(ctx, d, [q1, q2], h0, w, qq, wb)
+    ao = O.acc_prover(d, [q1o, q2o], h0, w, qq, wb, threads=8)
+    _same_proof(O, a.pi, ao.pi)
+    acc.verifier(ctx, d, [q1, q2], a)
+
+    def both(qs, qso, accum):
+        code_o = O.acc_verifier(d, qso, O.Accumulator.from_buffer_copy(bytes(accum)))
+        with pytest.raises(acc.Rejected) as e:
+            acc.verifier(ctx, d, qs, accum)
+        assert e.value.code == code_o, (e.value.code, code_o)
+        return code_o
+
+    def corrupt(q, qo):  # second instance with a wrong evaluation proof scalar
+        b, bo = type(q).from_buffer_copy(bytes(q)), type(qo).from_buffer_copy(bytes(qo))
+        b.pi.c[0] ^= 1
+        bo.pi.c[0] ^= 1
+        return b, bo
+
+    q2b, q2bo = corrupt(q2, q2o)
+    assert both([q1, q2b], [q1o, q2bo], a) == -10          # succinct check of instance 2
+    q1b, q1bo = corrupt(q1, q1o)
+    assert both([q1b, q2b], [q1bo, q2bo], a) == -10        # ... of instance 1 (both wrong)
+    badU = type(a).from_buffer_copy(bytes(a))
+    badU.h0[0][0] ^= 1
+    assert both([q1, q2b], [q1o, q2bo], badU) == -12       # U_0 is checked before any instance
+    # d_i != d: an instance of another size is succinct-checked at ITS size first (accepted), then refused
+    q3, q3o = _random_instance(env, 31, 4400)
+    assert both([q1, q3], [q1o, q3o], a) == -13
+    q3b, q3bo = corrupt(q3, q3o)
+    assert both([q1, q3b], [q1o, q3bo], a) == -10          # its succinct check comes before the d comparison
+    # malformed input (the reference panics): falls back to the one-by-one path and reports an error, not a decision
+    q4 = type(q1).from_buffer_copy(bytes(q1))
+    q4.pi.lg_n = 5
+    from halo_accumulation_b200 import HaloError
+
+    with pytest.raises(HaloError) as e:
+        acc.verifier(ctx, d, [q4, q2], a)
+    assert e.value.code == -1
+    acc.verifier(ctx, d, [q1, q2], a)                      # the context is still usable
