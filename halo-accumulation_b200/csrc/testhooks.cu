@@ -89,9 +89,11 @@ __global__ void __launch_bounds__(256) k_gather_tp(const uint4* __restrict__ tab
 // Cooperative variant: 4 adjacent lanes fetch one 64-byte slot with ONE instruction (16 bytes each), so both 32-byte
 // sectors of the slot are requested together; 8 slots per warp-instruction.  gathers = blocks * threads * iters / 4 * 4
 // (each lane still walks `iters` slots, shared with its 3 neighbours: count blocks * threads / 4 * iters).
+// LANES = 2: two adjacent lanes fetch one 32-byte slot (an x coordinate alone), 16 slots per warp-instruction.
+template <int LANES>
 __global__ void __launch_bounds__(256) k_gather_coop_tp(const uint4* __restrict__ table, uint64_t slots, int iters, uint32_t* sink) {
-    const unsigned lane = threadIdx.x & 31u, sub = lane & 3u;
-    uint64_t x = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2) * 0x9e3779b97f4a7c15ull + 0x1234567ull;  // same for the 4 lanes
+    const unsigned lane = threadIdx.x & 31u, sub = lane & (LANES - 1u);
+    uint64_t x = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES) * 0x9e3779b97f4a7c15ull + 0x1234567ull;  // same for the lanes of a group
     uint4 acc = make_uint4(0, 0, 0, 0);
     for (int i = 0; i < iters; i += 4) {
         const uint4* p[4];
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(256) k_gather_coop_tp(const uint4* __restrict_
             x ^= x << 13;
             x ^= x >> 7;
             x ^= x << 17;
-            p[k] = table + __umul64hi(x, slots) * 4 + sub;
+            p[k] = table + __umul64hi(x, slots) * LANES + sub;
         }
         uint4 v[4];
 #pragma unroll
@@ -342,8 +344,10 @@ int halo_test_gather_throughput(halo_ctx* ctx, uint64_t table_bytes, int blocks,
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
         HALO_CUDA(cudaEventRecord(e0, ctx->stream));
-        if (bytes < 0)
-            k_gather_coop_tp<<<blocks, threads, 0, ctx->stream>>>(table.as<uint4>(), table_bytes / 64, iters, sink.as<uint32_t>());
+        if (bytes == -32)
+            k_gather_coop_tp<2><<<blocks, threads, 0, ctx->stream>>>(table.as<uint4>(), table_bytes / 32, iters, sink.as<uint32_t>());
+        else if (bytes < 0)
+            k_gather_coop_tp<4><<<blocks, threads, 0, ctx->stream>>>(table.as<uint4>(), table_bytes / 64, iters, sink.as<uint32_t>());
         else
             k_gather_tp<<<blocks, threads, 0, ctx->stream>>>(table.as<uint4>(), table_bytes / 64, iters, bytes, sink.as<uint32_t>());
         HALO_CUDA(cudaEventRecord(e1, ctx->stream));

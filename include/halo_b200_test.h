@@ -29,7 +29,8 @@ int halo_test_imad_throughput(halo_ctx *ctx, int kind, int blocks, int threads, 
 int halo_test_check_canaries(int *live_buffers);
 /* Random-gather ceiling of HBM: blocks * threads threads each read `iters` pseudo-random 64-byte-aligned slots (16, 32 or
  * 64 bytes of each; bytes = -64: four adjacent lanes fetch one 64-byte slot with one instruction, blocks * threads / 4 *
- * iters gathers) of a table of `table_bytes` bytes; ms = best of 2 timed launches.  The denominator for the first
+ * iters gathers; bytes = -32: two adjacent lanes fetch one 32-byte slot, blocks * threads / 2 * iters gathers) of a table of
+ * `table_bytes` bytes; ms = best of 2 timed launches.  The denominator for the first
  * pair-tree pass and for the gathers of k_accumulate. */
 int halo_test_gather_throughput(halo_ctx *ctx, uint64_t table_bytes, int blocks, int threads, int iters, int bytes, float *ms);
 /* Times one HBM-bound Fr vector kernel on synthetic device-resident data (ms, best of 5): kind 0 = the c / z folds of
