@@ -32,7 +32,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "pallas_msm_points_per_s"
+CURVE = os.environ.get("HALO_B200_CURVE", "pallas")  # "vesta": the other half of the cycle, same kernels
+METRIC = f"{CURVE}_msm_points_per_s"
 UNIT = "points/s"
 IMAD_PER_MODMUL = 136  # 2 N^2 + N for N = 8 limbs
 CANON_W = 16           # canonical c = 16 -> 16 windows x 10 modmul per point in the bucket accumulation
@@ -124,7 +125,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": f"pallas_msm_2^{args.log_n}_per_gpu", "sample": sample},
+        "config": {"workload": f"{CURVE}_msm_2^{args.log_n}_per_gpu", "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -277,7 +278,7 @@ def run_ours(args):
         traffic = None  # dram__bytes_read + dram__bytes_write of one k_accumulate launch, from the committed ncu capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["accumulate_phase_pair_tree"]
-            if tj["workload"] == f"pallas_msm_2^{args.log_n}_per_gpu" and tj["fixed_base_tables"] == (not args.no_precompute):
+            if tj["workload"] == f"{CURVE}_msm_2^{args.log_n}_per_gpu" and tj["fixed_base_tables"] == (not args.no_precompute):
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
             pass
@@ -294,7 +295,7 @@ def run_ours(args):
             "metric": METRIC, "value": total_points / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
-            "config": {"workload": f"pallas_msm_2^{args.log_n}_per_gpu", "points_per_gpu": n, "total_points": total_points,
+            "config": {"workload": f"{CURVE}_msm_2^{args.log_n}_per_gpu", "points_per_gpu": n, "total_points": total_points,
                        "bases": "derived generators G_i (main.rs:18-45 rule), resident", "scalars": "uniform 254-bit, seeded",
                        "parallelism": f"point-slice x{world}, one all-gather of {world} x 96 B per step" if world > 1 else "single GPU",
                        "l2": "inputs_exceed_l2 (>= 1.5 GiB streamed per step)", "window_c": "auto",
