@@ -172,8 +172,72 @@ HALO_HD void fp_reduce_once(uint32_t x[8]) {
     for (int i = 0; i < 8; i++) x[i] = borrow ? x[i] : t[i];
 }
 
+#if !defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+// Host path (little-endian x86-64 / aarch64): the same bytes seen as 4 x u64.  The host glue of the hot path is a few
+// hundred point operations per call (transcript points, C', the Horner finish of every variable-base MSM: ~255
+// doublings); with 32-bit-limb loops a scalar multiplication on the host cost 0.3 ms.
+namespace host64 {
+typedef unsigned __int128 u128;
+template <class P>
+struct Mod {
+    static constexpr uint64_t p0 = 1ull | ((uint64_t)P::P1 << 32), p1 = (uint64_t)P::P2 | ((uint64_t)P::P3 << 32), p2 = 0,
+                              p3 = 0x4000000000000000ull;
+};
+inline void load(uint64_t o[4], const uint32_t v[8]) { __builtin_memcpy(o, v, 32); }
+inline void store(uint32_t v[8], const uint64_t o[4]) { __builtin_memcpy(v, o, 32); }
+inline uint64_t add4(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {
+    u128 c = (u128)a[0] + b[0];
+    r[0] = (uint64_t)c;
+    c = (c >> 64) + a[1] + b[1];
+    r[1] = (uint64_t)c;
+    c = (c >> 64) + a[2] + b[2];
+    r[2] = (uint64_t)c;
+    c = (c >> 64) + a[3] + b[3];
+    r[3] = (uint64_t)c;
+    return (uint64_t)(c >> 64);
+}
+inline uint64_t sub4(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {  // returns the borrow (0 / 1)
+    u128 d = (u128)a[0] - b[0];
+    r[0] = (uint64_t)d;
+    d = (u128)a[1] - b[1] - (uint64_t)((d >> 64) & 1);
+    r[1] = (uint64_t)d;
+    d = (u128)a[2] - b[2] - (uint64_t)((d >> 64) & 1);
+    r[2] = (uint64_t)d;
+    d = (u128)a[3] - b[3] - (uint64_t)((d >> 64) & 1);
+    r[3] = (uint64_t)d;
+    return (uint64_t)((d >> 64) & 1);
+}
+template <class P>
+inline void add(uint32_t r[8], const uint32_t a32[8], const uint32_t b32[8]) {
+    uint64_t a[4], b[4], s[4], d[4];
+    const uint64_t p[4] = {Mod<P>::p0, Mod<P>::p1, Mod<P>::p2, Mod<P>::p3};
+    load(a, a32);
+    load(b, b32);
+    add4(s, a, b);  // a, b < p < 2^255: no carry out
+    const uint64_t borrow = sub4(d, s, p);
+    for (int i = 0; i < 4; i++) s[i] = borrow ? s[i] : d[i];
+    store(r, s);
+}
+template <class P>
+inline void sub(uint32_t r[8], const uint32_t a32[8], const uint32_t b32[8]) {
+    uint64_t a[4], b[4], d[4], t[4];
+    const uint64_t p[4] = {Mod<P>::p0, Mod<P>::p1, Mod<P>::p2, Mod<P>::p3};
+    load(a, a32);
+    load(b, b32);
+    const uint64_t borrow = sub4(d, a, b);
+    add4(t, d, p);
+    for (int i = 0; i < 4; i++) d[i] = borrow ? t[i] : d[i];
+    store(r, d);
+}
+}  // namespace host64
+#endif
+
 template <class P>
 HALO_HD void fp_add(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
+#if !defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+    host64::add<P>(r.v, a.v, b.v);
+    return;
+#endif
     uint32_t s[8];
     add8(s, a.v, b.v);  // a, b < p < 2^255: no carry out
     fp_reduce_once<P>(s);
@@ -182,6 +246,10 @@ HALO_HD void fp_add(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
 }
 template <class P>
 HALO_HD void fp_sub(fp_t<P>& r, const fp_t<P>& a, const fp_t<P>& b) {
+#if !defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
+    host64::sub<P>(r.v, a.v, b.v);
+    return;
+#endif
     uint32_t d[8], m[8], t[8];
     uint32_t borrow = sub8(d, a.v, b.v);
     fp_mod_limbs<P>(m);
@@ -284,52 +352,52 @@ HALO_HD void mul8x8(uint32_t T[16], const uint32_t a[8], const uint32_t b[8]) {
 }
 
 #if !defined(__CUDA_ARCH__) && !defined(HALO_FP_FORCE_PORTABLE)
-// Host path (transcript glue, the O(255)-doubling Horner finish of an MSM): 4 x u64 CIOS on the same bytes.
+// Host path (transcript glue, the O(255)-doubling Horner finish of an MSM): 4 x u64 CIOS on the same bytes, unrolled, with the
+// shape of the modulus folded in (limb 2 is zero, limb 3 is 2^62: that product is a shift).
 template <class P>
 inline void fp_mul_host64(uint32_t r32[8], const uint32_t a32[8], const uint32_t b32[8]) {
-    typedef unsigned __int128 u128;
-    uint64_t a[4], b[4], p[4], t[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < 4; i++) {
-        a[i] = (uint64_t)a32[2 * i] | ((uint64_t)a32[2 * i + 1] << 32);
-        b[i] = (uint64_t)b32[2 * i] | ((uint64_t)b32[2 * i + 1] << 32);
-        p[i] = (uint64_t)fp_mod<P>(2 * i) | ((uint64_t)fp_mod<P>(2 * i + 1) << 32);
+    using host64::u128;
+    typedef host64::Mod<P> M;
+    uint64_t a[4], b[4];
+    host64::load(a, a32);
+    host64::load(b, b32);
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+#define HALO_H64_ROUND(bi)                                  \
+    {                                                       \
+        u128 c = (u128)a[0] * (bi) + t0;                    \
+        t0 = (uint64_t)c;                                   \
+        c = (c >> 64) + (u128)a[1] * (bi) + t1;             \
+        t1 = (uint64_t)c;                                   \
+        c = (c >> 64) + (u128)a[2] * (bi) + t2;             \
+        t2 = (uint64_t)c;                                   \
+        c = (c >> 64) + (u128)a[3] * (bi) + t3;             \
+        t3 = (uint64_t)c;                                   \
+        c = (c >> 64) + t4;                                 \
+        t4 = (uint64_t)c;                                   \
+        const uint64_t t5 = (uint64_t)(c >> 64);            \
+        const uint64_t m = t0 * P::INV64;                   \
+        c = (u128)m * M::p0 + t0;                           \
+        c = (c >> 64) + (u128)m * M::p1 + t1;               \
+        t0 = (uint64_t)c;                                   \
+        c = (c >> 64) + t2;                                 \
+        t1 = (uint64_t)c;                                   \
+        c = (c >> 64) + ((u128)m << 62) + t3;               \
+        t2 = (uint64_t)c;                                   \
+        c = (c >> 64) + t4;                                 \
+        t3 = (uint64_t)c;                                   \
+        t4 = t5 + (uint64_t)(c >> 64);                      \
     }
-    for (int i = 0; i < 4; i++) {
-        u128 c = 0;
-        for (int j = 0; j < 4; j++) {
-            c += (u128)a[j] * b[i] + t[j];
-            t[j] = (uint64_t)c;
-            c >>= 64;
-        }
-        c += t[4];
-        t[4] = (uint64_t)c;
-        t[5] = (uint64_t)(c >> 64);
-        uint64_t m = t[0] * P::INV64;
-        c = (u128)m * p[0] + t[0];
-        c >>= 64;
-        for (int j = 1; j < 4; j++) {
-            c += (u128)m * p[j] + t[j];
-            t[j - 1] = (uint64_t)c;
-            c >>= 64;
-        }
-        c += t[4];
-        t[3] = (uint64_t)c;
-        t[4] = t[5] + (uint64_t)(c >> 64);
-    }
-    // conditional subtraction
+    HALO_H64_ROUND(b[0])
+    HALO_H64_ROUND(b[1])
+    HALO_H64_ROUND(b[2])
+    HALO_H64_ROUND(b[3])
+#undef HALO_H64_ROUND
+    const uint64_t t[4] = {t0, t1, t2, t3}, p[4] = {M::p0, M::p1, M::p2, M::p3};
     uint64_t d[4];
-    u128 br = 0;
-    for (int i = 0; i < 4; i++) {
-        u128 x = (u128)t[i] - p[i] - br;
-        d[i] = (uint64_t)x;
-        br = (x >> 64) & 1;
-    }
-    bool ge = t[4] != 0 || br == 0;
-    for (int i = 0; i < 4; i++) {
-        uint64_t o = ge ? d[i] : t[i];
-        r32[2 * i] = (uint32_t)o;
-        r32[2 * i + 1] = (uint32_t)(o >> 32);
-    }
+    const uint64_t borrow = host64::sub4(d, t, p);
+    const bool ge = t4 != 0 || borrow == 0;
+    for (int i = 0; i < 4; i++) d[i] = ge ? d[i] : t[i];
+    host64::store(r32, d);
 }
 #endif
 
