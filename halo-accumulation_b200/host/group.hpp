@@ -13,6 +13,7 @@
 
 #include "../../include/halo_b200.h"
 #include "../csrc/ec.cuh"
+#include "../csrc/glv.cuh"
 #include "../csrc/sha3.cuh"
 
 namespace halo {
@@ -75,10 +76,8 @@ inline PallasPoint operator-(const PallasPoint& a) { PallasPoint r = a; if (!xyz
 inline PallasPoint operator-(const PallasPoint& a, const PallasPoint& b) { return a + (-b); }
 // `Projective * Fr`
 inline PallasPoint operator*(const PallasPoint& a, const PallasScalar& k) {
-    uint32_t kc[8];
-    fp_to_canon(kc, k);
     PallasPoint r;
-    xyzz_mul_canon(r.p, a.p, kc);
+    xyzz_mul_glv(r.p, a.p, k);  // GLV + joint sparse form (csrc/glv.cuh): half the doublings and additions of double-and-add
     return r;
 }
 // Projective equality (representation independent)

@@ -1,4 +1,4 @@
-"""Derives the GLV constants of csrc/ipa.cu (namespace glv, c_beta_mont) for a Pasta curve.
+"""Derives the GLV constants of csrc/glv.cuh (namespace glv, HALO_GLV_BETA_MONT) for a Pasta curve.
 
 Both curves are y^2 = x^3 + 5 with generator (-1, 2) and j-invariant 0: the base field holds a primitive cube root of
 unity beta, the scalar field the matching lambda with lambda * (x, y) = (beta x, y).  The lattice
@@ -129,7 +129,7 @@ def main():
                 assert c["A2"] == 0x93CD3A2C8198E2690C7C095A00000001
                 assert limbs(c["G1"], 5).startswith("{0x4a95a2d972171db4ull, 0x61afdea68480fa55ull")
                 assert limbs(c["G2"], 5).startswith("{0xc689c5879f98a4deull, 0x61afdea683e7688aull")
-                print("# matches csrc/ipa.cu (Pallas)")
+                print("# matches csrc/glv.cuh (Pallas)")
 
 
 if __name__ == "__main__":

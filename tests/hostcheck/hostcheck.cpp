@@ -3,6 +3,7 @@
 // Test-only; never shipped, never linked into libhalo_b200.so.
 #include <cstring>
 #include "../../halo-accumulation_b200/csrc/ec.cuh"
+#include "../../halo-accumulation_b200/csrc/glv.cuh"
 using namespace halo;
 extern "C" {
 void hc_fp_mul(int which, const uint32_t* a, const uint32_t* b, uint32_t* r) {
@@ -36,6 +37,11 @@ void hc_add_chain(const uint32_t* jac, uint64_t n, int dbls, uint32_t* out_jac) 
 }
 void hc_to_affine(const uint32_t* jac, uint32_t* aff) {
     jac_t p; memcpy(&p, jac, 96); xyzz_t q; jac_to_xyzz(q, p); affine_t a; xyzz_to_affine(a, q); memcpy(aff, &a, 64);
+}
+// `Projective * Fr` of the host layer: GLV split + joint sparse form (csrc/glv.cuh); k is a Montgomery scalar
+void hc_mul_glv(const uint32_t* jac, const uint32_t* k_mont, uint32_t* out_jac) {
+    jac_t p; memcpy(&p, jac, 96); xyzz_t q, r; jac_to_xyzz(q, p); fr_t k; memcpy(&k, k_mont, 32); xyzz_mul_glv(r, q, k);
+    jac_t j; xyzz_to_jac(j, r); memcpy(out_jac, &j, 96);
 }
 void hc_mul(const uint32_t* jac, const uint32_t* k_canon, uint32_t* out_jac) {
     jac_t p; memcpy(&p, jac, 96); xyzz_t q, r; jac_to_xyzz(q, p); xyzz_mul_canon(r, q, k_canon);

@@ -149,6 +149,20 @@ def test_shared_group_law_vs_oracle(hostcheck, oracle, tag):
     O.lib().orc_fp_to_canon(1, O._p(k), O._p(kc))
     hc.hc_mul(_p32(jacs[2]), _p32(kc), _p32(out))
     assert O.pt_eq(out, O.pt_mul(jacs[2], k))
+    # `Projective * Fr` of the host layer (GLV + joint sparse form, csrc/glv.cuh) against the oracle's double-and-add:
+    # edge scalars (0, +-1, +-lambda-sized, powers of two around the 128-bit split), random scalars, infinity, a
+    # non-normalised point
+    rnd = random.Random(41)
+    ks = [0, 1, 2, 3, PR.R - 1, PR.R - 2, (1 << 127), (1 << 128) - 1, 1 << 128, (1 << 128) + 1, (1 << 254), PR.R // 2, PR.R // 3]
+    ks += [rnd.randrange(PR.R) for _ in range(60)]
+    pts = [jacs[3], O.affine_to_jac(GS[0])[0], O.pt_from_affine_ints(None)]
+    for i, kv in enumerate(ks):
+        km = O.to_mont([kv])[0]
+        pj = pts[i % 3] if i >= 13 else pts[0]
+        hc.hc_mul_glv(_p32(np.ascontiguousarray(pj)), _p32(km), _p32(out))
+        assert O.pt_eq(out, O.pt_mul(pj, km)), hex(kv)
+    hc.hc_mul_glv(_p32(np.ascontiguousarray(pts[2])), _p32(O.to_mont([5])[0]), _p32(out))
+    assert O.pt_to_affine_ints(out) is None
 
 
 def test_host_transcript_serialisation_vs_oracle(libs, oracle):

@@ -37,11 +37,11 @@ def test_vesta_cpu_suite():
 
 
 def test_glv_constants_are_derived():
-    """tools/gen_glv_consts.py reproduces the Pallas constants of csrc/ipa.cu and its Vesta output is what ipa.cu carries."""
+    """tools/gen_glv_consts.py reproduces the Pallas constants of csrc/glv.cuh and its Vesta output is what glv.cuh carries."""
     tool = os.path.join(ROOT, "halo-accumulation_b200", "tools", "gen_glv_consts.py")
-    src = open(os.path.join(ROOT, "halo-accumulation_b200", "csrc", "ipa.cu")).read().replace(" ", "")
+    src = open(os.path.join(ROOT, "halo-accumulation_b200", "csrc", "glv.cuh")).read().replace(" ", "")
     out = subprocess.run([sys.executable, tool, "pallas"], capture_output=True, text=True, check=True).stdout
-    assert "# matches csrc/ipa.cu (Pallas)" in out
+    assert "# matches csrc/glv.cuh (Pallas)" in out
     out = subprocess.run([sys.executable, tool, "vesta"], capture_output=True, text=True, check=True).stdout
     lines = [l for l in out.splitlines() if "=" in l and not l.startswith("#")]
     assert len(lines) == 6
