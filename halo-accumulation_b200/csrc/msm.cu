@@ -836,19 +836,26 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, cons
         else
             msm_finish_host(h_parts + k * SLOT, plans[k], outs[k]);
     };
-    if (count == 2 && ins[0].n + ins[0].n_tail > 0 && ins[1].n + ins[1].n_tail > 0 && !plans[0].fixed && !plans[1].fixed) {
-        bool spawned = false;
-        std::thread other;
-        try {
-            other = std::thread(finish, 1);
-            spawned = true;
-        } catch (const std::system_error&) {  // no thread available: finish both here (nothing may unwind across the ABI)
+    // (the results of an IPA round, L and R, and the up to four small MSMs of a verifier batch: one host thread each)
+    int heavy = 0;
+    for (int k = 0; k < count; k++) heavy += ins[k].n + ins[k].n_tail > 0 && !plans[k].fixed;
+    if (count >= 2 && heavy == count) {
+        std::thread others[MAXB];
+        bool spawned[MAXB] = {false, false, false, false};
+        for (int k = 1; k < count; k++) {
+            try {
+                others[k] = std::thread(finish, k);
+                spawned[k] = true;
+            } catch (const std::system_error&) {  // no thread available: finished below (nothing may unwind across the ABI)
+            }
         }
         finish(0);
-        if (spawned)
-            other.join();
-        else
-            finish(1);
+        for (int k = 1; k < count; k++) {
+            if (spawned[k])
+                others[k].join();
+            else
+                finish(k);
+        }
     } else {
         for (int k = 0; k < count; k++) finish(k);
     }
