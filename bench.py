@@ -314,7 +314,7 @@ def run_ours(args):
             "e2e": {"value": total_points / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "api": "halo_msm_gens_submit / halo_msm_gens_collect (pinned host scalars, two steps in flight)",
                     "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 3 * 128, "result_matches_resident": same,
-                    "blocking_call": {"api": "halo_msm_gens (one call; internally two point slices through the pipeline slots for n >= 2^23)", "value": total_points / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms}},
+                    "blocking_call": {"api": "halo_msm_gens (one call; internally two point slices, 5/16 and 11/16, through the pipeline slots for n >= 2^23)", "value": total_points / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "imad", "kernel": "bucket accumulation phase: k_pair_fwd / k_pair_bwd x 4 tree passes (affine, batched inversion) + k_accumulate (XYZZ tail)", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD32/s",

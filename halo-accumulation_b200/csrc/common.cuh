@@ -168,7 +168,9 @@ struct halo_ctx {
     int tune_ipa_frozen_c = 10;  // window of the frozen-tail MSMs (8192 points, latency bound in the bucket reduction): 0.78 -> 0.71 ms per round vs c = 12
     int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
     int tune_sort_ahead = 1;  // pipelined submit: CTAs per SM of the counting sort running beside the previous MSM (0: off)
-    int tune_split_blocking = 23;  // halo_msm_gens: two half-size MSMs through the pipeline slots for n >= 2^this (0: never)
+    int tune_split_blocking = 23;  // halo_msm_gens: two point slices through the pipeline slots for n >= 2^this (0: never)
+    int tune_split_first_16ths = 5;  // size of the first slice in sixteenths of n: its H2D copy is exposed, the second slice's copy hides behind
+                                     // the first slice's kernels (2^24: 8 -> 41.1 ms, 6 -> 38.4, 5 -> 38.2, 4 -> 39.7, 3 -> 41.0; scripts/gpu_split_probe.py)
     int tune_pair_passes = -1;  // -1: automatic; 0: XYZZ accumulation only; P > 0: force P pair-tree passes
     uint64_t kernel_launches = 0;
     halo::Timings last;

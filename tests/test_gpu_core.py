@@ -297,10 +297,13 @@ def test_msm_pipelined_submit_collect(ctx, oracle):
     # the first); forced here at a small size, odd length
     ctx.set_tuning("split_blocking", 10)
     try:
-        assert O.pt_eq(ctx.msm_gens(scs[0]), exp[0])
-        assert O.pt_eq(ctx.msm_gens(scs[1][:n - 3], off=3), O.msm_affine(gs[3:n], scs[1][:n - 3], threads=8))
+        for first in (5, 1, 8, 15):  # size of the first slice in sixteenths (5 is the default)
+            ctx.set_tuning("split_first_16ths", first)
+            assert O.pt_eq(ctx.msm_gens(scs[0]), exp[0])
+            assert O.pt_eq(ctx.msm_gens(scs[1][:n - 3], off=3), O.msm_affine(gs[3:n], scs[1][:n - 3], threads=8))
     finally:
         ctx.set_tuning("split_blocking", 23)
+        ctx.set_tuning("split_first_16ths", 5)
     # a third submit without collecting is refused, not queued silently
     import halo_accumulation_b200 as H
     t0, t1 = ctx.msm_gens_submit(scs[0]), ctx.msm_gens_submit(scs[1])
