@@ -317,7 +317,7 @@ def run_ours(args):
                     "blocking_call": {"api": "halo_msm_gens (one call; internally two point slices, 5/16 and 11/16, through the pipeline slots for n >= 2^23)", "value": total_points / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms}},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "imad", "kernel": "bucket accumulation phase: k_pair_fwd / k_pair_bwd x 4 tree passes (affine, batched inversion) + k_accumulate (XYZZ tail)", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD32/s",
+            "roofline": {"bound": "imad", "bound_note": "integer pipe (IMAD32 issue rate): the path is big-integer arithmetic, neither HBM nor tensor bound; BASELINE.json's north_star asks for the fraction of the integer-pipe roofline", "kernel": "bucket accumulation phase: k_pair_fwd / k_pair_bwd x 4 tree passes (affine, batched inversion) + k_accumulate (XYZZ tail)", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD32/s",
                          "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "DRAM bytes of the phase per MSM (ncu, profiles/r01_traffic.json); pass 0 of the tree (19 of 33 ms) is HBM bound on 128-byte random accesses at 3.6-4.0 TB/s, the rest integer-pipe bound",
                          "hbm_gbs_phase": (traffic / (phases["accumulate"] * 1e-3) / 1e9) if traffic else None,
                          "peak_source": "measured in this run (libhalo_b200 mad.lo.u32 microbenchmark, 16 independent chains per thread, all SMs); MEASURED_PEAKS.json has no integer-pipe figure. IMAD.WIDE / IMAD.HI issue at half this rate (profiles/r01_imad_pipe_rates.jsonl)",
