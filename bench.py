@@ -6,18 +6,26 @@
 
 A "step" is one MSM  sum_i s_i * G_i  over n = 2^L points per GPU (default 2^24, the size the metric is quoted on;
 1 GiB of affine bases + 512 MiB of scalars per GPU, so every step streams inputs far larger than the 126 MB L2).
-With N > 1 the MSM is sharded by point slice (weak scaling: every rank holds its own 2^L-point slice of an
-N * 2^L-point MSM) and the partial results are combined with one all-gather per step.
+With N > 1 the MSM is sharded by point slice behind the C ABI (halo_comm_*, csrc/comm.cu: every rank holds its own
+2^L-point slice of an N * 2^L-point MSM -- weak scaling -- and the ranks' partials meet in one ncclAllGather on the
+library's stream).
 
-`value`     : points/s, inputs resident in HBM, CUDA events on the library's stream, max over ranks; two steps in flight
-              (submit / collect over device-resident scalars), the strictly sequential figure is `sequential_calls`.
-`e2e`       : same metric through the C ABI call halo_msm_gens with HOST (pinned) scalars: H2D of the step's scalars
-              and D2H of the window sums inside the timed region.
-`roofline`  : integer pipe (IMAD) for the dominant phase, the bucket accumulation (pair-tree passes k_pair_fwd / k_pair_bwd
-              and the XYZZ tail k_accumulate); peak measured in-run by the library's IMAD microbenchmark
-              (MEASURED_PEAKS.json carries no integer figure).
-`cpu_baseline` / `--impl reference`: the reference's arkworks algorithm restated in C (oracle/), timed on the host
-              cores on a bounded sample of the same workload.  The reference itself is Rust and cannot run here.
+`value`       points/s, inputs resident in HBM, CUDA events on the library's stream, max over ranks; two steps in flight
+              (submit / collect over device-resident scalars); the strictly sequential figure is `sequential_calls`.
+`e2e`         same metric through the C ABI with HOST scalars: H2D of the step's scalars and D2H of the partials inside
+              the timed region.  Pipelined from pinned memory (`value`), the blocking drop-in call from pinned memory
+              (`blocking_call`) and from PAGEABLE memory (`blocking_call_pageable`: what a Rust Vec<Fr> is).
+`variable_base` the same MSM without the precomputed multiples of the generators (the path of point_dot / IPA rounds).
+`roofline`    integer pipe (IMAD) for the dominant phase, the bucket accumulation; peak measured in-run by the library's
+              IMAD microbenchmark (MEASURED_PEAKS.json carries no integer figure).  `frac` uses SURVEY 8(d)'s canonical
+              accounting (c = 16: 16 windows x 10 modmul per point); `executed` restates it with the multiplications the
+              kernels actually issue.
+`strong_scaling` ONE MSM of 2^16 .. 2^24 points sharded over the N GPUs (BASELINE config 5), ms / points/s / fraction of
+              the N-GPU integer roofline per size, each result checked against the oracle.
+`oracle_match` the timed result equals the CPU oracle's (N = 1: its arkworks-shaped Pippenger at the same 2^24 size -- the
+              same run is the `cpu_baseline` -- and the discrete-log property; N > 1: the discrete-log property per slice).
+`cpu_baseline` / `--impl reference`: the reference's arkworks algorithm restated in C (oracle/), timed on the host cores at
+              the SAME size (one 2^24-point MSM per step).  The reference itself is Rust and cannot run here.
 """
 import argparse
 import json
@@ -37,6 +45,7 @@ METRIC = f"{CURVE}_msm_points_per_s"
 UNIT = "points/s"
 IMAD_PER_MODMUL = 136  # 2 N^2 + N for N = 8 limbs
 CANON_W = 16           # canonical c = 16 -> 16 windows x 10 modmul per point in the bucket accumulation
+SCALAR_SEED = 4
 
 
 def dist_env():
@@ -44,6 +53,21 @@ def dist_env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return rank, world, local
+
+
+def make_config(log_n, world):
+    """The workload, identical for both arms (`--impl ours` and `--impl reference`)."""
+    n = 1 << log_n
+    return {"workload": f"{CURVE}_msm_2^{log_n}_per_gpu", "points_per_gpu": n, "total_points": n * world,
+            "bases": "derived generators G_i (main.rs:18-45 rule)", "scalars": f"uniform 254-bit, numpy PCG64 seed {SCALAR_SEED} + rank",
+            "parallelism": f"point-slice x{world}, one all-gather per MSM" if world > 1 else "single GPU",
+            "l2": "inputs_exceed_l2 (>= 1.5 GiB streamed per step)"}
+
+
+def bench_scalars(n, rank):
+    from oracle import oracle as O  # only the seeded generator of the test inputs (numpy), no arithmetic
+
+    return O.random_scalars(n, SCALAR_SEED + rank)
 
 
 class ClockSampler(threading.Thread):
@@ -90,54 +114,41 @@ def host_threads():
     return n
 
 
-def cpu_msm_baseline(log_n_sample, threads, seed=4):
-    """The reference's CPU path (arkworks-shaped Pippenger restated in oracle/halo_oracle.c) on a bounded sample."""
-    from oracle import oracle as O
-
-    n = 1 << log_n_sample
-    bases = O.derive_points(2, n)
-    scalars = O.random_scalars(n, seed)
-    t = time.perf_counter()
-    O.msm_affine(bases, scalars, threads=threads)
-    dt = time.perf_counter() - t
-    reps = max(1, min(16, int(round(10.0 / dt))))  # ~10 s of wall clock in total, fresh scalars per repetition
-    total = dt
-    for r in range(1, reps):
-        scalars = O.random_scalars(n, seed + r)
-        t = time.perf_counter()
-        O.msm_affine(bases, scalars, threads=threads)
-        total += time.perf_counter() - t
-    return n * reps / total, total, reps
-
-
 def run_reference(args):
+    """The reference's CPU path (arkworks-shaped Pippenger restated in oracle/halo_oracle.c) on the SAME workload: one MSM of
+    2^log_n derived generators x seeded scalars per step, all host threads (windows x point chunks)."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
     threads = host_threads()
     from oracle import oracle as O
 
-    n = 1 << args.cpu_log_n
-    bases = O.derive_points(2, n)
-    scalars = O.random_scalars(n, 4)
+    n = 1 << args.log_n
+    t0 = time.perf_counter()
+    bases = O.derive_points_fast(2, n)  # setup, untimed
+    setup_s = time.perf_counter() - t0
+    scalars = bench_scalars(n, 0)
     for _ in range(min(args.warmup, 1)):
         O.msm_affine(bases, scalars, threads=threads)
     t = time.perf_counter()
     for _ in range(args.steps):
-        O.msm_affine(bases, scalars, threads=threads)
+        res = O.msm_affine(bases, scalars, threads=threads)
     dt = (time.perf_counter() - t) / args.steps
+    ok = bool(O.pt_eq(res, O.msm_derived_by_dlog(0, scalars, threads=threads)))
     val = n / dt
-    sample = f"MSM of 2^{args.cpu_log_n} points per step (bounded sample of the 2^{args.log_n}-point workload), windows spread over {threads} host threads"
+    sample = (f"one MSM of 2^{args.log_n} points per step = the full per-GPU workload, {args.steps} timed steps after "
+              f"{min(args.warmup, 1)} warm-up; windows x point chunks over {threads} host threads"
+              + (f"; with {world} GPUs the other arm runs {world} such slices at once, this arm times one slice" if world > 1 else ""))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": f"{CURVE}_msm_2^{args.log_n}_per_gpu", "sample": sample},
+        "config": make_config(args.log_n, world),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "self_check": ok, "setup_s": setup_s,
         "note": "reference is Rust/arkworks (no toolchain here): timed arm is its algorithm restated in C (oracle/), kind=port",
-    }))
+    }), flush=True)
 
 
 def run_ours(args):
@@ -153,26 +164,29 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("HALO_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL's own log lines (NCCL_DEBUG, if the launcher sets it) are left alone: the one JSON line is printed last
+        dist.init_process_group("nccl", device_id=dev)
     n = 1 << args.log_n
     ctx = H.Context(local, n)
+    comm = parallel.make_comm(ctx, None, dev) if world > 1 else None
+    n_global = n * world
     first = rank * n
     t0 = time.perf_counter()
-    ctx.derive_generators_range(first, n)  # this rank's point slice of the N * n point MSM
+    if comm:
+        comm.derive_generators(n_global)  # this rank's point slice of the N * n point MSM
+    else:
+        ctx.derive_generators(n)
     derive_s = time.perf_counter() - t0
     t0 = time.perf_counter()
-    if not args.no_precompute:
-        ctx.precompute_generators(0)       # FIXED-base tables: multiples 2^(off_w) G_i of the resident generators (setup)
+    if not args.no_precompute:  # FIXED-base tables: multiples 2^(off_w) G_i of the resident generators (setup)
+        comm.precompute_generators(0) if comm else ctx.precompute_generators(0)
     precompute_s = time.perf_counter() - t0
-    dev = torch.device("cuda", local)
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    d_scalars = torch.randint(-(1 << 63), (1 << 63) - 1, (n, 4), dtype=torch.int64, device=dev, generator=g)
-    d_scalars[:, 3] &= (1 << 62) - 1  # any 256-bit value < 2^254 < r is a valid Montgomery residue
+    h_page = bench_scalars(n, rank)                    # pageable host memory (numpy)
     h_scalars = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
-    h_scalars.copy_(d_scalars)
+    h_scalars.copy_(torch.from_numpy(h_page.view(np.int64)))
+    d_scalars = h_scalars.to(dev)
     torch.cuda.synchronize()
     h_np = h_scalars.numpy().view(np.uint64)
 
@@ -181,28 +195,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def maxr(*vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
     def step_resident():
-        part = ctx.msm_gens_resident(d_scalars.data_ptr(), n)
-        return parallel.combine(part, None, dev) if world > 1 else part
+        if comm:
+            return comm.msm_gens_sharded_resident(d_scalars.data_ptr(), n, n_global)
+        return ctx.msm_gens_resident(d_scalars.data_ptr(), n)
 
-    def step_e2e():
-        part = ctx.msm_gens(h_np)
-        return parallel.combine(part, None, dev) if world > 1 else part
+    def step_e2e(h):
+        if comm:
+            return comm.msm_gens_sharded(h, n_global)
+        return ctx.msm_gens(h)
 
-    # ---- resident (`value`) ----
-    # K independent MSM steps over scalars resident in HBM, two steps in flight (halo_msm_gens_submit_resident /
-    # _collect): the counting sort of step k+1 (L2-atomic bound) runs beside the bucket accumulation of step k
-    # (integer-pipe bound).  The same K steps as strictly sequential blocking calls are reported as `sequential_calls`.
-    def run_resident_pipelined(k_steps):
-        t = ctx.msm_gens_submit_resident(d_scalars.data_ptr(), n)
-        out = None
-        for k in range(k_steps):
-            nxt = ctx.msm_gens_submit_resident(d_scalars.data_ptr(), n) if k + 1 < k_steps else None
-            part = ctx.msm_gens_collect(t)
-            out = parallel.combine(part, None, dev) if world > 1 else part
-            t = nxt
-        return out
+    def finish(part):
+        return comm.allgather_sum(part) if comm else part
 
+    # ---- resident, strictly sequential blocking calls ----
     for _ in range(args.warmup):
         res_seq = step_resident()
     barrier()
@@ -210,52 +223,54 @@ def run_ours(args):
     for _ in range(args.steps):
         res_seq = step_resident()
     seq_ms = max(ctx.timer_stop(), 0.0) / args.steps
-    run_resident_pipelined(max(args.warmup, 2))
+
+    # ---- resident (`value`): K MSM steps over scalars resident in HBM, two steps in flight (halo_msm_gens_submit_resident /
+    # _collect): the counting sort of step k+1 (L2-atomic bound) runs beside the bucket accumulation of step k ----
+    def run_pipelined(k_steps, submit):
+        t = submit()
+        out = None
+        for k in range(k_steps):
+            nxt = submit() if k + 1 < k_steps else None
+            out = finish(ctx.msm_gens_collect(t))
+            t = nxt
+        return out
+
+    run_pipelined(max(args.warmup, 2), lambda: ctx.msm_gens_submit_resident(d_scalars.data_ptr(), n))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ctx.kernel_launches()
     ctx.timer_start()
     w0 = time.perf_counter()
-    res = run_resident_pipelined(args.steps)
+    res = run_pipelined(args.steps, lambda: ctx.msm_gens_submit_resident(d_scalars.data_ptr(), n))
     ev_ms = ctx.timer_stop()
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
     launches = ctx.kernel_launches() - l0
     clocks = sampler.summary()
     ms_step = max(ev_ms, 0.0) / args.steps
-    # ---- e2e (host buffers through the C ABI) ----
-    # (a) blocking call halo_msm_gens: H2D, kernels, D2H strictly in sequence
-    for _ in range(max(args.warmup, 1)):
-        step_e2e()
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(args.steps):
-        res_e = step_e2e()
-    barrier()
-    e2e_sync_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-    # (b) pipelined calls halo_msm_gens_submit / _collect, two steps in flight: the H2D copy of step k+1 (its own 512 MiB,
-    #     copied inside the timed region like every other step's) overlaps the kernels of step k
-    def collect(t):
-        part = ctx.msm_gens_collect(t)
-        return parallel.combine(part, None, dev) if world > 1 else part
 
-    # warm-up: `warmup` steps through the same two-slot pattern (both slots allocate their device buffers on first use)
-    t = ctx.msm_gens_submit(h_np)
-    for k in range(max(args.warmup, 2)):
-        nxt = ctx.msm_gens_submit(h_np) if k + 1 < max(args.warmup, 2) else None
-        collect(t)
-        t = nxt
+    # ---- e2e (host buffers through the C ABI) ----
+    def timed_host(f, steps, warm):
+        for _ in range(warm):
+            out = f()
+        barrier()
+        w = time.perf_counter()
+        for _ in range(steps):
+            out = f()
+        barrier()
+        return out, (time.perf_counter() - w) * 1e3 / steps
+
+    res_e, e2e_sync_ms = timed_host(lambda: step_e2e(h_np), args.steps, max(args.warmup, 1))        # blocking call, pinned
+    res_pg, e2e_page_ms = timed_host(lambda: step_e2e(h_page), max(3, args.steps // 2), 1)          # blocking call, pageable
+    run_pipelined(max(args.warmup, 2), lambda: ctx.msm_gens_submit(h_np))                           # both slots allocate on first use
     barrier()
     w0 = time.perf_counter()
-    t = ctx.msm_gens_submit(h_np)
-    for k in range(args.steps):
-        nxt = ctx.msm_gens_submit(h_np) if k + 1 < args.steps else None
-        res_p = collect(t)
-        t = nxt
+    res_p = run_pipelined(args.steps, lambda: ctx.msm_gens_submit(h_np))
     barrier()
     e2e_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-    # ---- per-phase profile (dominant phase: bucket accumulation), CUDA events on the library's stream ----
+
+    # ---- per-phase profile of the FIXED-base path (dominant phase: bucket accumulation), CUDA events on the library's stream ----
     ctx.set_profiling(True)
     acc_ms = []
     for _ in range(max(3, min(args.steps, 5))):
@@ -263,38 +278,77 @@ def run_ours(args):
         acc_ms.append(ctx.last_msm_timings())
     ctx.set_profiling(False)
     phases = {k: float(np.mean([t[k] for t in acc_ms])) for k in acc_ms[0]}
-    # max over ranks
+
+    # ---- variable base: the same MSM without the tables of precomputed multiples ----
+    ctx.set_fixed_base(False)
+    var_steps = max(3, args.steps // 2)
+    res_var = step_resident()
+    barrier()
+    ctx.timer_start()
+    for _ in range(var_steps):
+        res_var = step_resident()
+    var_ms = max(ctx.timer_stop(), 0.0) / var_steps
+    ctx.set_fixed_base(True)
+
+    ms_step, e2e_ms, wall_step, phases["accumulate"], e2e_sync_ms, seq_ms, var_ms, e2e_page_ms = maxr(
+        ms_step, e2e_ms, wall_ms / args.steps, phases["accumulate"], e2e_sync_ms, seq_ms, var_ms, e2e_page_ms)
+    same = all(H.points_equal(res, x) for x in (res_e, res_p, res_seq, res_var, res_pg))
+
+    # ---- the oracle's verdict on the timed result (untimed; the oracle is the checker, never the thing measured) ----
+    from oracle import oracle as O
+
+    threads_cpu = host_threads()
+    cpu = None
+    th = max(1, threads_cpu // world)
+    dl_local = O.msm_derived_by_dlog(first, h_page, threads=th)   # (sum_i a_i s_i) * (-1, 2) over this rank's slice
+    dl_total = comm.allgather_sum(dl_local) if comm else dl_local
+    oracle_match = {"dlog_property": bool(O.pt_eq(res, dl_total))}
+    if world == 1 and not args.no_cpu_baseline:
+        gs = ctx.get_generators(0, n)                              # the very bases the GPU used, read back
+        t = time.perf_counter()
+        exp = O.msm_affine(gs, h_page, threads=threads_cpu)         # arkworks-shaped Pippenger at the SAME size
+        dt = time.perf_counter() - t
+        del gs
+        oracle_match["pippenger_same_size"] = bool(O.pt_eq(res, exp))
+        cpu = {"value": n / dt, "unit": UNIT, "cores": threads_cpu, "kind": "port",
+               "sample": f"1 MSM of 2^{args.log_n} points = the full workload, same bases and scalars as the GPU arm ({dt:.1f} s); "
+                         f"arkworks-shaped Pippenger restated in C, windows x point chunks over {threads_cpu} threads"}
+    ok_all = all(oracle_match.values())
     if world > 1:
-        t = torch.tensor([ms_step, e2e_ms, wall_ms / args.steps, phases["accumulate"], e2e_sync_ms, seq_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_ms, wall_step, phases["accumulate"], e2e_sync_ms, seq_ms = [float(x) for x in t.tolist()]
-    else:
-        wall_step = wall_ms / args.steps
-    same = (bool(np.array_equal(res, res_e)) or _points_equal(res, res_e)) and _points_equal(res, res_p) and _points_equal(res, res_seq)
+        t = torch.tensor([1.0 if ok_all else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok_all = bool(t.item() > 0.5)
+
+    # ---- integer-pipe peak, measured here: independent IMAD chains on every SM ----
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    blocks, threads, iters = sms * 8, 256, 4096
+    imad_ms = min(ctx.test_imad_throughput(0, blocks, threads, iters) for _ in range(3))
+    imad_peak = blocks * threads * iters * 16 / imad_ms / 1e9  # T IMAD32/s: dependent-multiplicand mad.lo.u32 chains
+
+    def whole_msm_frac(points, ms, gpus=1):
+        return (points * 160 + 14.68e6) * IMAD_PER_MODMUL / (ms * 1e-3) / 1e12 / (imad_peak * gpus)
+
+    # ---- strong scaling (BASELINE config 5): ONE MSM of 2^lg points over the N GPUs ----
+    strong = None
+    if not args.no_strong:
+        strong = strong_scaling_sweep(args, ctx, comm, world, rank, dev, barrier, maxr, whole_msm_frac, O, th)
 
     out = None
     if rank == 0:
         total_points = n * world
-        # integer-pipe peak, measured here: independent IMAD chains on every SM
-        sms = torch.cuda.get_device_properties(local).multi_processor_count
-        blocks, threads, iters = sms * 8, 256, 4096
-        imad_ms = min(ctx.test_imad_throughput(0, blocks, threads, iters) for _ in range(3))
-        imad_peak = blocks * threads * iters * 16 / imad_ms / 1e9  # T IMAD32/s: dependent-multiplicand mad.lo.u32 chains
-        alg_imad = n * CANON_W * 10 * IMAD_PER_MODMUL  # algorithmic IMAD32 of one k_accumulate launch (canonical c = 16)
+        alg_imad = n * CANON_W * 10 * IMAD_PER_MODMUL  # algorithmic IMAD32 of the accumulation phase (canonical c = 16)
         achieved = alg_imad / (phases["accumulate"] * 1e-3) / 1e12
-        traffic = None  # dram__bytes_read + dram__bytes_write of one k_accumulate launch, from the committed ncu capture
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["accumulate_phase_pair_tree"]
-            if tj["workload"] == f"{CURVE}_msm_2^{args.log_n}_per_gpu" and tj["fixed_base_tables"] == (not args.no_precompute):
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        except Exception:
-            pass
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            threads_cpu = host_threads()
-            v, dt, reps = cpu_msm_baseline(args.cpu_log_n, threads_cpu)
-            cpu = {"value": v, "unit": UNIT, "cores": threads_cpu, "kind": "port",
-                   "sample": f"{reps} MSMs of 2^{args.cpu_log_n} points ({dt:.1f} s in total), arkworks-shaped Pippenger restated in C, windows over {threads_cpu} threads"}
+        traffic = None  # dram__bytes_read + dram__bytes_write of the accumulation phase, from the committed ncu capture
+        traffic_file = None
+        for fn in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", fn)))["accumulate_phase_pair_tree"]
+                if tj["workload"] == f"{CURVE}_msm_2^{args.log_n}_per_gpu" and tj["fixed_base_tables"] == (not args.no_precompute):
+                    traffic, traffic_file = tj["dram_bytes_read"] + tj["dram_bytes_write"], fn
+                    break
+            except Exception:
+                pass
+        # executed work: W windows x (6.2 modmul per affine pair-tree addition for the first P levels, 10 for the XYZZ tail)
         secondary = None
         if world == 1 and not args.no_secondary:
             secondary = secondary_metrics(ctx, args)
@@ -302,44 +356,97 @@ def run_ours(args):
             "metric": METRIC, "value": total_points / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
-            "config": {"workload": f"{CURVE}_msm_2^{args.log_n}_per_gpu", "points_per_gpu": n, "total_points": total_points,
-                       "bases": "derived generators G_i (main.rs:18-45 rule), resident", "scalars": "uniform 254-bit, seeded",
-                       "parallelism": f"point-slice x{world}, one all-gather of {world} x 96 B per step" if world > 1 else "single GPU",
-                       "l2": "inputs_exceed_l2 (>= 1.5 GiB streamed per step)", "window_c": "auto",
-                       "steps_in_flight": "2 (halo_msm_gens_submit_resident / _collect: the counting sort of step k+1 overlaps the accumulation of step k)",
-                       "fixed_base_tables": (not args.no_precompute)},
+            "config": make_config(args.log_n, world),
+            "impl_config": {"window_c": "auto", "fixed_base_tables": (not args.no_precompute),
+                            "steps_in_flight": "2 (halo_msm_gens_submit_resident / _collect: the counting sort of step k+1 overlaps the accumulation of step k)",
+                            "collective": f"ncclAllGather inside libhalo_b200.so (halo_comm_*), NCCL {H._capi.load().halo_nccl_version()}" if world > 1 else None},
+            "oracle_match": ok_all, "oracle_checks": oracle_match, "paths_agree": same,
             "wall_ms_per_step": wall_step,
-            "sequential_calls": {"api": "halo_msm_gens_resident (one blocking call per step, nothing overlaps)", "ms_per_step": seq_ms,
-                                 "value": total_points / (seq_ms * 1e-3)},
+            "sequential_calls": {"api": ("halo_msm_gens_sharded_resident" if world > 1 else "halo_msm_gens_resident") + " (one blocking call per step, nothing overlaps)",
+                                 "ms_per_step": seq_ms, "value": total_points / (seq_ms * 1e-3)},
+            "variable_base": {"api": "same call without halo_precompute_generators tables (W bucket sets, Horner on the host): the path of point_dot / the IPA rounds",
+                              "ms_per_step": var_ms, "value": total_points / (var_ms * 1e-3), "whole_msm_frac": whole_msm_frac(n, var_ms)},
             "e2e": {"value": total_points / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "api": "halo_msm_gens_submit / halo_msm_gens_collect (pinned host scalars, two steps in flight)",
                     "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 3 * 128, "result_matches_resident": same,
-                    "blocking_call": {"api": "halo_msm_gens (one call; internally two point slices, 5/16 and 11/16, through the pipeline slots for n >= 2^23)", "value": total_points / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms}},
+                    "blocking_call": {"api": ("halo_msm_gens_sharded" if world > 1 else "halo_msm_gens") + " from pinned host memory (one call per step)",
+                                      "value": total_points / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms},
+                    "blocking_call_pageable": {"api": "the same call from PAGEABLE host memory (a plain Vec<Fr> / numpy array), staged through pinned chunks inside the library",
+                                               "value": total_points / (e2e_page_ms * 1e-3), "ms_per_step": e2e_page_ms}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "imad", "bound_note": "integer pipe (IMAD32 issue rate): the path is big-integer arithmetic, neither HBM nor tensor bound; BASELINE.json's north_star asks for the fraction of the integer-pipe roofline", "kernel": "bucket accumulation phase: k_pair_fwd / k_pair_bwd x 4 tree passes (affine, batched inversion) + k_accumulate (XYZZ tail)", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD32/s",
-                         "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "DRAM bytes of the phase per MSM (ncu, profiles/r01_traffic.json); pass 0 of the tree (19 of 33 ms) is HBM bound on 128-byte random accesses at 3.6-4.0 TB/s, the rest integer-pipe bound",
+                         "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": f"DRAM bytes of the phase per MSM (ncu, profiles/{traffic_file})",
                          "hbm_gbs_phase": (traffic / (phases["accumulate"] * 1e-3) / 1e9) if traffic else None,
                          "peak_source": "measured in this run (libhalo_b200 mad.lo.u32 microbenchmark, 16 independent chains per thread, all SMs); MEASURED_PEAKS.json has no integer-pipe figure. IMAD.WIDE / IMAD.HI issue at half this rate (profiles/r01_imad_pipe_rates.jsonl)",
-                         "algorithmic": f"{n} pts x {CANON_W} windows x 10 modmul x {IMAD_PER_MODMUL} IMAD32 per launch",
+                         "algorithmic": f"{n} pts x {CANON_W} windows x 10 modmul x {IMAD_PER_MODMUL} IMAD32 per launch (SURVEY 8d canonical accounting, c = 16)",
                          "launch_ms": phases["accumulate"], "phases_ms": phases,
-                         "whole_msm_frac": (n * 160 + 14.68e6) * IMAD_PER_MODMUL / (ms_step * 1e-3) / 1e12 / imad_peak},
+                         "whole_msm_frac": whole_msm_frac(n, ms_step),
+                         "executed": {"note": "what the kernels issue: 13 windows (c = 20), 15/16 of the additions affine in the pair tree (6.2 modmul each: 5M + 1S + shared inversion), the rest XYZZ (10)",
+                                      "modmul_per_point": 13 * (15 / 16 * 6.2 + 1 / 16 * 10),
+                                      "frac": n * 13 * (15 / 16 * 6.2 + 1 / 16 * 10) * IMAD_PER_MODMUL / (phases["accumulate"] * 1e-3) / 1e12 / imad_peak}},
+            "strong_scaling": strong,
             "cpu_baseline": cpu,
             "secondary": secondary,
             "derive_generators_s": derive_s, "precompute_tables_s": precompute_s,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    if comm:
+        comm.close()
     ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
     return out
 
 
-def _points_equal(a, b):
+def strong_scaling_sweep(args, ctx, comm, world, rank, dev, barrier, maxr, whole_msm_frac, O, oracle_threads):
+    """ONE MSM of 2^lg points, lg = 16 .. log_n, sharded by point slice over the `world` GPUs (strong scaling): FIXED-base
+    tables per slice, device-resident scalars, the library's all-gather inside the timed region, CUDA events on the
+    library's stream, max over ranks.  Every size is checked against the oracle (discrete-log property of the derived
+    generators on every rank's slice; the arkworks-shaped Pippenger as well up to 2^20)."""
+    import torch
+
     import halo_accumulation_b200 as H
 
-    return H.points_equal(a, b)
+    rows = {}
+    for lg in [l for l in (16, 18, 20, 22, 24) if l <= args.log_n]:
+        nt = 1 << lg
+        if nt < world:
+            continue
+        first, count = H.comm_slice(nt, rank, world)
+        if comm:
+            comm.derive_generators(nt)
+            comm.precompute_generators(0)
+        else:
+            ctx.derive_generators(nt)
+            ctx.precompute_generators(0)
+        h = bench_scalars(nt, 100 + lg)[first:first + count]
+        d = torch.from_numpy(h.view(np.int64).copy()).to(dev)
+        torch.cuda.synchronize()
+        call = (lambda: comm.msm_gens_sharded_resident(d.data_ptr(), count, nt)) if comm else (lambda: ctx.msm_gens_resident(d.data_ptr(), count))
+        reps = 20 if lg <= 20 else (8 if lg <= 22 else 4)
+        for _ in range(3):
+            out = call()
+        best = 1e30
+        for _ in range(3):
+            barrier()
+            ctx.timer_start()
+            for _ in range(reps):
+                out = call()
+            best = min(best, maxr(ctx.timer_stop() / reps)[0])
+        dl = O.msm_derived_by_dlog(first, h, threads=oracle_threads)
+        exp = comm.allgather_sum(dl) if comm else dl
+        ok = bool(O.pt_eq(out, exp))
+        if lg <= 20 and rank == 0:
+            ok = ok and bool(O.pt_eq(out, O.msm_affine(O.derive_points_fast(2, nt), bench_scalars(nt, 100 + lg), threads=oracle_threads)))
+        rows[f"2^{lg}"] = {"ms": best, "points_per_s": nt / (best * 1e-3), "frac_of_imad_roofline": whole_msm_frac(nt, best, world),
+                           "points_per_gpu": count, "oracle_match": ok}
+        del d
+    return {"gpus": world, "what": "one MSM of 2^lg points sharded by point slice over the GPUs; FIXED-base tables; scalars resident; "
+                                   "all-gather and finish inside the timed call; fraction = SURVEY 8(d) whole-MSM work / time / (gpus x measured IMAD peak)",
+            "sizes": rows}
 
 
 def secondary_metrics(ctx, args):
@@ -391,8 +498,18 @@ def secondary_metrics(ctx, args):
         t = time.perf_counter()
         acc.decider(ctx, a)
         dec = min(dec, (time.perf_counter() - t) * 1e3)
+    # the oracle's decision on the accumulator just timed (its decider = succinct check + one 2^20 MSM on the host cores)
+    from oracle import oracle as O
+
+    S, Hh = ctx.get_SH()
+    O.set_params(S, Hh, ctx.get_generators(0, n))
+    t = time.perf_counter()
+    orc = O.acc_decider(O.Accumulator.from_buffer_copy(bytes(a)), threads=host_threads())
+    orc_ms = (time.perf_counter() - t) * 1e3
     return {f"asdl_decider_ms_2^{lg}": dec, f"pcdl_check_ms_2^{lg}": best, f"pcdl_open_hiding_ms_2^{lg}": open_ms, f"pcdl_open_ms_2^{lg}": open_plain_ms,
-            f"pcdl_commit_ms_2^{lg}": commit_ms, f"asdl_prover_ms_2^{lg}": prover_ms, "timing": "host wall clock around the synchronous call, best of 2 after one warm-up (open_ms includes a commit)"}
+            f"pcdl_commit_ms_2^{lg}": commit_ms, f"asdl_prover_ms_2^{lg}": prover_ms,
+            "oracle_decider_accepts": orc == 0, f"oracle_decider_cpu_ms_2^{lg}": orc_ms,
+            "timing": "host wall clock around the synchronous call, best of 2 after one warm-up (open_ms includes a commit)"}
 
 
 def main():
@@ -402,10 +519,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-n", type=int, default=24, help="log2 of the points per GPU")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--cpu-log-n", type=int, default=20, help="log2 of the bounded CPU sample")
     ap.add_argument("--secondary-log-n", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sweep (one MSM of 2^16 .. 2^log_n points over the GPUs)")
     ap.add_argument("--no-precompute", action="store_true", help="variable-base path only (no tables of precomputed multiples)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -12,7 +12,7 @@ import numpy as np
 from . import _build
 from ._capi import HaloError, arr, load, p64, u8p
 
-__all__ = ["Context", "HaloError", "build", "points_sum", "points_equal"]
+__all__ = ["Context", "Comm", "MultiGpu", "HaloError", "build", "points_sum", "points_equal", "comm_slice"]
 
 
 def points_sum(points_jac):
@@ -41,6 +41,90 @@ def check_canaries():
     live = C.c_int()
     bad = load().halo_test_check_canaries(C.byref(live))
     return int(bad), live.value
+
+
+def comm_slice(n_total, rank, size):
+    """halo_comm_slice: the contiguous point slice [first, first + count) of rank `rank` of `size`."""
+    first, count = C.c_uint64(), C.c_uint64()
+    load().halo_comm_slice(C.c_uint64(n_total), int(rank), int(size), C.byref(first), C.byref(count))
+    return first.value, count.value
+
+
+class Comm:
+    """Rank form of the sharded MSM (include/halo_b200.h, "multi-GPU"): one communicator per context, NCCL inside the library."""
+
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * Comm.ID_BYTES)()
+        rc = load().halo_comm_unique_id(buf)
+        if rc != 0:
+            raise HaloError(rc, "halo_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def __init__(self, ctx, uid, nranks, rank):
+        self._lib, self.ctx = load(), ctx
+        assert len(uid) == Comm.ID_BYTES
+        h = C.c_void_p()
+        buf = (C.c_uint8 * Comm.ID_BYTES).from_buffer_copy(uid)
+        ctx._chk(self._lib.halo_comm_init_rank(ctx._h, buf, int(nranks), int(rank), C.byref(h)))
+        self._h, self.rank, self.size = h, rank, nranks
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.halo_comm_destroy(self._h)
+            self._h = None
+
+    def derive_generators(self, n_total):
+        self.ctx._chk(self._lib.halo_comm_derive_generators(self._h, C.c_uint64(n_total)))
+
+    def precompute_generators(self, window=0):
+        self.ctx._chk(self._lib.halo_comm_precompute_generators(self._h, int(window)))
+
+    def msm_gens_sharded(self, local_scalars, n_global, off_local=0):
+        s = arr(local_scalars).reshape(-1, 4)
+        out = np.zeros(12, dtype=np.uint64)
+        self.ctx._chk(self._lib.halo_msm_gens_sharded(self._h, p64(s), C.c_uint64(off_local), C.c_uint64(s.shape[0]), C.c_uint64(n_global), p64(out)))
+        return out
+
+    def msm_gens_sharded_resident(self, d_ptr, n_local, n_global, off_local=0):
+        out = np.zeros(12, dtype=np.uint64)
+        self.ctx._chk(self._lib.halo_msm_gens_sharded_resident(self._h, C.c_void_p(d_ptr), C.c_uint64(off_local), C.c_uint64(n_local),
+                                                               C.c_uint64(n_global), p64(out)))
+        return out
+
+    def allgather_sum(self, point_jac):
+        p = arr(point_jac, (12,))
+        out = np.zeros(12, dtype=np.uint64)
+        self.ctx._chk(self._lib.halo_comm_allgather_sum(self._h, p64(p), p64(out)))
+        return out
+
+
+class MultiGpu:
+    """Node form: one caller thread, g devices (halo_mgpu_*); the multi-GPU body of `point_dot_affine` over GS[0..n)."""
+
+    def __init__(self, devices, n_total, precompute_window=0):
+        self._lib = load()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._lib.halo_mgpu_create(devs, len(devices), C.c_uint64(n_total), int(precompute_window), C.byref(h))
+        if rc != 0:
+            raise HaloError(rc, "halo_mgpu_create failed")
+        self._h, self.size, self.n_total = h, len(devices), n_total
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.halo_mgpu_destroy(self._h)
+            self._h = None
+
+    def msm_gens(self, scalars):
+        s = arr(scalars).reshape(-1, 4)
+        out = np.zeros(12, dtype=np.uint64)
+        rc = self._lib.halo_mgpu_msm_gens(self._h, p64(s), C.c_uint64(s.shape[0]), p64(out))
+        if rc != 0:
+            raise HaloError(rc, self._lib.halo_mgpu_last_error(self._h).decode())
+        return out
 
 
 class _MsmDesc(C.Structure):  # halo_msm_desc, include/halo_b200.h

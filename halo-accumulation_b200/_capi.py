@@ -45,6 +45,22 @@ def load():
     lib.halo_num_generators.restype = C.c_uint64
     lib.halo_save_generators.argtypes = [C.c_void_p, C.c_char_p]
     lib.halo_load_generators_file.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+    lib.halo_comm_slice.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
+    lib.halo_comm_slice.restype = None
+    lib.halo_comm_destroy.argtypes = [C.c_void_p]
+    lib.halo_comm_destroy.restype = None
+    lib.halo_comm_init_rank.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.halo_comm_derive_generators.argtypes = [C.c_void_p, C.c_uint64]
+    lib.halo_comm_precompute_generators.argtypes = [C.c_void_p, C.c_int]
+    lib.halo_msm_gens_sharded.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]
+    lib.halo_msm_gens_sharded_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]
+    lib.halo_comm_allgather_sum.argtypes = [C.c_void_p, u64p, u64p]
+    lib.halo_mgpu_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+    lib.halo_mgpu_destroy.argtypes = [C.c_void_p]
+    lib.halo_mgpu_destroy.restype = None
+    lib.halo_mgpu_msm_gens.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p]
+    lib.halo_mgpu_last_error.argtypes = [C.c_void_p]
+    lib.halo_mgpu_last_error.restype = C.c_char_p
     if lib.halo_curve_name().decode() != _build.CURVE:
         raise RuntimeError(f"{path} was built for {lib.halo_curve_name().decode()}, HALO_B200_CURVE asks for {_build.CURVE}")
     _lib = lib

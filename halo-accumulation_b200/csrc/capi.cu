@@ -1,6 +1,8 @@
 // capi.cu -- extern "C" entry points of libhalo_b200.so (include/halo_b200.h).
 #include <cstdio>
 #include <cstring>
+#include <system_error>
+#include <thread>
 
 #include "../../include/halo_b200.h"
 #include "common.cuh"
@@ -12,10 +14,15 @@ using namespace halo;
 
 namespace halo {
 
-// Registry behind DevBuf's canaries (one process-wide list; contexts are single-threaded like the reference).
+// Registry behind DevBuf's canaries: one process-wide list, guarded by a mutex (a context is single-threaded like the
+// reference, but several contexts may live on several host threads).
 std::vector<DevBuf*>& devbuf_registry() {
     static std::vector<DevBuf*> r;
     return r;
+}
+std::mutex& devbuf_registry_mutex() {
+    static std::mutex m;
+    return m;
 }
 
 __global__ void __launch_bounds__(256) k_mark_infinity(affine_t* __restrict__ bases, const uint8_t* __restrict__ inf, uint64_t n) {
@@ -46,6 +53,64 @@ int set_error(halo_ctx* ctx, int code, const char* fmt, const char* a, const cha
 }  // namespace halo
 
 namespace halo {
+void h2d_copy(halo_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return;
+    constexpr size_t CH = halo_ctx::STAGE_CHUNK;
+    bool pageable = false;
+    if (ctx->tune_stage_pageable && bytes >= 4 * CH) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess)
+            pageable = at.type == cudaMemoryTypeUnregistered;
+        else
+            cudaGetLastError();
+    }
+    if (!pageable) {
+        HALO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return;
+    }
+    constexpr int T = halo_ctx::STAGE_THREADS, S = halo_ctx::STAGE_SLOTS;
+    for (int i = 0; i < T * S; i++)
+        if (!ctx->stage_pinned[i]) {
+            HALO_CUDA(cudaMallocHost(&ctx->stage_pinned[i], CH));
+            HALO_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+        }
+    const size_t nchunks = (bytes + CH - 1) / CH;
+    cudaError_t errs[T];
+    auto work = [&](int t) {
+        errs[t] = cudaSetDevice(ctx->device);
+        size_t use = 0;
+        for (size_t k = (size_t)t; k < nchunks && errs[t] == cudaSuccess; k += T, use++) {
+            const int slot = t * S + (int)(use % S);
+            if (use >= (size_t)S) errs[t] = cudaEventSynchronize(ctx->stage_ev[slot]);  // the DMA out of this slot two chunks ago
+            const size_t off = k * CH, len = bytes - off < CH ? bytes - off : CH;
+            memcpy(ctx->stage_pinned[slot], static_cast<const char*>(src) + off, len);
+            if (errs[t] == cudaSuccess)
+                errs[t] = cudaMemcpyAsync(static_cast<char*>(dst) + off, ctx->stage_pinned[slot], len, cudaMemcpyHostToDevice, st);
+            if (errs[t] == cudaSuccess) errs[t] = cudaEventRecord(ctx->stage_ev[slot], st);
+        }
+    };
+    // the ring may still be draining from the previous staged copy (a different stream): wait before refilling it
+    for (int i = 0; i < T * S; i++) HALO_CUDA(cudaEventSynchronize(ctx->stage_ev[i]));
+    std::thread th[T];
+    int spawned = 0;
+    for (int t = 1; t < T; t++) {
+        try {
+            th[t] = std::thread(work, t);
+            spawned |= 1 << t;
+        } catch (const std::system_error&) {
+        }
+    }
+    work(0);
+    for (int t = 1; t < T; t++) {
+        if (spawned & (1 << t))
+            th[t].join();
+        else
+            work(t);  // no thread available: this thread takes the chunks as well
+    }
+    for (int t = 0; t < T; t++)
+        if (errs[t] != cudaSuccess) throw CudaError{errs[t], "staged host-to-device copy", __FILE__, __LINE__};
+}
+
 static void async_init(halo_ctx* ctx) {
     if (ctx->copy_stream) return;
     HALO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -126,7 +191,7 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     ctx->stage_misc.release();
     ctx->poly_dev.release();
     for (halo::DevBuf* b : {&ctx->ipa_G, &ctx->ipa_cs, &ctx->ipa_zs, &ctx->ipa_pbar, &ctx->ipa_tail, &ctx->ipa_frozen,
-                           &ctx->ipa_sums, &ctx->ipa_den, &ctx->ipa_inv_scratch, &ctx->ipa_bx, &ctx->ipa_diff, &ctx->ipa_den2}) b->release();
+                           &ctx->ipa_sums, &ctx->ipa_den, &ctx->ipa_inv_scratch, &ctx->ipa_bx, &ctx->ipa_diff, &ctx->ipa_den2, &ctx->ipa_ops}) b->release();
     for (MsmWorkspace* wsp : {&ctx->ws, &ctx->ws2}) {
     MsmWorkspace& ws = *wsp;
     for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,
@@ -140,6 +205,10 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (void* p : ctx->stage_pinned)
+        if (p) cudaFreeHost(p);
+    for (cudaEvent_t e : ctx->stage_ev)
+        if (e) cudaEventDestroy(e);
     for (auto& s : ctx->slots) {
         s.scalars.release();
         for (DevBuf* b : {&s.sort_ws.counts, &s.sort_ws.offsets, &s.sort_ws.entries, &s.sort_ws.scan_tmp}) b->release();
@@ -171,6 +240,7 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "split_blocking")) ctx->tune_split_blocking = value;
     else if (!strcmp(key, "split_first_16ths")) ctx->tune_split_first_16ths = value < 1 ? 1 : value > 15 ? 15 : value;
     else if (!strcmp(key, "sort_ahead")) ctx->tune_sort_ahead = value;
+    else if (!strcmp(key, "stage_pageable")) ctx->tune_stage_pageable = value;
     else if (!strcmp(key, "ipa_defer_rounds")) ctx->tune_ipa_defer = value;
     else if (!strcmp(key, "ipa_two_lanes")) ctx->tune_ipa_two_lanes = value;
     else if (!strcmp(key, "ipa_freeze_len")) ctx->tune_ipa_freeze_len = value;
@@ -522,7 +592,7 @@ int halo_msm_gens(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t
     }
     HALO_TRY(ctx)
     ctx->stage_scalars.reserve((n ? n : 1) * sizeof(fr_t));
-    if (n) HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) h2d_copy(ctx, ctx->stage_scalars.p, scalars, n * sizeof(fr_t), ctx->stream);
     xyzz_t r;
     msm_gens_device(ctx, ctx->stage_scalars.as<fr_t>(), off, n, r);
     out_jac_from_xyzz(r, out_jac);
@@ -551,7 +621,7 @@ static int submit_impl(halo_ctx* ctx, const uint64_t* scalars, bool resident, ui
             // contract is that they are complete when this call is made
         } else {
             s.scalars.reserve(n * sizeof(fr_t));
-            HALO_CUDA(cudaMemcpyAsync(s.scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+            h2d_copy(ctx, s.scalars.p, scalars, n * sizeof(fr_t), ctx->copy_stream);
             HALO_CUDA(cudaEventRecord(s.copied, ctx->copy_stream));
             HALO_CUDA(cudaStreamWaitEvent(ahead_on ? ctx->sort_stream : ctx->stream, s.copied, 0));
             in.scalars = s.scalars.as<fr_t>();
@@ -616,8 +686,8 @@ int halo_msm(halo_ctx* ctx, const uint64_t* bases_affine, const uint8_t* inf_fla
     ctx->stage_scalars.reserve((n ? n : 1) * sizeof(fr_t));
     ctx->stage_bases.reserve((n ? n : 1) * sizeof(affine_t));
     if (n) {
-        HALO_CUDA(cudaMemcpyAsync(ctx->stage_scalars.p, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
-        HALO_CUDA(cudaMemcpyAsync(ctx->stage_bases.p, bases_affine, n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+        h2d_copy(ctx, ctx->stage_scalars.p, scalars, n * sizeof(fr_t), ctx->stream);
+        h2d_copy(ctx, ctx->stage_bases.p, bases_affine, n * sizeof(affine_t), ctx->stream);
         if (inf_flags) {
             ctx->stage_misc.reserve(n);
             HALO_CUDA(cudaMemcpyAsync(ctx->stage_misc.p, inf_flags, n, cudaMemcpyHostToDevice, ctx->stream));

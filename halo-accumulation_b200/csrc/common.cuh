@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -40,6 +41,7 @@ struct CudaError {
 // kernel wrote past any live buffer.
 struct DevBuf;
 std::vector<DevBuf*>& devbuf_registry();
+std::mutex& devbuf_registry_mutex();  // contexts on different host threads grow / release buffers concurrently
 struct DevBuf {
     static constexpr size_t CANARY = 256;
     void* p = nullptr;
@@ -54,11 +56,13 @@ struct DevBuf {
         HALO_CUDA(cudaMalloc(&p, bytes + CANARY));
         cap = bytes;
         HALO_CUDA(cudaMemset(static_cast<char*>(p) + cap, 0xA5, CANARY));
+        std::lock_guard<std::mutex> lock(devbuf_registry_mutex());
         devbuf_registry().push_back(this);
     }
     void release() {
         if (p) {
             cudaFree(p);
+            std::lock_guard<std::mutex> lock(devbuf_registry_mutex());
             auto& r = devbuf_registry();
             for (size_t i = 0; i < r.size(); i++)
                 if (r[i] == this) {
@@ -112,10 +116,24 @@ struct MsmWorkspace {
     DevBuf pt_a, pt_b, pt_prefix, pt_levels;  // pair-tree passes (msm_pairs.cu): ping-pong slot arrays, prefixes, product hierarchy
 };
 
+// Operation list of the generator fold (ipa.cu, k_fold_multi), built on the host per opening round.
+struct FoldOpsHost {
+    uint8_t code[3072];
+};
+
 struct Timings {
     float digits_ms = 0, scan_ms = 0, scatter_ms = 0, accumulate_ms = 0, reduce_ms = 0, total_ms = 0;
 };
 
+}  // namespace halo
+
+struct halo_ctx;
+namespace halo {
+// Host-to-device copy of a caller buffer on `st`.  Pinned (or registered) memory goes to cudaMemcpyAsync directly.  Large
+// PAGEABLE buffers -- a Rust Vec<Fr>, a numpy array -- would be staged by the driver through one small bounce buffer at a
+// fraction of the PCIe rate; they are instead copied by a few host threads into a ring of pinned chunks, each chunk's DMA
+// enqueued as soon as it is filled.  Returns when the caller's buffer has been read completely (the DMAs may still run).
+void h2d_copy(halo_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st);
 }  // namespace halo
 
 // The opaque handle behind `halo_ctx*` (include/halo_b200.h).
@@ -144,6 +162,8 @@ struct halo_ctx {
     // buffers of the (single) in-flight PCDL opening, kept across openings: cudaMalloc / cudaFree of 100+ MB per open
     // costs tens of milliseconds
     halo::DevBuf ipa_G, ipa_cs, ipa_zs, ipa_pbar, ipa_tail, ipa_frozen;
+    halo::DevBuf ipa_ops;          // device copy of fold_ops
+    halo::FoldOpsHost fold_ops;    // per context: two contexts may open concurrently from two host threads
     halo::DevBuf ipa_sums, ipa_den, ipa_inv_scratch, ipa_bx, ipa_diff, ipa_den2;  // generator fold: XYZZ sums, ZZ * ZZZ and the batched inversion's hierarchy
     bool ipa_busy = false;
     // asynchronous MSM pipeline (halo_msm_gens_submit / _collect): two in-flight slots, H2D on its own stream so the copy
@@ -159,6 +179,12 @@ struct halo_ctx {
     } slots[2];
     cudaStream_t copy_stream = nullptr, sort_stream = nullptr;  // sort_stream: highest priority
     int next_slot = 0;
+    // staging ring for host-to-device copies out of PAGEABLE caller memory (h2d_copy, capi.cu)
+    static constexpr int STAGE_THREADS = 4, STAGE_SLOTS = 2;
+    static constexpr size_t STAGE_CHUNK = 8u << 20;
+    void* stage_pinned[STAGE_THREADS * STAGE_SLOTS] = {};
+    cudaEvent_t stage_ev[STAGE_THREADS * STAGE_SLOTS] = {};
+    int tune_stage_pageable = 1;  // 0: hand pageable pointers to cudaMemcpyAsync as they are
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     int force_c = 0;

@@ -75,11 +75,11 @@ __global__ void __launch_bounds__(128) k_fold_finish(const xyzz_t* __restrict__ 
 // term), merges all terms into one operation list (uniform across the grid, so the loop is divergence free) and uploads it.
 constexpr int FOLD_MAX_DEFER = 4;
 constexpr int FOLD_MAX_OPS = 3072;
-struct FoldOps {
-    uint8_t code[FOLD_MAX_OPS];  // 0xff: double; else (stream | sign << 7), stream = 2 (t - 1) + half
-    int n_ops;
-};
-__device__ __constant__ FoldOps c_fold_ops;
+// The operation list is per CONTEXT (halo_ctx::fold_ops on the host, halo_ctx::ipa_ops on the device): two contexts may run
+// openings concurrently from two host threads, on the same device or not (INTEGRATION.md "threading"), so neither a
+// process-wide host buffer nor a __constant__ symbol (one per device, shared by every stream) may hold it.  The kernel
+// reads it with uniform addresses (one L1 broadcast per operation, negligible beside the ~10 multiplications that follow).
+static_assert(FOLD_MAX_OPS == sizeof(halo::FoldOpsHost::code), "halo_ctx::fold_ops capacity");
 
 __device__ __forceinline__ uint64_t fold_term_offset(uint64_t n, int D, int t) {
     uint64_t off = 0;
@@ -138,16 +138,16 @@ __global__ void __launch_bounds__(128) k_fold_prep2(const affine_t* __restrict__
 __global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_multi(const affine_t* __restrict__ G0, uint64_t n, int D,
                                                                          const fq_t* __restrict__ bx,
                                                                          const affine_t* __restrict__ diff,
+                                                                         const uint8_t* __restrict__ ops, int n_ops,
                                                                          xyzz_t* __restrict__ sums, fq_t* __restrict__ den) {
     const uint64_t m = n >> D;
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     xyzz_t acc;
     xyzz_set_inf(acc);
-    const int n_ops = c_fold_ops.n_ops;
 #pragma unroll 1
     for (int o = 0; o < n_ops; o++) {
-        const uint32_t code = c_fold_ops.code[o];
+        const uint32_t code = __ldg(ops + o);
         if (code == 0xffu) {
             xyzz_dbl(acc, acc);
         } else {
@@ -250,8 +250,9 @@ static void fold_multi(halo_ctx* ctx, const affine_t* src, uint64_t n, const fr_
         make_glv_jsf(coef[t], dg[t]);
         if (dg[t].top > top) top = dg[t].top;
     }
-    static FoldOps ops;  // one opening per context at a time; the copy below is staged before the call returns
+    FoldOpsHost& ops = ctx->fold_ops;  // one opening per context at a time; the copy below is staged before the call returns
     int no = 0;
+    if ((top + 1) * T > FOLD_MAX_OPS) throw CudaError{cudaErrorInvalidValue, "fold_multi: operation list too long", __FILE__, __LINE__};
     for (int i = top; i >= 0; i--) {
         ops.code[no++] = 0xff;
         for (int t = 1; t < T; t++) {
@@ -265,9 +266,8 @@ static void fold_multi(halo_ctx* ctx, const affine_t* src, uint64_t n, const fr_
             ops.code[no++] = (uint8_t)((t - 1) | (kind << 4) | (neg ? 0x80 : 0));
         }
     }
-    if (no > FOLD_MAX_OPS) throw CudaError{cudaErrorInvalidValue, "fold_multi: operation list too long", __FILE__, __LINE__};
-    ops.n_ops = no;
-    HALO_CUDA(cudaMemcpyToSymbolAsync(c_fold_ops, &ops, sizeof ops, 0, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->ipa_ops.reserve(FOLD_MAX_OPS);
+    HALO_CUDA(cudaMemcpyAsync(ctx->ipa_ops.p, ops.code, (size_t)no, cudaMemcpyHostToDevice, ctx->stream));
     ctx->ipa_bx.reserve((size_t)(T - 1) * m * sizeof(fq_t));
     ctx->ipa_diff.reserve((size_t)(T - 1) * m * sizeof(affine_t));
     ctx->ipa_den2.reserve((size_t)(T - 1) * m * sizeof(fq_t));
@@ -279,6 +279,7 @@ static void fold_multi(halo_ctx* ctx, const affine_t* src, uint64_t n, const fr_
     batch_invert(ctx, ctx->stream, ctx->ipa_den2.as<fq_t>(), (uint32_t)((T - 1) * m), ctx->ipa_inv_scratch);
     k_fold_prep2<<<pgrid, 128, 0, ctx->stream>>>(G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_den2.as<fq_t>(), ctx->ipa_diff.as<affine_t>());
     k_fold_multi<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_diff.as<affine_t>(),
+                                                                       ctx->ipa_ops.as<uint8_t>(), no,
                                                                        ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>());
     batch_invert(ctx, ctx->stream, ctx->ipa_den.as<fq_t>(), (uint32_t)m, ctx->ipa_inv_scratch);
     k_fold_finish<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>(), m,

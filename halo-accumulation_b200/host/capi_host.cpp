@@ -23,7 +23,34 @@ int guarded(F&& f) {
     } catch (const std::exception& e) {
         g_host_error = e.what();
         return HALO_EINVAL;
+    } catch (...) {  // nothing unwinds across the C ABI
+        g_host_error = "unexpected internal exception";
+        return HALO_EINVAL;
     }
+}
+// Verifier-side inputs are raw limbs from the caller: canonical residues and points on the curve, or HALO_EINVAL
+// (see host/group.hpp "validation at the C boundary").
+void validate(const halo_eval_proof& pi) {
+    ensure(pi.lg_n <= HALO_MAX_LG, HALO_EINVAL, "proof: lg_n out of range");
+    for (uint32_t i = 0; i < pi.lg_n; i++)
+        ensure(point_valid(pi.Ls[i]) && point_valid(pi.Rs[i]), HALO_EINVAL, "proof: L / R is not a canonical point on the curve");
+    ensure(point_valid(pi.U), HALO_EINVAL, "proof: U is not a canonical point on the curve");
+    ensure(scalar_valid(pi.c), HALO_EINVAL, "proof: c is not a canonical scalar");
+    if (pi.hiding) {
+        ensure(point_valid(pi.C_bar), HALO_EINVAL, "proof: C_bar is not a canonical point on the curve");
+        ensure(scalar_valid(pi.w_prime), HALO_EINVAL, "proof: w' is not a canonical scalar");
+    }
+}
+void validate(const halo_instance& q) {
+    ensure(point_valid(q.C), HALO_EINVAL, "instance: C is not a canonical point on the curve");
+    ensure(scalar_valid(q.z) && scalar_valid(q.v), HALO_EINVAL, "instance: z / v is not a canonical scalar");
+    validate(q.pi);
+}
+void validate(const halo_accumulator& a) {
+    ensure(point_valid(a.C_bar) && point_valid(a.U0), HALO_EINVAL, "accumulator: C_bar / U_0 is not a canonical point on the curve");
+    ensure(scalar_valid(a.z) && scalar_valid(a.v) && scalar_valid(a.w) && scalar_valid(a.h0[0]) && scalar_valid(a.h0[1]), HALO_EINVAL,
+           "accumulator: z / v / w / h_0 is not a canonical scalar");
+    validate(a.pi);
 }
 PolyView poly_from(const uint64_t* c, uint64_t n) { return PolyView(reinterpret_cast<const PallasScalar*>(c), n); }
 }  // namespace
@@ -71,7 +98,11 @@ int halo_pcdl_open(halo_ctx* ctx, const uint64_t* coeffs, uint64_t n_coeffs, con
 int halo_pcdl_succinct_check(halo_ctx* ctx, const uint64_t C_jac[12], uint64_t d, const uint64_t z[4], const uint64_t v[4],
                              const halo_eval_proof* pi, uint64_t* xis_out, uint64_t U_out[12]) {
     return guarded([&] {
-        auto hu = pcdl::succinct_check(ctx, point_load(C_jac), d, scalar_load(z), scalar_load(v), pcdl::proof_from_c(*pi));
+        ensure(pi != nullptr, HALO_EINVAL, "null proof");
+        validate(*pi);
+        auto hu = pcdl::succinct_check(ctx, point_load_checked(C_jac, "C is not a canonical point on the curve"), d,
+                                       scalar_load_checked(z, "z is not a canonical scalar"),
+                                       scalar_load_checked(v, "v is not a canonical scalar"), pcdl::proof_from_c(*pi));
         if (xis_out) std::memcpy(xis_out, hu.first.xis.data(), hu.first.xis.size() * 32);
         if (U_out) point_store(U_out, hu.second);
     });
@@ -79,7 +110,13 @@ int halo_pcdl_succinct_check(halo_ctx* ctx, const uint64_t C_jac[12], uint64_t d
 
 int halo_pcdl_check(halo_ctx* ctx, const uint64_t C_jac[12], uint64_t d, const uint64_t z[4], const uint64_t v[4],
                     const halo_eval_proof* pi) {
-    return guarded([&] { pcdl::check(ctx, point_load(C_jac), d, scalar_load(z), scalar_load(v), pcdl::proof_from_c(*pi)); });
+    return guarded([&] {
+        ensure(pi != nullptr, HALO_EINVAL, "null proof");
+        validate(*pi);
+        pcdl::check(ctx, point_load_checked(C_jac, "C is not a canonical point on the curve"), d,
+                    scalar_load_checked(z, "z is not a canonical scalar"), scalar_load_checked(v, "v is not a canonical scalar"),
+                    pcdl::proof_from_c(*pi));
+    });
 }
 
 int halo_h_eval(const uint64_t* xis, uint32_t lg_n, const uint64_t z[4], uint64_t out[4]) {
@@ -93,8 +130,12 @@ int halo_h_eval(const uint64_t* xis, uint32_t lg_n, const uint64_t z[4], uint64_
 int halo_acc_prover(halo_ctx* ctx, uint64_t d, const halo_instance* qs, uint64_t m, const uint64_t h0[2][4], const uint64_t w[4],
                     const uint64_t* q, uint64_t n_q, const uint64_t w_bar[4], halo_accumulator* acc) {
     return guarded([&] {
+        ensure(qs != nullptr || m == 0, HALO_EINVAL, "null instance list");
         std::vector<acc::Instance> v;
-        for (uint64_t i = 0; i < m; i++) v.push_back(acc::instance_from_c(qs[i]));
+        for (uint64_t i = 0; i < m; i++) {
+            validate(qs[i]);
+            v.push_back(acc::instance_from_c(qs[i]));
+        }
         acc::Accumulator a = acc::prover(ctx, d, v, PallasPoly{scalar_load(h0[0]), scalar_load(h0[1])}, scalar_load(w),
                                          poly_from(q, n_q), scalar_load(w_bar));
         acc::accumulator_to_c(a, *acc);
@@ -103,14 +144,23 @@ int halo_acc_prover(halo_ctx* ctx, uint64_t d, const halo_instance* qs, uint64_t
 
 int halo_acc_verifier(halo_ctx* ctx, uint64_t d, const halo_instance* qs, uint64_t m, const halo_accumulator* acc) {
     return guarded([&] {
+        ensure(acc != nullptr && (qs != nullptr || m == 0), HALO_EINVAL, "null accumulator / instance list");
+        validate(*acc);
         std::vector<acc::Instance> v;
-        for (uint64_t i = 0; i < m; i++) v.push_back(acc::instance_from_c(qs[i]));
+        for (uint64_t i = 0; i < m; i++) {
+            validate(qs[i]);
+            v.push_back(acc::instance_from_c(qs[i]));
+        }
         acc::verifier(ctx, d, v, acc::accumulator_from_c(*acc));
     });
 }
 
 int halo_acc_decider(halo_ctx* ctx, const halo_accumulator* acc) {
-    return guarded([&] { acc::decider(ctx, acc::accumulator_from_c(*acc)); });
+    return guarded([&] {
+        ensure(acc != nullptr, HALO_EINVAL, "null accumulator");
+        validate(*acc);
+        acc::decider(ctx, acc::accumulator_from_c(*acc));
+    });
 }
 
 void halo_acc_to_instance(const halo_accumulator* acc, halo_instance* q) {

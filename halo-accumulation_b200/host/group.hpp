@@ -70,6 +70,44 @@ inline void point_store(uint64_t* jac12, const PallasPoint& a) {
     xyzz_to_jac(j, a.p);
     std::memcpy(jac12, &j, 96);
 }
+// ---- validation at the C boundary ------------------------------------------------------------------
+// The reference's types cannot hold a non-canonical residue or an off-curve point (arkworks validates when a value is
+// deserialised, and every in-memory value is built by field / group operations).  Raw limbs arriving through the C ABI
+// carry no such guarantee, so the verifier-side entry points check them once: limbs < modulus, and for a Jacobian point
+// z == 0 (infinity) or Y^2 = X^3 + 5 Z^6.  Failure is HALO_EINVAL (malformed input), never a verifier decision.
+template <class P>
+inline bool fp_is_canonical(const fp_t<P>& a) {
+    uint32_t m[8], t[8];
+    fp_mod_limbs<P>(m);
+    return sub8(t, a.v, m) != 0;  // borrow <=> a < modulus
+}
+inline bool scalar_valid(const uint64_t* p) { return fp_is_canonical(scalar_load(p)); }
+inline bool point_valid(const uint64_t* jac12) {
+    jac_t j;
+    std::memcpy(&j, jac12, 96);
+    if (!fp_is_canonical(j.x) || !fp_is_canonical(j.y) || !fp_is_canonical(j.z)) return false;
+    if (fp_is_zero(j.z)) return true;  // infinity (arkworks: any (x, y, 0))
+    fq_t lhs, rhs, z2, z6, five;
+    fp_sqr(lhs, j.y);
+    fp_sqr(rhs, j.x);
+    fp_mul(rhs, rhs, j.x);
+    fp_sqr(z2, j.z);
+    fp_sqr(z6, z2);
+    fp_mul(z6, z6, z2);
+    fp_from_u32(five, 5);
+    fp_mul(z6, z6, five);
+    fp_add(rhs, rhs, z6);
+    return fp_eq(lhs, rhs);
+}
+inline PallasScalar scalar_load_checked(const uint64_t* p, const char* what) {
+    ensure(p != nullptr && scalar_valid(p), HALO_EINVAL, what);
+    return scalar_load(p);
+}
+inline PallasPoint point_load_checked(const uint64_t* jac12, const char* what) {
+    ensure(jac12 != nullptr && point_valid(jac12), HALO_EINVAL, what);
+    return point_load(jac12);
+}
+
 inline PallasPoint point_zero() { PallasPoint r; xyzz_set_inf(r.p); return r; }
 inline PallasPoint operator+(const PallasPoint& a, const PallasPoint& b) { PallasPoint r = a; xyzz_add(r.p, b.p); return r; }
 inline PallasPoint operator-(const PallasPoint& a) { PallasPoint r = a; if (!xyzz_is_inf(r.p)) xyzz_neg(r.p); return r; }

@@ -20,7 +20,8 @@
  * context.  Verifier-style rejections are NOT errors at this level: the library returns points and
  * scalars, the host layer above (pcdl / acc) raises the reference's `ensure!` failures.
  * A context is bound to one CUDA device and one stream; it is not thread-safe (the reference is
- * single-threaded); calls are synchronous unless the name ends in `_async`.  All host buffers are
+ * single-threaded), but different contexts may be used from different host threads at the same time, on the same
+ * device or not; calls are synchronous except the `_submit` / `_collect` pairs.  All host buffers are
  * owned by the caller; all device memory is owned by the context.  There is no CPU fallback: if
  * no CUDA device is usable, halo_ctx_create fails with HALO_ECUDA.
  */
@@ -38,7 +39,7 @@ extern "C" {
 #define HALO_EINVAL (-1) /* n not a power of two / exceeds the context's max_n (pcdl.rs:102-104, :261-262) */
 #define HALO_ELEN (-2)   /* length mismatch (pedersen.rs:7-12) */
 #define HALO_ECUDA (-3)  /* CUDA runtime failure; see halo_last_error */
-#define HALO_ENCCL (-4)
+#define HALO_ENCCL (-4)  /* NCCL failure (libnccl.so.2 missing, communicator error, ranks disagreeing on the MSM plan) */
 #define HALO_ENOMEM (-5)
 #define HALO_ESTATE (-6) /* call out of order (e.g. generators not loaded) */
 #define HALO_EIO (-7)    /* generator store: file cannot be opened / read / written */
@@ -122,14 +123,63 @@ int halo_msm_gens_collect(halo_ctx *ctx, int ticket, uint64_t out_jac[12]);
 int halo_msm_gens_resident(halo_ctx *ctx, const void *d_scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]);
 int halo_msm_gens_submit_resident(halo_ctx *ctx, const void *d_scalars, uint64_t off, uint64_t n, int *ticket);
 
-/* Sum of g Jacobian points on the host, in index order: combines the per-GPU partial MSM results after the
- * single all-gather of the sharded MSM. */
+/* Sum of g Jacobian points on the host, in index order. */
 int halo_points_sum(const uint64_t *points_jac /*[g][12]*/, uint64_t g, uint64_t out_jac[12]);
 /* Projective equality of two Jacobian points (cross-multiplied, as `==` on arkworks' Projective): 1 / 0. */
 int halo_points_equal(const uint64_t a_jac[12], const uint64_t b_jac[12]);
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of this library is launched on). */
 int halo_timer_start(halo_ctx *ctx);
 int halo_timer_stop(halo_ctx *ctx, float *elapsed_ms);
+
+/* ---- multi-GPU: the MSM sharded by point slice ---------------------------------------------------------
+ * Only the MSM shards.  Rank r of g holds the contiguous slice [first_r, first_r + count_r) of the generators
+ * (halo_comm_slice) and the matching slice of the scalars; every rank runs the Pippenger on its slice and the partial
+ * results meet in ONE ncclAllGather over NVLink / NVSwitch, enqueued by the library on the context's stream; the ranks'
+ * partials are added in rank order and finished once, so every rank returns the same point.  Replaces group.rs:24-26 at scale.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2", or the path in HALO_NCCL_LIB) the first time one of these is called.
+ *
+ * Rank form: one process or thread per GPU (torchrun, MPI, a thread pool).  Rank 0 calls halo_comm_unique_id, the caller
+ * distributes the 128 bytes by its own means, then EVERY rank calls halo_comm_init_rank (a collective: it returns when all
+ * ranks have joined).  Every halo_msm_gens_sharded* / halo_comm_allgather_sum call is a collective as well: all ranks must
+ * make it, in the same order, with the same n_global. */
+#define HALO_COMM_ID_BYTES 128
+typedef struct halo_comm halo_comm;
+int halo_comm_unique_id(uint8_t id[HALO_COMM_ID_BYTES]);
+int halo_comm_init_rank(halo_ctx *ctx, const uint8_t id[HALO_COMM_ID_BYTES], int nranks, int rank, halo_comm **out);
+void halo_comm_destroy(halo_comm *comm);
+int halo_comm_rank(const halo_comm *comm);
+int halo_comm_size(const halo_comm *comm);
+int halo_nccl_version(void); /* e.g. 22809; 0 if NCCL cannot be loaded */
+/* The contiguous point slice of rank `rank` of `size` over n_total points: [*first, *first + *count). */
+void halo_comm_slice(uint64_t n_total, int rank, int size, uint64_t *first, uint64_t *count);
+/* Derives this rank's slice of the n_total generators (halo_derive_generators_range over halo_comm_slice). */
+int halo_comm_derive_generators(halo_comm *comm, uint64_t n_total);
+/* halo_precompute_generators with a window chosen from the LARGEST slice, so that every rank builds tables for the same
+ * plan (window = 0: automatic). */
+int halo_comm_precompute_generators(halo_comm *comm, int window);
+/* sum over ALL ranks of sum_{i < n_local} local_scalars[i] * G_{first_rank + off_local + i}: this rank contributes its
+ * n_local points (0 allowed); n_global = the total number of points of the whole MSM (sum of the ranks' n_local), from
+ * which every rank derives the same window plan.  Result on every rank. */
+int halo_msm_gens_sharded(halo_comm *comm, const uint64_t *local_scalars /*[n_local][4]*/, uint64_t off_local, uint64_t n_local,
+                          uint64_t n_global, uint64_t out_jac[12]);
+/* Same with this rank's scalars already on its device (CUDA pointer). */
+int halo_msm_gens_sharded_resident(halo_comm *comm, const void *d_local_scalars, uint64_t off_local, uint64_t n_local,
+                                   uint64_t n_global, uint64_t out_jac[12]);
+/* All-gather of one Jacobian point per rank and their sum in rank order: combines per-rank results that were computed by
+ * other calls (e.g. the pipelined halo_msm_gens_submit / _collect on every rank). */
+int halo_comm_allgather_sum(halo_comm *comm, const uint64_t point_jac[12], uint64_t out_jac[12]);
+
+/* Node form: ONE caller thread, g devices.  The library owns a context, a communicator (ncclCommInitAll) and a worker
+ * thread per device, derives each device's slice of the n_total generators and (precompute_window >= 0; 0 = automatic
+ * window) its FIXED-base tables.  halo_mgpu_msm_gens then is the multi-GPU body of `point_dot_affine` over GS[0..n):
+ * every device copies its part of the caller's scalar vector, runs its slice and joins the all-gather. */
+typedef struct halo_mgpu halo_mgpu;
+int halo_mgpu_create(const int *devices, int g, uint64_t n_total, int precompute_window, halo_mgpu **out);
+void halo_mgpu_destroy(halo_mgpu *m);
+int halo_mgpu_size(const halo_mgpu *m);
+halo_ctx *halo_mgpu_ctx(halo_mgpu *m, int i);
+const char *halo_mgpu_last_error(halo_mgpu *m);
+int halo_mgpu_msm_gens(halo_mgpu *m, const uint64_t *scalars /*[n][4]*/, uint64_t n, uint64_t out_jac[12]);
 
 /* ---- scalar vectors -------------------------------------------------------------------------------- */
 /* sum_i xs[i] * ys[i] in Fr.  Replaces group.rs:13-15 `scalar_dot`. */

@@ -443,6 +443,116 @@ void orc_derive_points(u64 start, u64 count, u64 *out_affine) {
     }
 }
 
+/* Batched normalisation (Montgomery's trick): one inversion per block instead of one per point. */
+static void jac_batch_to_affine(aff_t *out, const jac_t *in, int cnt) {
+    u64 pre[256][4], run[4], inv[4], zi[4], zi2[4], zi3[4];
+    fq_one(run);
+    for (int i = 0; i < cnt; i++) {
+        fq_copy(pre[i], run);
+        if (!jac_is_inf(&in[i])) fq_mul(run, run, in[i].z);
+    }
+    fq_inv(inv, run);
+    for (int i = cnt - 1; i >= 0; i--) {
+        if (jac_is_inf(&in[i])) {
+            fq_zero(out[i].x);
+            fq_zero(out[i].y);
+            continue;
+        }
+        fq_mul(zi, inv, pre[i]);
+        fq_mul(inv, inv, in[i].z);
+        fq_sqr(zi2, zi);
+        fq_mul(zi3, zi2, zi);
+        fq_mul(out[i].x, in[i].x, zi2);
+        fq_mul(out[i].y, in[i].y, zi3);
+    }
+}
+
+/* The same points by a fixed-base table of the generator (16 windows of 16 bits: e * 65536^w * (-1, 2), 64 MiB), 16 mixed
+ * additions per point instead of a 255-step double-and-add, normalised in blocks: the CPU arm of the benchmark needs 2^24
+ * bases and must not spend minutes deriving them.  tests/test_oracle_golden.py checks it against orc_derive_points and
+ * consts.rs. */
+void orc_derive_points_fast(u64 start, u64 count, u64 *out_affine) {
+    enum { TW = 16, TE = 65535, BLK = 256 };
+    aff_t *table = (aff_t *)malloc((size_t)TW * TE * sizeof(aff_t));
+    jac_t *col = (jac_t *)malloc((size_t)TE * sizeof(jac_t));
+    jac_t base;
+    fq_copy(base.x, GEN_X);
+    fq_copy(base.y, GEN_Y);
+    fq_one(base.z);
+    for (int w = 0; w < TW; w++) {
+        jac_t acc = base;
+        for (int e = 0; e < TE; e++) { /* (e + 1) * 65536^w * G */
+            col[e] = acc;
+            jac_add(&acc, &acc, &base);
+        }
+        base = acc; /* 65536 * previous base */
+#pragma omp parallel for schedule(static)
+        for (int e0 = 0; e0 < TE; e0 += BLK) jac_batch_to_affine(&table[(size_t)w * TE + e0], &col[e0], TE - e0 < BLK ? TE - e0 : BLK);
+    }
+    free(col);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long i0 = 0; i0 < (long long)count; i0 += BLK) {
+        jac_t pts[BLK];
+        int cnt = (long long)count - i0 < BLK ? (int)((long long)count - i0) : BLK;
+        for (int j = 0; j < cnt; j++) {
+            u64 k = start + (u64)i0 + (u64)j;
+            u8 msg[sizeof(GENESIS) - 1 + 8];
+            memcpy(msg, GENESIS, sizeof(GENESIS) - 1);
+            for (int b = 0; b < 8; b++) msg[sizeof(GENESIS) - 1 + b] = (u8)(k >> (8 * b));
+            u8 dg[32];
+            orc_sha3_256(msg, sizeof msg, dg);
+            u64 sm[4], sc[4];
+            fr_from_le_bytes_mod_order(sm, dg);
+            fr_to_canon(sc, sm);
+            jac_set_inf(&pts[j]);
+            for (int w = 0; w < TW; w++) {
+                unsigned e = (unsigned)(sc[w >> 2] >> (16 * (w & 3))) & 0xffffu;
+                if (e) jac_add_affine(&pts[j], &pts[j], &table[(size_t)w * TE + (e - 1)]);
+            }
+        }
+        jac_batch_to_affine((aff_t *)(out_affine + 8 * (u64)i0), pts, cnt);
+    }
+    free(table);
+}
+
+/* Size-independent property of an MSM over DERIVED generators: G_i = s_{i+2} * (-1, 2) (main.rs:18-32), hence
+ *   sum_i a_i G_{first+i} = (sum_i a_i s_{first+i+2} mod r) * (-1, 2)
+ * -- one SHA3 and one Fr multiplication per point instead of a Pippenger.  Used to check MSM results at sizes and shard
+ * layouts where running the full CPU MSM on every rank would take minutes. */
+void orc_msm_derived_by_dlog(u64 first, const u64 *scalars, u64 n, int threads, u64 out[12]) {
+    if (threads < 1) threads = 1;
+    u64 *partial = (u64 *)calloc((size_t)threads * 4, sizeof(u64));
+#pragma omp parallel num_threads(threads)
+    {
+        int t = omp_get_thread_num(), nt = omp_get_num_threads();
+        u64 acc[4], prod[4];
+        fr_zero(acc);
+        for (u64 i = (u64)t; i < n; i += (u64)nt) {
+            u64 k = first + i + 2;
+            u8 msg[sizeof(GENESIS) - 1 + 8];
+            memcpy(msg, GENESIS, sizeof(GENESIS) - 1);
+            for (int b = 0; b < 8; b++) msg[sizeof(GENESIS) - 1 + b] = (u8)(k >> (8 * b));
+            u8 dg[32];
+            orc_sha3_256(msg, sizeof msg, dg);
+            u64 s[4];
+            fr_from_le_bytes_mod_order(s, dg);
+            fr_mul(prod, s, scalars + 4 * i);
+            fr_add(acc, acc, prod);
+        }
+        fr_copy(partial + 4 * t, acc);
+    }
+    u64 tot[4];
+    fr_zero(tot);
+    for (int t = 0; t < threads; t++) fr_add(tot, tot, partial + 4 * t);
+    free(partial);
+    jac_t g, r;
+    fq_copy(g.x, GEN_X);
+    fq_copy(g.y, GEN_Y);
+    fq_one(g.z);
+    jac_mul(&r, &g, tot);
+    memcpy(out, &r, 96);
+}
+
 static jac_t PP_S, PP_H;
 static aff_t *PP_GS = NULL;
 static u64 PP_N = 0;
@@ -477,11 +587,11 @@ u64 orc_params_n(void) { return PP_N; }
 /* ------------------------------------------------------------------------------------------ */
 static int ceil_log2(u64 n) { int l = 0; while (((u64)1 << l) < n) l++; return l; }
 
-static void msm_window(const aff_t *bases, const u8 *inf, const int32_t *digits, u64 n, int W, int w, int c, jac_t *out) {
-    u64 nb = (u64)1 << (c - 1);
-    jac_t *buckets = (jac_t *)malloc(nb * sizeof(jac_t));
+/* One window of arkworks' msm_bigint_wnaf: bucket accumulation over the points [lo, hi), then (reduce != 0) the running-sum
+ * sweep from the top bucket.  reduce == 0 leaves the raw buckets in `buckets` for a merge (see orc_msm_affine). */
+static void msm_window_fill(const aff_t *bases, const u8 *inf, const int32_t *digits, u64 lo, u64 hi, int W, int w, jac_t *buckets, u64 nb) {
     for (u64 b = 0; b < nb; b++) jac_set_inf(&buckets[b]);
-    for (u64 i = 0; i < n; i++) {
+    for (u64 i = lo; i < hi; i++) {
         int32_t d = digits[i * W + w];
         if (d == 0 || (inf && inf[i])) continue;
         if (d > 0) {
@@ -492,6 +602,8 @@ static void msm_window(const aff_t *bases, const u8 *inf, const int32_t *digits,
             jac_add_affine(&buckets[-d - 1], &buckets[-d - 1], &nq);
         }
     }
+}
+static void msm_window_sweep(const jac_t *buckets, u64 nb, jac_t *out) {
     jac_t running, res;
     jac_set_inf(&running);
     jac_set_inf(&res);
@@ -499,8 +611,14 @@ static void msm_window(const aff_t *bases, const u8 *inf, const int32_t *digits,
         jac_add(&running, &running, &buckets[b]);
         jac_add(&res, &res, &running);
     }
-    free(buckets);
     *out = res;
+}
+static void msm_window(const aff_t *bases, const u8 *inf, const int32_t *digits, u64 n, int W, int w, int c, jac_t *out) {
+    u64 nb = (u64)1 << (c - 1);
+    jac_t *buckets = (jac_t *)malloc(nb * sizeof(jac_t));
+    msm_window_fill(bases, inf, digits, 0, n, W, w, buckets, nb);
+    msm_window_sweep(buckets, nb, out);
+    free(buckets);
 }
 
 void orc_msm_affine(const u64 *bases_affine, const u8 *inf, const u64 *scalars, u64 n, int threads, u64 out[12]) {
@@ -527,8 +645,39 @@ void orc_msm_affine(const u64 *bases_affine, const u8 *inf, const u64 *scalars, 
         }
     }
     jac_t *wsum = (jac_t *)malloc(W * sizeof(jac_t));
+    /* arkworks' `parallel` feature runs one window per thread (the reference leaves it off: threads <= 1).  With more
+     * threads than windows (15 windows at n = 2^24, 16-32 host threads), or fewer windows than a multiple of the thread
+     * count, whole cores would idle; so each window is also cut into S point chunks with their own bucket arrays, merged
+     * bucket by bucket before the window's running-sum sweep.  Same group element; only the CPU baseline's utilisation
+     * changes. */
+    int S = 1;
+    if (threads > 1 && n >= ((u64)1 << 16)) {
+        S = (threads + W - 1) / W;
+        if (W % threads != 0 && S < 2) S = 2;
+        if (S > 8) S = 8;
+    }
+    if (S == 1) {
 #pragma omp parallel for schedule(dynamic, 1) if (threads > 1) num_threads(threads > 1 ? threads : 1)
-    for (int w = 0; w < W; w++) msm_window((const aff_t *)bases_affine, inf, digits, n, W, w, c, &wsum[w]);
+        for (int w = 0; w < W; w++) msm_window((const aff_t *)bases_affine, inf, digits, n, W, w, c, &wsum[w]);
+    } else {
+        u64 nb = (u64)1 << (c - 1);
+        jac_t *bk = (jac_t *)malloc((u64)W * S * nb * sizeof(jac_t));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+        for (int t = 0; t < W * S; t++) {
+            int w = t / S, sidx = t % S;
+            u64 lo = n * (u64)sidx / S, hi = n * (u64)(sidx + 1) / S;
+            msm_window_fill((const aff_t *)bases_affine, inf, digits, lo, hi, W, w, bk + (u64)t * nb, nb);
+        }
+#pragma omp parallel for schedule(static) num_threads(threads)
+        for (long long j = 0; j < (long long)((u64)W * nb); j++) {
+            u64 w = (u64)j / nb, b = (u64)j % nb;
+            jac_t *dst = bk + (w * S) * nb + b;
+            for (int sidx = 1; sidx < S; sidx++) jac_add(dst, dst, bk + (w * S + sidx) * nb + b);
+        }
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+        for (int w = 0; w < W; w++) msm_window_sweep(bk + ((u64)w * S) * nb, nb, &wsum[w]);
+        free(bk);
+    }
     for (int w = W - 1; w >= 1; w--) {
         jac_add(&total, &total, &wsum[w]);
         for (int k = 0; k < c; k++) jac_double(&total, &total);

@@ -106,6 +106,11 @@ void orc_pt_serialize_compressed(const uint64_t p[12], uint8_t out[33]);
 /* ---- public parameters: main.rs:18-45 ---- */
 /* P_k = [SHA3-256(genesis || k as u64 LE) mod r] * (-1, 2), k in [start, start+count) -> affine */
 void orc_derive_points(uint64_t start, uint64_t count, uint64_t *out_affine /*[count][8]*/);
+/* same points through a fixed-base table of (-1, 2) (setup of the benchmark's CPU arm; checked against the line above) */
+void orc_derive_points_fast(uint64_t start, uint64_t count, uint64_t *out_affine /*[count][8]*/);
+/* sum_i scalars[i] * G_{first+i} for the DERIVED generators via their known discrete logs:
+ * (sum_i scalars[i] * s_{first+i+2}) * (-1, 2).  Property check, cost O(n) hashes. */
+void orc_msm_derived_by_dlog(uint64_t first, const uint64_t *scalars, uint64_t n, int threads, uint64_t out[12]);
 /* S = P_0, H = P_1 (Jacobian with z = 1), GS[i] = P_{i+2}  */
 void orc_set_params(const uint64_t S[12], const uint64_t H[12], const uint64_t *gs_affine, uint64_t n);
 void orc_derive_params(uint64_t n); /* derive and install S, H, GS[0..n) */

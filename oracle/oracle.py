@@ -225,6 +225,21 @@ def derive_points(start, count):
     return out
 
 
+def derive_points_fast(start, count):
+    """orc_derive_points through a fixed-base table (setup of the benchmark's CPU arm)."""
+    out = np.zeros((count, 8), dtype=np.uint64)
+    lib().orc_derive_points_fast(C.c_uint64(start), C.c_uint64(count), _p(out))
+    return out
+
+
+def msm_derived_by_dlog(first, scalars, threads=1):
+    """sum_i scalars[i] * G_{first+i} over the derived generators through their known discrete logs (property check)."""
+    scalars = _arr(scalars).reshape(-1, 4)
+    out = np.zeros(12, dtype=np.uint64)
+    lib().orc_msm_derived_by_dlog(C.c_uint64(first), _p(scalars), C.c_uint64(scalars.shape[0]), int(threads), _p(out))
+    return out
+
+
 def derive_params(n):
     lib().orc_derive_params(C.c_uint64(n))
 

@@ -1,5 +1,8 @@
 """BASELINE config 4: ASDL IVC chain -- k accumulation steps (random_instance + prover, benches/acc.rs:76-98) followed
-by the fast path (k verifiers + one decider, benches/acc.rs:64-74) at n = 2^lg.  Times each phase on the GPU path."""
+by the fast path (k verifiers + one decider, benches/acc.rs:64-74) at n = 2^lg.  Times each phase on the GPU path, then
+(outside the timed regions) hands the chain to the CPU oracle: acc_verifier on three spot steps (first, middle, last) and
+acc_decider on the final accumulator.  `all_accept` is the conjunction of the GPU path's own k verifiers + decider (they
+raise on a rejection) and of the oracle's decisions."""
 import json, sys, time
 import numpy as np
 sys.path.insert(0, ".")
@@ -42,6 +45,19 @@ for qs, ac in zip(qss, accs):
     acc.verifier(ctx, d, qs, ac)
 t_ver = time.perf_counter() - t
 t = time.perf_counter(); acc.decider(ctx, accs[-1]); t_dec = time.perf_counter() - t
+# ---- the oracle's view of the same chain (checker only, untimed) ----
+from oracle import oracle as O
+S, Hh = ctx.get_SH()
+O.set_params(S, Hh, ctx.get_generators(0, n))
+T = max(1, O.lib().orc_num_threads())
+as_o = lambda x, cls: cls.from_buffer_copy(bytes(x))
+spots = sorted({0, k // 2, k - 1})
+oracle_verifier = {s: O.acc_verifier(d, [as_o(q, O.Instance) for q in qss[s]], as_o(accs[s], O.Accumulator)) for s in spots}
+t = time.perf_counter(); oracle_decider = O.acc_decider(as_o(accs[-1], O.Accumulator), threads=T); t_odec = time.perf_counter() - t
+all_accept = all(rc == 0 for rc in oracle_verifier.values()) and oracle_decider == 0
 print(json.dumps({"config": f"ivc_chain_2^{lg}_k{k}", "setup_s": setup_s, "random_instance_ms": t_inst / k * 1e3, "prover_ms": t_prov / k * 1e3,
                   "verifier_ms": t_ver / k * 1e3, "decider_ms": t_dec * 1e3, "fast_path_total_s": t_ver + t_dec,
-                  "chain_total_s": t_inst + t_prov, "kernel_launches": ctx.kernel_launches(), "all_accept": True}))
+                  "chain_total_s": t_inst + t_prov, "kernel_launches": ctx.kernel_launches(), "all_accept": all_accept,
+                  "oracle": {"acc_verifier_rc_at_steps": {str(s): rc for s, rc in oracle_verifier.items()}, "acc_decider_rc": oracle_decider,
+                             "acc_decider_cpu_ms": t_odec * 1e3, "threads": T}}))
+assert all_accept, "the oracle rejects the GPU chain"

@@ -187,6 +187,61 @@ def test_pcdl_full_check_rejects_wrong_U(env):
     assert e.value.code == rc
 
 
+def test_malformed_inputs_are_refused_at_the_boundary(env):
+    """Raw limbs crossing the C ABI into the verifier-side calls are validated once (canonical residues, points on the curve):
+    arkworks types cannot hold anything else, so such input is HALO_EINVAL, not an accept / reject decision."""
+    from halo_accumulation_b200 import HaloError
+
+    ctx, O, pcdl, acc = env["ctx"], env["O"], env["pcdl"], env["acc"]
+    n, d = 64, 63
+    q, _ = _random_instance(env, d, 8800)
+    h0, (w, wb), qq = O.random_scalars(2, 8801), O.random_scalars(2, 8802), O.random_scalars(n - 1, 8803)
+    a = acc.prover(ctx, d, [q], h0, w, qq, wb)
+    acc.verifier(ctx, d, [q], a)
+    pi = q.pi
+    Cm, z, v = np.array(q.C), np.array(q.z), np.array(q.v)
+    pcdl.check(ctx, Cm, d, z, v, pi)
+
+    def refused(f):
+        with pytest.raises(HaloError) as e:
+            f()
+        assert e.value.code == -1, e.value.code
+
+    bad = type(pi).from_buffer_copy(bytes(pi))
+    bad.Ls[2][5] ^= 4                                    # y of L_2: off the curve
+    refused(lambda: pcdl.check(ctx, Cm, d, z, v, bad))
+    refused(lambda: pcdl.succinct_check(ctx, Cm, d, z, v, bad))
+    bad = type(pi).from_buffer_copy(bytes(pi))
+    bad.U[3] = 0xFFFFFFFFFFFFFFFF                        # x >= p: not a canonical residue
+    refused(lambda: pcdl.check(ctx, Cm, d, z, v, bad))
+    bad = type(pi).from_buffer_copy(bytes(pi))
+    bad.c[3] = 0x7FFFFFFFFFFFFFFF                        # scalar >= r
+    refused(lambda: pcdl.check(ctx, Cm, d, z, v, bad))
+    Cbad = Cm.copy()
+    Cbad[0] ^= np.uint64(1)
+    refused(lambda: pcdl.check(ctx, Cbad, d, z, v, pi))
+    zbad = z.copy()
+    zbad[3] = np.uint64(0x4000000000000000) + np.uint64(1 << 40)  # >= r
+    refused(lambda: pcdl.check(ctx, Cm, d, zbad, v, pi))
+    abad = type(a).from_buffer_copy(bytes(a))
+    abad.U0[1] ^= 2
+    refused(lambda: acc.verifier(ctx, d, [q], abad))
+    refused(lambda: acc.decider(ctx, abad))
+    abad = type(a).from_buffer_copy(bytes(a))
+    abad.C_bar[8] ^= 1                                   # z coordinate of a Jacobian point: no longer on the curve
+    refused(lambda: acc.decider(ctx, abad))
+    qbad = type(q).from_buffer_copy(bytes(q))
+    qbad.pi.Rs[0][0] ^= 1
+    refused(lambda: acc.verifier(ctx, d, [qbad], a))
+    refused(lambda: acc.prover(ctx, d, [qbad], h0, w, qq, wb))
+    # infinity is a valid point (arkworks: z = 0): a decision, not an error
+    inf = type(pi).from_buffer_copy(bytes(pi))
+    C.memset(inf.Ls[1], 0, 96)
+    with pytest.raises(pcdl.Rejected):
+        pcdl.check(ctx, Cm, d, z, v, inf)
+    acc.verifier(ctx, d, [q], a)                         # the context is still usable
+
+
 def test_pcdl_argument_errors(env):
     import halo_accumulation_b200 as H
 
@@ -316,11 +371,15 @@ def test_open_and_full_check_2_20(ctx, oracle):
         pcdl.check(ctx, Cm, d, z, v, pi)
         assert O.pcdl_check(Cm, d, z, v, O.EvalProof.from_buffer_copy(bytes(pi)), threads=16) == 0
         bad = type(pi).from_buffer_copy(bytes(pi))
-        bad.Rs[7][0] ^= 1
+        C.memmove(bad.Rs[7], bytes(pi.Ls[7]), 96)  # a valid point in the wrong place: a verifier decision, same on both sides
         with pytest.raises(pcdl.Rejected) as e:
             pcdl.check(ctx, Cm, d, z, v, bad)
-        # (the flipped limb may take the point off the curve; both sides only need to reject at the same check)
-        assert e.value.code == O.pcdl_check(Cm, d, z, v, O.EvalProof.from_buffer_copy(bytes(bad)), threads=16)
+        assert e.value.code == O.pcdl_check(Cm, d, z, v, O.EvalProof.from_buffer_copy(bytes(bad)), threads=16) == -10
+        bad.Rs[7][0] ^= 1  # off the curve: malformed input (HALO_EINVAL), not a decision
+        from halo_accumulation_b200 import HaloError
+        with pytest.raises(HaloError) as e:
+            pcdl.check(ctx, Cm, d, z, v, bad)
+        assert e.value.code == -1
         # hiding variant (deferred head rounds over the FIXED-base tables, blinding polynomial, w'): accepted by both
         w, wb = O.random_scalars(2, 5)
         q = O.random_scalars(p.shape[0] - 1, 6)
