@@ -241,6 +241,8 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "split_first_16ths")) ctx->tune_split_first_16ths = value < 1 ? 1 : value > 15 ? 15 : value;
     else if (!strcmp(key, "sort_ahead")) ctx->tune_sort_ahead = value;
     else if (!strcmp(key, "stage_pageable")) ctx->tune_stage_pageable = value;
+    else if (!strcmp(key, "reduce_quad")) ctx->tune_reduce_quad = value;
+    else if (!strcmp(key, "pair_bwd_async")) ctx->tune_pair_bwd_async = value;
     else if (!strcmp(key, "ipa_defer_rounds")) ctx->tune_ipa_defer = value;
     else if (!strcmp(key, "ipa_two_lanes")) ctx->tune_ipa_two_lanes = value;
     else if (!strcmp(key, "ipa_freeze_len")) ctx->tune_ipa_freeze_len = value;

@@ -169,7 +169,8 @@ void sharded_msm(halo_comm* c, const fr_t* d_scalars, uint64_t off_local, uint64
     halo_ctx* ctx = c->ctx;
     NcclApi* api = nccl_api();
     const bool fixed = comm_use_fixed(c, n_global);
-    const MsmPlan plan = comm_plan(c, n_global, fixed);
+    MsmPlan plan = comm_plan(c, n_global, fixed);
+    if (plan.red_quad != (ctx->tune_reduce_quad != 0)) plan_set_reduce(plan, ctx->tune_reduce_quad != 0);
     const int nwin = plan.fixed ? 1 : plan.W;
     const int used = 1 + 3 * nwin;
     xyzz_t* d_send = c->send.as<xyzz_t>();

@@ -106,7 +106,9 @@ struct MsmPlan {
     // bucket reduction geometry: slabs of red_T << red_log_s buckets
     int red_T = 0, red_log_s = 0;
     uint32_t red_slabs = 0;
+    bool red_quad = true;  // k_reduce_slabs_quad (quad-cooperative additions) or the one-lane k_reduce_slabs
 };
+void plan_set_reduce(MsmPlan& p, bool quad);
 MsmPlan msm_make_plan(uint64_t n, int force_c);
 
 struct MsmWorkspace {
@@ -191,12 +193,15 @@ struct halo_ctx {
     int tune_acc_static = 0, tune_acc_blocks_per_sm = 0;
     bool force_two_lanes = false;  // run a pair of large MSMs (deferred IPA rounds) on the two lanes as well
     int tune_ipa_two_lanes = 1, tune_ipa_freeze_len = 0;
-    int tune_ipa_frozen_c = 10;  // window of the frozen-tail MSMs (8192 points, latency bound in the bucket reduction): 0.78 -> 0.71 ms per round vs c = 12
+    int tune_ipa_frozen_c = 11;  // window of the frozen-tail MSMs (8192 points): round 1 measured 10 best with the one-lane single-slab reduction;
+                                 // with the two-level quad reduction 11 is (8192-point MSM 0.46 / 0.38 / 0.41 ms at c = 10 / 11 / 12)
     int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
     int tune_sort_ahead = 1;  // pipelined submit: CTAs per SM of the counting sort running beside the previous MSM (0: off)
     int tune_split_blocking = 23;  // halo_msm_gens: two point slices through the pipeline slots for n >= 2^this (0: never)
     int tune_split_first_16ths = 5;  // size of the first slice in sixteenths of n: its H2D copy is exposed, the second slice's copy hides behind
                                      // the first slice's kernels (2^24: 8 -> 41.1 ms, 6 -> 38.4, 5 -> 38.2, 4 -> 39.7, 3 -> 41.0; scripts/gpu_split_probe.py)
+    int tune_pair_bwd_async = 0;  // pass 0 of the pair tree: 1 = cp.async-staged operands (k_pair_bwd0; measured +-1 %: profiles/r02_pair_bwd_async_ab.jsonl), 0 = per-lane gathers
+    int tune_reduce_quad = 1;   // 0: one-lane bucket reduction (k_reduce_slabs), for A/B measurements
     int tune_pair_passes = -1;  // -1: automatic; 0: XYZZ accumulation only; P > 0: force P pair-tree passes
     uint64_t kernel_launches = 0;
     halo::Timings last;

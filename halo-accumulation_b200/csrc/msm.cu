@@ -27,6 +27,7 @@ namespace halo {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
+void plan_set_reduce(MsmPlan& p, bool quad);
 static void plan_fill(MsmPlan& p, int c, bool fixed) {
     p.c = c;
     p.fixed = fixed;
@@ -36,11 +37,41 @@ static void plan_fill(MsmPlan& p, int c, bool fixed) {
     // near-equal widths summing to 255; the low windows take the remainder so the top window is the narrow one
     int base = 255 / p.W, rem = 255 - base * p.W;
     for (int w = 0; w < MSM_MAX_WINDOWS; w++) p.widths.w[w] = w < p.W ? (uint8_t)(base + (w < rem ? 1 : 0)) : 0;
-    // bucket reduction geometry: slabs of T * s buckets, T threads per CTA
-    p.red_T = p.M < 256u ? (int)p.M : 256;
+    plan_set_reduce(p, true);
+}
+// bucket reduction geometry: slabs of T * s buckets, T (logical) threads per CTA.  quad: k_reduce_slabs_quad (T <= 128
+// quads, slabs of up to 2048 buckets); else k_reduce_slabs (T <= 256 threads).
+void plan_set_reduce(MsmPlan& p, bool quad) {
+    // Measured (scripts/gpu_reduce_probe.py, profiles/r02_reduce_*): the reduction of one slab is a job for ONE CTA, and a
+    // CTA's arithmetic runs on one SM (~0.4 G multiplications/s): with a slab per window, a 22-window MSM of 2048 buckets
+    // per window kept 22 of the 148 SMs busy for 0.3 ms.  So windows of >= 1024 buckets are cut into slabs until every SM
+    // has a CTA or two; a second launch (one CTA per window, 0.07 ms at 32-128 slabs, 0.31 ms at 1024) combines the slab
+    // partials, hence at most 128 slabs per window and none for small windows.  The quad-cooperative kernel has the
+    // shorter dependent chain but issues ~40 % more instructions per addition: it wins while the reduction is latency
+    // bound (<= 3 * 2^17 buckets in all), the one-lane kernel wins beyond (2^22 variable base: 0.69 against 0.83 ms).
+    const uint32_t nwin = p.fixed ? 1u : (uint32_t)p.W;
+    quad = quad && (uint64_t)nwin * p.M <= 393216u;
+    p.red_quad = quad;
+    if (!quad) {
+        p.red_T = p.M < 256u ? (int)p.M : 256;
+        p.red_log_s = 0;
+        while (((uint32_t)p.red_T << p.red_log_s) < p.M && p.red_log_s < 3) p.red_log_s++;
+        p.red_slabs = p.M / ((uint32_t)p.red_T << p.red_log_s);
+        return;
+    }
+    uint32_t G = 1;
+    if (p.M >= 512u)
+        while (G * nwin < 296u && G < 128u && p.M / (2 * G) >= 256u) G *= 2;
+    uint32_t B = p.M / G;                  // buckets per slab (power of two)
+    while (B > 128u * 16u) B >>= 1;        // at most 16 items per logical thread
+    uint32_t T = B / 8 ? B / 8 : 1;        // ~8 items per logical thread, 16 .. 128 quads per CTA
+    if (B <= 512u) T = B / 4 ? B / 4 : 1;  // single-slab windows (frozen IPA rounds): 4 items, the shortest chain measured
+    if (T < 16) T = B < 16 ? B : 16;
+    if (T > 128) T = 128;
+    p.red_T = (int)T;
     p.red_log_s = 0;
-    while (((uint32_t)p.red_T << p.red_log_s) < p.M && p.red_log_s < 3) p.red_log_s++;
-    p.red_slabs = p.M / ((uint32_t)p.red_T << p.red_log_s);
+    while ((T << p.red_log_s) < B) p.red_log_s++;
+    p.red_slabs = p.M / (T << p.red_log_s);
 }
 
 static int ceil_lg(uint64_t n) {
@@ -49,11 +80,12 @@ static int ceil_lg(uint64_t n) {
     return l;
 }
 
-// Window widths below are the measured optima on B200 (scripts/gpu_msm_probe.py sweeps, profiles/r01_msm_window_sweep.txt):
-// total cost = W * (n mixed adds) + bucket reduction (2 full adds per bucket, latency bound when thinly filled).
+// Window widths below are the measured optima on B200 (scripts/gpu_msm_probe.py sweeps: profiles/r01_msm_window_sweep.txt,
+// re-measured with the two-level / quad-cooperative bucket reduction in profiles/r02_msm_window_sweep_variable.txt):
+// total cost = W * (n mixed adds) + bucket reduction (~2.5 full adds per bucket).
 MsmPlan msm_make_plan(uint64_t n, int force_c) {
     const int lg = ceil_lg(n);
-    int c = lg <= 6 ? 4 : lg <= 8 ? 6 : lg <= 10 ? 8 : lg <= 12 ? 10 : lg <= 14 ? 12 : lg <= 18 ? 14 : lg <= 20 ? 15 : 16;  // c <= 12: single reduction slab
+    int c = lg <= 6 ? 4 : lg <= 8 ? 7 : lg <= 10 ? 8 : lg <= 14 ? 11 : lg <= 16 ? 13 : lg <= 17 ? 14 : 16;
     if (force_c) c = force_c;
     if (c < 4) c = 4;  // W = 255 / c + 1 <= MSM_MAX_WINDOWS
     if (c > 20) c = 20;
@@ -548,6 +580,191 @@ __global__ void __launch_bounds__(REDUCE_THREADS) k_reduce_slabs(const xyzz_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// 5b. the same reduction with QUAD-COOPERATIVE point additions (the default; "reduce_quad" = 0 selects the kernel above).
+//     The reduction is a chain of ~30-70 dependent point additions per CTA with almost nothing to run beside it: its cost
+//     is latency, 14 dependent multiplications of ~0.3 us per addition.  Here one point lives in four adjacent lanes (lane
+//     k holds coordinate k of (X, Y, ZZ, ZZZ)) and the 12M + 2S of add-2008-s are issued as FOUR levels of one
+//     multiplication per lane, operands and results moving between the lanes of the quad by shuffles:
+//        level 1   U1 = X1 ZZ2 | S1 = Y1 ZZZ2 | U2 = X2 ZZ1 | S2 = Y2 ZZZ1          (operand: xor-2 shuffle of point 2)
+//                  P = U2 - U1 on lanes 0, 2;  R = S2 - S1 on lanes 1, 3            (xor-2 shuffle of the products)
+//        level 2   PP = P^2   | RR = R^2     | ZZ1 ZZ2     | ZZZ1 ZZZ2
+//        level 3   PPP = P PP |     -        | Q = U1 PP   |     -                  (PP broadcast from lane 0)
+//        level 4   ZZZ3 = ZZZ1 ZZZ2 PPP | V = R (Q - X3), X3 = RR - PPP - 2Q | ZZ3 = ZZ1 ZZ2 PP | T = S1 PPP
+//                  X3 -> lane 0, Y3 = V - T on lane 1, ZZ3 on lane 2, ZZZ3 -> lane 3
+//     Infinity operands are resolved by selects; equal or opposite operands (P = 0) fall back to the one-lane routine on
+//     a replicated copy -- rare (crafted inputs), exact.  Every lane of a warp must call quad_add (full-mask shuffles).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ fq_t fq_shfl(const fq_t& v, int src) {
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], src);
+    return r;
+}
+__device__ __forceinline__ fq_t fq_shfl_xor(const fq_t& v, int m) {
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, v.v[i], m);
+    return r;
+}
+__device__ __forceinline__ fq_t fq_sel(bool c, const fq_t& a, const fq_t& b) {
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = c ? a.v[i] : b.v[i];
+    return r;
+}
+__device__ __forceinline__ fq_t xyzz_coord(const xyzz_t& p, unsigned k) {
+    return k == 0 ? p.x : k == 1 ? p.y : k == 2 ? p.zz : p.zzz;
+}
+__device__ __noinline__ fq_t quad_add(fq_t acc, fq_t q) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, k = lane & 3u, qb = lane & ~3u;
+    // infinity <=> ZZ == 0: the flag lives on lane 2 of the quad
+    const unsigned za = __ballot_sync(FULL, fp_is_zero(acc)), zq = __ballot_sync(FULL, fp_is_zero(q));
+    const bool acc_inf = (za >> (qb + 2)) & 1u, q_inf = (zq >> (qb + 2)) & 1u;
+    fq_t t = fq_shfl_xor(q, 2);  // ZZ2 | ZZZ2 | X2 | Y2
+    fq_t m1;
+    fp_mul(m1, acc, t);          // U1 | S1 | U2 | S2
+    fq_t o1 = fq_shfl_xor(m1, 2);  // U2 | S2 | U1 | S1
+    fq_t d;
+    {
+        const fq_t hi = fq_sel(k < 2, o1, m1), lo = fq_sel(k < 2, m1, o1);
+        fp_sub(d, hi, lo);       // P | R | P | R
+    }
+    const unsigned zd = __ballot_sync(FULL, fp_is_zero(d));
+    const bool p_zero = (zd >> qb) & 1u;
+    fq_t m2;
+    {
+        const fq_t a2 = fq_sel(k < 2, d, acc), b2 = fq_sel(k < 2, d, q);
+        fp_mul(m2, a2, b2);      // PP | RR | ZZ1 ZZ2 | ZZZ1 ZZZ2
+    }
+    const fq_t PPb = fq_shfl(m2, (int)qb);
+    fq_t m3;
+    {
+        const fq_t a3 = fq_sel(k == 2, o1, d);
+        fp_mul(m3, a3, PPb);     // PPP | (unused) | Q | (unused)
+    }
+    const fq_t PPPb = fq_shfl(m3, (int)qb), Qb = fq_shfl(m3, (int)qb + 2);
+    const fq_t zzz12 = fq_shfl(m2, (int)qb + 3);  // used by lane 0
+    fq_t x3, w;
+    fp_sub(x3, m2, PPPb);  // meaningful on lane 1 (m2 = RR)
+    fp_sub(x3, x3, Qb);
+    fp_sub(x3, x3, Qb);
+    fp_sub(w, Qb, x3);
+    fq_t m4;
+    {
+        const fq_t a4 = k == 0 ? zzz12 : k == 1 ? d : k == 2 ? m2 : o1;
+        const fq_t b4 = k == 0 ? PPPb : k == 1 ? w : k == 2 ? PPb : PPPb;
+        fp_mul(m4, a4, b4);      // ZZZ3 | V | ZZ3 | T
+    }
+    const fq_t e = fq_sel(k == 1, x3, m4);
+    const int src = (int)qb + (k == 0 ? 1 : k == 1 ? 3 : k == 2 ? 2 : 0);
+    const fq_t g = fq_shfl(e, src);  // X3 | T | ZZ3 | ZZZ3
+    fq_t res;
+    fp_sub(res, m4, g);              // lane 1: Y3 = V - T
+    res = fq_sel(k == 1, res, g);
+    res = fq_sel(q_inf, acc, fq_sel(acc_inf, q, res));
+    const bool special = p_zero && !acc_inf && !q_inf;  // doubling or cancellation
+    if (__any_sync(FULL, special)) {
+        xyzz_t A, B;
+        A.x = fq_shfl(acc, (int)qb), A.y = fq_shfl(acc, (int)qb + 1), A.zz = fq_shfl(acc, (int)qb + 2), A.zzz = fq_shfl(acc, (int)qb + 3);
+        B.x = fq_shfl(q, (int)qb), B.y = fq_shfl(q, (int)qb + 1), B.zz = fq_shfl(q, (int)qb + 2), B.zzz = fq_shfl(q, (int)qb + 3);
+        if (special) {
+            xyzz_add_nl(A, B);
+            res = xyzz_coord(A, k);
+        }
+    }
+    return res;
+}
+
+constexpr int RQ_MAX_T = 128;  // logical threads (quads) per CTA: 512 physical threads
+// Same contract as k_reduce_slabs; blockDim.x = max(32, 4 * T), logical thread j = threadIdx.x / 4.
+__global__ void __launch_bounds__(4 * RQ_MAX_T) k_reduce_slabs_quad(const xyzz_t* __restrict__ in, const xyzz_t* __restrict__ extra,
+                                                                    size_t in_stride, int T, int log_s, xyzz_t* __restrict__ outA,
+                                                                    xyzz_t* __restrict__ outR, xyzz_t* __restrict__ outE, int out_stride) {
+    __shared__ xyzz_t smA[RQ_MAX_T], smB[RQ_MAX_T];
+    fq_t* cA = reinterpret_cast<fq_t*>(smA);  // coordinate k of logical thread j: c[4 j + k]
+    fq_t* cB = reinterpret_cast<fq_t*>(smB);
+    const int j = (int)(threadIdx.x >> 2);
+    const unsigned k = threadIdx.x & 3u;
+    const bool act = j < T;
+    const uint32_t s = 1u << log_s;
+    const size_t base = (size_t)blockIdx.y * in_stride + (((size_t)blockIdx.x * T + (act ? j : 0)) << log_s);
+    const fq_t* Q = reinterpret_cast<const fq_t*>(in + base);
+    fq_t zero;
+    fp_zero(zero);
+    // running sums from the top: R = sum Q_t, A = sum (t + 1) Q_t over this logical thread's s items
+    fq_t R = zero, A = zero;
+    for (int t = (int)s - 1; t >= 0; t--) {
+        const fq_t q = act ? Q[4 * t + k] : zero;
+        R = quad_add(R, q);
+        A = quad_add(A, R);
+    }
+    // inclusive suffix scan of R over the CTA: Suf_j = sum_{i >= j} R_i
+    fq_t Suf = R;
+    if (act) cA[4 * j + k] = Suf;
+    __syncthreads();
+    for (int stride = 1; stride < T; stride <<= 1) {
+        const bool has = act && j + stride < T;
+        const fq_t other = has ? cA[4 * (j + stride) + k] : zero;
+        __syncthreads();
+        Suf = quad_add(Suf, other);
+        if (act) cA[4 * j + k] = Suf;
+        __syncthreads();
+    }
+    const fq_t total = cA[k];  // logical thread 0: sum of all R_j
+    __syncthreads();
+    // two tree sums at once, in disjoint halves of the CTA: F = sum_{j >= 1} Suf_j (= sum_j j R_j) and sum_j A_j
+    if (act) {
+        cA[4 * j + k] = j == 0 ? zero : Suf;
+        cB[4 * j + k] = A;
+    }
+    __syncthreads();
+    if (T >= 2) {
+        const int half = T >> 1;
+        const int tree = j >= half ? 1 : 0, jj = j & (half - 1);
+        fq_t* c = tree ? cB : cA;
+        for (int stride = half; stride >= 1; stride >>= 1) {
+            const bool on = act && jj < stride;
+            const fq_t x = on ? c[4 * jj + k] : zero, y = on ? c[4 * (jj + stride) + k] : zero;
+            const fq_t r = quad_add(x, y);
+            __syncthreads();
+            if (on) c[4 * jj + k] = r;
+            __syncthreads();
+        }
+    }
+    const size_t o = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * out_stride;
+    fq_t* oR = reinterpret_cast<fq_t*>(outR + o);
+    if (j == 0) oR[k] = total;
+    if (threadIdx.x == 0) {  // slab result A = sum_j A_j + 2^log_s F: a handful of one-lane operations
+        xyzz_t F = smA[0], S = smB[0];
+        for (int t = 0; t < log_s; t++) xyzz_dbl_nl(F);
+        xyzz_add_nl(S, F);
+        outA[o] = S;
+    }
+    if (extra) {  // plain sum of a second array (level 2: the slabs' A partials)
+        __syncthreads();
+        const fq_t* X = reinterpret_cast<const fq_t*>(extra + base);
+        fq_t e = zero;
+        for (uint32_t t = 0; t < s; t++) {
+            const fq_t q = act ? X[4 * t + k] : zero;
+            e = quad_add(e, q);
+        }
+        if (act) cA[4 * j + k] = e;
+        __syncthreads();
+        for (int stride = T >> 1; stride >= 1; stride >>= 1) {
+            const bool on = act && j < stride;
+            const fq_t x = on ? cA[4 * j + k] : zero, y = on ? cA[4 * (j + stride) + k] : zero;
+            const fq_t r = quad_add(x, y);
+            __syncthreads();
+            if (on) cA[4 * j + k] = r;
+            __syncthreads();
+        }
+        fq_t* oE = reinterpret_cast<fq_t*>(outE + o);
+        if (j == 0) oE[k] = cA[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fixed-base tables: table[w * n + i] = 2^(off_w) * G_i (affine), w = 0 .. W-1, off_w = sum of the lower window widths
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_precompute(const affine_t* __restrict__ gens, uint32_t n, const MsmWidths widths, int W,
@@ -587,7 +804,10 @@ void msm_precompute_tables(halo_ctx* ctx, int force_c) {
 // ------------------------------------------------------------------------------------------------
 // Device part of one MSM.  d_out receives 3 points per window (one "window" in FIXED mode): [E, A2, R2] with
 // window sum S = E + slab * (A2 - R2); a single-slab plan writes S into E and leaves A2 = R2 = infinity.
-void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out, int lane, const SortAhead* ahead) {
+void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out, int lane, const SortAhead* ahead) {
+    // the reduction kernel is part of the plan (its slab geometry is what msm_finish_host undoes): settle it here, in the
+    // caller's copy
+    if (plan.red_quad != (ctx->tune_reduce_quad != 0)) plan_set_reduce(plan, ctx->tune_reduce_quad != 0);
     const uint32_t n = in.n;
     const uint32_t ntot = in.n + in.n_tail;
     // lane 0: the context's stream and workspace.  lane 1: a second stream and workspace, so two latency-bound MSMs of
@@ -623,7 +843,7 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
     sws.scan_tmp.reserve(4096 * 4);
     ws.task_partial.reserve((size_t)(2 * plan.red_slabs + 3) * nwin * sizeof(xyzz_t));
     if ((NB + SCAN_TILE - 1) / SCAN_TILE > 2048) throw CudaError{cudaErrorInvalidValue, "bucket count too large for scan", __FILE__, __LINE__};
-    if (plan.red_slabs > (uint32_t)REDUCE_THREADS * 16) throw CudaError{cudaErrorInvalidValue, "too many reduction slabs", __FILE__, __LINE__};
+    if (plan.red_slabs > (uint32_t)(plan.red_quad ? RQ_MAX_T : REDUCE_THREADS) * 64) throw CudaError{cudaErrorInvalidValue, "too many reduction slabs", __FILE__, __LINE__};
 
     uint32_t* counts = sws.counts.as<uint32_t>();
     uint32_t* offsets = sws.offsets.as<uint32_t>();
@@ -730,21 +950,27 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t*
     }
     mark(4);
     HALO_CUDA(cudaMemsetAsync(d_out, 0, (size_t)3 * nwin * sizeof(xyzz_t), st));
+    const bool quad = plan.red_quad;
+    const int maxT = quad ? RQ_MAX_T : REDUCE_THREADS;
+    auto reduce = [&](dim3 grid, int T, int log_s, const xyzz_t* src, const xyzz_t* extra, size_t stride, xyzz_t* oA, xyzz_t* oR, xyzz_t* oE,
+                      int ostride) {
+        if (quad)
+            k_reduce_slabs_quad<<<grid, 4 * T < 32 ? 32 : 4 * T, 0, st>>>(src, extra, stride, T, log_s, oA, oR, oE, ostride);
+        else
+            k_reduce_slabs<<<grid, T, 0, st>>>(src, extra, stride, T, log_s, oA, oR, oE, ostride);
+    };
     if (plan.red_slabs == 1) {
-        // A is the window sum; R goes to scratch
-        k_reduce_slabs<<<dim3(1, nwin), plan.red_T, 0, st>>>(buckets, nullptr, plan.M, plan.red_T, plan.red_log_s, d_out,
-                                                             ws.task_partial.as<xyzz_t>(), nullptr, 3);
-        // (R lands at stride 3 in scratch; reserve enough)
+        // A is the window sum; R goes to scratch (at stride 3)
+        reduce(dim3(1, nwin), plan.red_T, plan.red_log_s, buckets, nullptr, plan.M, d_out, ws.task_partial.as<xyzz_t>(), nullptr, 3);
         ctx->kernel_launches += 1;
     } else {
         xyzz_t* slabA = ws.task_partial.as<xyzz_t>();
         xyzz_t* slabR = slabA + (size_t)nwin * plan.red_slabs;
-        k_reduce_slabs<<<dim3(plan.red_slabs, nwin), plan.red_T, 0, st>>>(buckets, nullptr, plan.M, plan.red_T, plan.red_log_s,
-                                                                           slabA, slabR, nullptr, 1);
-        int T2 = plan.red_slabs < (uint32_t)REDUCE_THREADS ? (int)plan.red_slabs : REDUCE_THREADS;
+        reduce(dim3(plan.red_slabs, nwin), plan.red_T, plan.red_log_s, buckets, nullptr, plan.M, slabA, slabR, nullptr, 1);
+        int T2 = plan.red_slabs < (uint32_t)maxT ? (int)plan.red_slabs : maxT;
         int log_s2 = 0;
         while (((uint32_t)T2 << log_s2) < plan.red_slabs) log_s2++;
-        k_reduce_slabs<<<dim3(1, nwin), T2, 0, st>>>(slabR, slabA, plan.red_slabs, T2, log_s2, d_out + 1, d_out + 2, d_out, 3);
+        reduce(dim3(1, nwin), T2, log_s2, slabR, slabA, plan.red_slabs, d_out + 1, d_out + 2, d_out, 3);
         ctx->kernel_launches += 2;
     }
     mark(5);

@@ -27,7 +27,8 @@ struct SortAhead {
     int ctas_per_sm;  // 0: full grid
 };
 // Device part of one MSM: 3 partial points per window into d_out (see msm.cu).
-void msm_enqueue(halo_ctx* ctx, const MsmInput& in, const MsmPlan& plan, xyzz_t* d_out, int lane = 0, const SortAhead* ahead = nullptr);
+// (`plan` is the caller's copy: the reduction geometry in it is settled here and read back by msm_finish_host)
+void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out, int lane = 0, const SortAhead* ahead = nullptr);
 // First `passes` levels of the bucket sums as flat pairwise affine additions with batched inversion (msm_pairs.cu).
 const affine_t* pair_tree_enqueue(halo_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const MsmInput& in, const uint32_t* entries,
                                   const uint32_t* total_slots, uint64_t slots_max, int passes);

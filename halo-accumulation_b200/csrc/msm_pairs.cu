@@ -224,6 +224,135 @@ __global__ void __launch_bounds__(128) k_prod_down(fq_t* __restrict__ vals, uint
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------------------
+// Pass 0 stages its operands through shared memory with cp.async: while the warp computes step s (32 pairs: 4M + 1S + 2 each)
+// the 64 bases of step s - 1 are in flight, fetched cooperatively (4 adjacent lanes copy the four 16-byte chunks of one
+// base with ONE instruction -- the access pattern that reaches HBM's random-access rate, see pt_gather_pair_coop) straight
+// into the owner lane's row of the tile.  No registers hold data in flight (the register prefetch and the shuffle
+// transpose of round 1 both lost to register pressure), entries are loaded two steps ahead.  Two 4 KiB buffers per warp,
+// 32 KiB per CTA, 6 CTAs per SM.
+struct BwdTile {
+    uint4 v[2][32][4];  // [operand][owner lane][16-byte chunk]
+};
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void pt_stage_pair_async(BwdTile& tile, uint2 e, const affine_t* __restrict__ bases, uint32_t n,
+                                                    const affine_t* __restrict__ tail_bases, uint32_t lane) {
+    const uint32_t c = lane & 3u;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int owner = (r & 3) * 8 + (int)(lane >> 2);
+        const uint32_t ent = __shfl_sync(0xffffffffu, r < 4 ? e.x : e.y, owner);
+        if (ent != PT_SENTINEL) {
+            const uint32_t idx = ent & 0x7fffffffu;
+            const affine_t* p = idx < n ? bases + idx : tail_bases + (idx - n);
+            cp_async16(&tile.v[r >> 2][owner][c], reinterpret_cast<const uint4*>(p) + c);
+        }
+    }
+    cp_async_commit();
+}
+__device__ __forceinline__ void pt_take_staged(affine_t& p, bool& inf, const BwdTile& tile, int operand, uint32_t ent, uint32_t lane) {
+    if (ent == PT_SENTINEL) {
+        inf = true;
+        affine_set_inf(p);
+        return;
+    }
+    uint4* pp = reinterpret_cast<uint4*>(&p);
+#pragma unroll
+    for (int k = 0; k < 4; k++) pp[k] = tile.v[operand][lane][k];
+    inf = affine_is_inf(p);
+    if (ent >> 31) fp_neg(p.y, p.y);
+}
+
+// The arithmetic of one pair, shared by both instantiations: 1/den from the thread's running inverse and prefix[q].
+__device__ __forceinline__ void pt_pair_finish(affine_t& r, const affine_t& a, bool ainf, const affine_t& b, bool binf, fq_t& invtot,
+                                               const fq_t* __restrict__ prefix, uint32_t q) {
+    fq_t den;
+    const int mode = pt_classify(den, ainf, binf, a.x, b.x, a.y, b.y);
+    if (mode == PT_SKIP) {
+        if (ainf && binf)
+            pt_set_inf(r);
+        else if (ainf)
+            r = b;
+        else if (binf)
+            r = a;
+        else
+            pt_set_inf(r);  // a = -b
+    } else {
+        fq_t inv, pre = prefix[q], num, lam, t;
+        fp_mul(inv, invtot, pre);
+        fp_mul(invtot, invtot, den);
+        if (mode == PT_ADD) {
+            fp_sub(num, b.y, a.y);
+        } else {  // tangent: 3 x^2 / (2 y)
+            fp_sqr(t, a.x);
+            fp_dbl(num, t);
+            fp_add(num, num, t);
+        }
+        fp_mul(lam, num, inv);
+        fp_sqr(t, lam);
+        fp_sub(t, t, a.x);
+        fp_sub(r.x, t, b.x);
+        fp_sub(t, a.x, r.x);
+        fp_mul(t, lam, t);
+        fp_sub(r.y, t, a.y);
+    }
+}
+
+#ifndef HALO_PAIR_BWD0_BLOCKS
+#define HALO_PAIR_BWD0_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, HALO_PAIR_BWD0_BLOCKS) k_pair_bwd0(const uint32_t* __restrict__ entries, const affine_t* __restrict__ bases,
+                                                                          uint32_t n, const affine_t* __restrict__ tail_bases,
+                                                                          const uint32_t* __restrict__ total_slots,
+                                                                          const fq_t* __restrict__ prefix, const fq_t* __restrict__ tot_inv,
+                                                                          affine_t* __restrict__ out) {
+    __shared__ BwdTile tiles[4][2];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gwarp = tid >> 5, lane = tid & 31u;
+    const uint32_t Q = *total_slots >> 1;
+    if (pt_pair_index(gwarp, 0, 0) >= Q) return;  // warp uniform
+    BwdTile* tile = tiles[threadIdx.x >> 5];
+    fq_t invtot = tot_inv[tid];
+    const uint2* ents = reinterpret_cast<const uint2*>(entries);
+    const uint2 none = make_uint2(PT_SENTINEL, PT_SENTINEL);
+    auto load_entry = [&](int s) {
+        const uint32_t q = pt_pair_index(gwarp, s, lane);
+        return q < Q ? ents[q] : none;
+    };
+    uint2 e0 = load_entry(PT_K - 1), e1 = load_entry(PT_K - 2);
+    pt_stage_pair_async(tile[(PT_K - 1) & 1], e0, bases, n, tail_bases, lane);
+#pragma unroll 1
+    for (int s = PT_K - 1; s >= 0; s--) {
+        const uint2 e2 = s >= 2 ? load_entry(s - 2) : none;
+        if (s >= 1) {
+            pt_stage_pair_async(tile[(s - 1) & 1], e1, bases, n, tail_bases, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const uint32_t q = pt_pair_index(gwarp, s, lane);
+        if (q < Q) {
+            affine_t a, b, r;
+            bool ainf, binf;
+            pt_take_staged(a, ainf, tile[s & 1], 0, e0.x, lane);
+            pt_take_staged(b, binf, tile[s & 1], 1, e0.y, lane);
+            pt_pair_finish(r, a, ainf, b, binf, invtot, prefix, q);
+            out[q] = r;
+        }
+        __syncwarp();  // every lane has read its row before the stage two steps on overwrites this buffer
+        e0 = e1;
+        e1 = e2;
+    }
+}
+
 // 7 CTAs per SM (72 registers, 24 bytes of spill): measured best of 4 (92 registers) .. 8 (64 registers): MSM 2^24
 // 36.16 / 35.71 (6) / 35.52 (7) / 36.41 ms (8)
 template <bool PASS0>
@@ -244,9 +373,7 @@ __global__ void __launch_bounds__(128, 7) k_pair_bwd(const uint32_t* __restrict_
         affine_t a, b;
         bool ainf, binf;
         if (PASS0) {
-            // per-lane gathers: this kernel is bound by its 4M + 1S per pair, and the cooperative fetch of the forward
-            // kernel (shuffles, shared-memory transpose, 16 more registers) measured 9 % slower here; prefetching the
-            // next step's entries measured 1 % slower
+            // per-lane gathers (the round-1 kernel, kept for A/B: halo_set_tuning "pair_bwd_async" = 0)
             const uint2 e = reinterpret_cast<const uint2*>(entries)[q];
             pt_gather(a, ainf, e.x, bases, n, tail_bases);
             pt_gather(b, binf, e.y, bases, n, tail_bases);
@@ -256,37 +383,8 @@ __global__ void __launch_bounds__(128, 7) k_pair_bwd(const uint32_t* __restrict_
             ainf = pt_x_is_inf(a.x);
             binf = pt_x_is_inf(b.x);
         }
-        fq_t den;
-        const int mode = pt_classify(den, ainf, binf, a.x, b.x, a.y, b.y);
         affine_t r;
-        if (mode == PT_SKIP) {
-            if (ainf && binf)
-                pt_set_inf(r);
-            else if (ainf)
-                r = b;
-            else if (binf)
-                r = a;
-            else
-                pt_set_inf(r);  // a = -b
-        } else {
-            fq_t inv, pre = prefix[q], num, lam, t;
-            fp_mul(inv, invtot, pre);
-            fp_mul(invtot, invtot, den);
-            if (mode == PT_ADD) {
-                fp_sub(num, b.y, a.y);
-            } else {  // tangent: 3 x^2 / (2 y)
-                fp_sqr(t, a.x);
-                fp_dbl(num, t);
-                fp_add(num, num, t);
-            }
-            fp_mul(lam, num, inv);
-            fp_sqr(t, lam);
-            fp_sub(t, t, a.x);
-            fp_sub(r.x, t, b.x);
-            fp_sub(t, a.x, r.x);
-            fp_mul(t, lam, t);
-            fp_sub(r.y, t, a.y);
-        }
+        pt_pair_finish(r, a, ainf, b, binf, invtot, prefix, q);
         out[q] = r;
     }
 }
@@ -346,7 +444,10 @@ const affine_t* pair_tree_enqueue(halo_ctx* ctx, MsmWorkspace& ws, cudaStream_t 
         for (int j = 0; j + 1 < L; j++) k_prod_up<<<grids[j + 1], 128, 0, st>>>(vals[j], sizes[j], pres[j], vals[j + 1]);
         k_inv<<<ceil_div(sizes[L - 1], 128), 128, 0, st>>>(vals[L - 1], sizes[L - 1]);
         for (int j = L - 2; j >= 0; j--) k_prod_down<<<grids[j + 1], 128, 0, st>>>(vals[j], sizes[j], pres[j], vals[j + 1]);
-        if (p == 0)
+        if (p == 0 && ctx->tune_pair_bwd_async)
+            k_pair_bwd0<<<grids[0], 128, 0, st>>>(entries, in.bases, in.fixed_stride ? 0x7fffffffu : nb, in.tail_bases, total_slots, prefix,
+                                                  vals[0], dst);
+        else if (p == 0)
             k_pair_bwd<true><<<grids[0], 128, 0, st>>>(entries, in.bases, in.fixed_stride ? 0x7fffffffu : nb, in.tail_bases, nullptr,
                                                        total_slots, p, prefix, vals[0], dst);
         else
