@@ -244,6 +244,7 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "reduce_quad")) ctx->tune_reduce_quad = value;
     else if (!strcmp(key, "pair_bwd_async")) ctx->tune_pair_bwd_async = value;
     else if (!strcmp(key, "ipa_defer_rounds")) ctx->tune_ipa_defer = value;
+    else if (!strcmp(key, "ipa_defer2_rounds")) ctx->tune_ipa_defer2 = value;
     else if (!strcmp(key, "ipa_two_lanes")) ctx->tune_ipa_two_lanes = value;
     else if (!strcmp(key, "ipa_freeze_len")) ctx->tune_ipa_freeze_len = value;
     else if (!strcmp(key, "ipa_frozen_c")) ctx->tune_ipa_frozen_c = value;

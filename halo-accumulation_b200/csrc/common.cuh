@@ -196,6 +196,8 @@ struct halo_ctx {
     int tune_ipa_frozen_c = 11;  // window of the frozen-tail MSMs (8192 points): round 1 measured 10 best with the one-lane single-slab reduction;
                                  // with the two-level quad reduction 11 is (8192-point MSM 0.46 / 0.38 / 0.41 ms at c = 10 / 11 / 12)
     int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
+    int tune_ipa_defer2 = 0;    // later deferred stages over the materialised vector, at most this many rounds each; 0 = off: measured slower at 2^20
+                                // (rounds 3-6 as one stage: 4 x 2.1 ms L / R + 5.3 ms latency-bound fold of 8192 outputs against 4.9 + 6.2 ms; profiles/r02_ipa_stage2_probe.txt)
     int tune_sort_ahead = 1;  // pipelined submit: CTAs per SM of the counting sort running beside the previous MSM (0: off)
     int tune_split_blocking = 23;  // halo_msm_gens: two point slices through the pipeline slots for n >= 2^this (0: never)
     int tune_split_first_16ths = 5;  // size of the first slice in sixteenths of n: its H2D copy is exposed, the second slice's copy hides behind

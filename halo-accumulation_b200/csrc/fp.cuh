@@ -481,9 +481,10 @@ HALO_HD void fp_from_u32(fp_t<P>& r, uint32_t x) {
     fp_from_canon(r, t);
 }
 
-// a^(p-2) (Fermat).  Used once per normalised point / per IPA round, never in an inner loop.
+// a^(p-2) (Fermat): 254 squarings + ~65 multiplications, one dependent chain.  Kept as the independent cross-check of
+// fp_inv below (tests) -- a lone warp needs 0.105 ms for it (profiles/r02_reduce_launches.csv, k_inv).
 template <class P>
-HALO_HD void fp_inv(fp_t<P>& r, const fp_t<P>& a) {
+HALO_HD void fp_inv_fermat(fp_t<P>& r, const fp_t<P>& a) {
     // exponent p - 2: limbs(p) with limb0 = 1 - 2 -> borrow: p - 2 = [0xffffffff, P1-1, P2, P3, 0,0,0,0x40000000]
     uint32_t e[8] = {0xffffffffu, P::P1 - 1u, P::P2, P::P3, 0u, 0u, 0u, 0x40000000u};
     fp_t<P> acc;
@@ -493,6 +494,177 @@ HALO_HD void fp_inv(fp_t<P>& r, const fp_t<P>& a) {
         if ((e[i >> 5] >> (i & 31)) & 1u) fp_mul(acc, acc, a);
     }
     r = acc;
+}
+
+// ---- inversion by division steps (Bernstein-Yang "safegcd", the 30-bit-limb formulation used for 256-bit moduli) --------
+// Every serial point normalisation, the top of every batched inversion (k_inv: once per pair-tree pass, twice per generator
+// fold) and the transcript's challenge inversions are ONE dependent chain; as a Fermat power that chain is ~78 000
+// instructions.  The division-step algorithm replaces it by 20 rounds of { 30 branch-free steps on single 32-bit words that
+// build a 2 x 2 transition matrix; apply the matrix to (f, g) and, modulo p, to (d, e) -- nine signed 30-bit limbs each }:
+// ~15 000 instructions, no data-dependent branch (all lanes of a warp stay converged), 600 >= 590 steps suffice for any
+// 256-bit input.  Integers only: the input is the Montgomery residue aR, the integer inverse (aR)^-1 is turned into the
+// Montgomery residue a^-1 R by one multiplication with R^3.  inv(0) = 0, like the Fermat power.
+namespace dsinv {
+constexpr int32_t M30 = 0x3fffffff;
+struct s30 {
+    int32_t v[9];
+};
+template <class P>
+HALO_HD constexpr int32_t mod30(int i) {  // limb i of p in 30-bit limbs (p = 2^254 + t, t < 2^126: limbs 5..7 are zero)
+    // bits [30 i, 30 i + 30) of p, from the 32-bit limbs fp_mod<P>(.)
+    const int lo = 30 * i, w = lo >> 5, sh = lo & 31;
+    uint64_t x = (uint64_t)fp_mod<P>(w) >> sh;
+    if (sh > 2 && w + 1 < 8) x |= (uint64_t)fp_mod<P>(w + 1) << (32 - sh);
+    return (int32_t)(x & (uint64_t)M30);
+}
+HALO_HD void to30(s30& r, const uint32_t a[8]) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const int lo = 30 * i, w = lo >> 5, sh = lo & 31;
+        uint64_t x = (uint64_t)a[w] >> sh;
+        if (sh > 2 && w + 1 < 8) x |= (uint64_t)a[w + 1] << (32 - sh);
+        r.v[i] = (int32_t)(x & (uint64_t)M30);
+    }
+}
+HALO_HD void from30(uint32_t r[8], const s30& a) {  // a normalised: limbs in [0, 2^30), value < 2^256
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const int lo = 32 * w, i = lo / 30, sh = lo % 30;  // bit lo of the value is bit sh of limb i
+        uint64_t x = (uint64_t)(uint32_t)a.v[i] >> sh;
+        x |= (uint64_t)(uint32_t)a.v[i + 1] << (30 - sh);
+        if (i + 2 < 9 && 60 - sh < 32) x |= (uint64_t)(uint32_t)a.v[i + 2] << (60 - sh);
+        r[w] = (uint32_t)x;
+    }
+}
+struct trans {
+    int32_t u, v, q, r;
+};
+// 30 division steps on the low words; returns the new zeta and the transition matrix scaled by 2^30
+HALO_HD int32_t divsteps30(int32_t zeta, uint32_t f0, uint32_t g0, trans& t) {
+    uint32_t u = 1, v = 0, q = 0, r = 1, f = f0, g = g0;
+#pragma unroll 6
+    for (int i = 0; i < 30; i++) {
+        uint32_t m1 = (uint32_t)(zeta >> 31);       // all ones iff zeta < 0
+        const uint32_t m2 = 0u - (g & 1u);          // all ones iff g odd
+        const uint32_t x = (f ^ m1) - m1, y = (u ^ m1) - m1, z = (v ^ m1) - m1;  // (+-f, +-u, +-v)
+        g += x & m2;
+        q += y & m2;
+        r += z & m2;
+        m1 &= m2;                                    // swap iff zeta < 0 and g odd
+        zeta = (int32_t)(((uint32_t)zeta ^ m1) - 1u);
+        f += g & m1;
+        u += q & m1;
+        v += r & m1;
+        g >>= 1;
+        u <<= 1;
+        v <<= 1;
+    }
+    t.u = (int32_t)u, t.v = (int32_t)v, t.q = (int32_t)q, t.r = (int32_t)r;
+    return zeta;
+}
+// (d, e) <- t (d, e) / 2^30 (mod p), entries stay in (-2p, p)
+template <class P>
+HALO_HD void update_de(s30& d, s30& e, const trans& t) {
+    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+    const int32_t sd = d.v[8] >> 31, se = e.v[8] >> 31;
+    int32_t md = (t.u & sd) + (t.v & se), me = (t.q & sd) + (t.r & se);
+    int64_t cd = u * d.v[0] + v * e.v[0], ce = q * d.v[0] + r * e.v[0];
+    // p = 1 (mod 2^30), so p^-1 mod 2^30 = 1: choose md, me so that the low 30 bits of t (d, e) + p (md, me) vanish
+    md -= (int32_t)(((uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+    me -= (int32_t)(((uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+    cd += (int64_t)mod30<P>(0) * md;
+    ce += (int64_t)mod30<P>(0) * me;
+    cd >>= 30;
+    ce >>= 30;
+#pragma unroll
+    for (int i = 1; i < 9; i++) {
+        cd += u * d.v[i] + v * e.v[i];
+        ce += q * d.v[i] + r * e.v[i];
+        if (mod30<P>(i) != 0) {
+            cd += (int64_t)mod30<P>(i) * md;
+            ce += (int64_t)mod30<P>(i) * me;
+        }
+        d.v[i - 1] = (int32_t)cd & M30;
+        cd >>= 30;
+        e.v[i - 1] = (int32_t)ce & M30;
+        ce >>= 30;
+    }
+    d.v[8] = (int32_t)cd;
+    e.v[8] = (int32_t)ce;
+}
+// (f, g) <- t (f, g) / 2^30 (exact)
+HALO_HD void update_fg(s30& f, s30& g, const trans& t) {
+    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+    int64_t cf = u * f.v[0] + v * g.v[0], cg = q * f.v[0] + r * g.v[0];
+    cf >>= 30;
+    cg >>= 30;
+#pragma unroll
+    for (int i = 1; i < 9; i++) {
+        cf += u * f.v[i] + v * g.v[i];
+        cg += q * f.v[i] + r * g.v[i];
+        f.v[i - 1] = (int32_t)cf & M30;
+        cf >>= 30;
+        g.v[i - 1] = (int32_t)cg & M30;
+        cg >>= 30;
+    }
+    f.v[8] = (int32_t)cf;
+    g.v[8] = (int32_t)cg;
+}
+// r in (-2p, p) -> [0, p), negated first when sign < 0
+template <class P>
+HALO_HD void normalize(s30& r, int32_t sign) {
+    int32_t c;
+    const int32_t add1 = r.v[8] >> 31, neg = sign >> 31;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        r.v[i] += mod30<P>(i) & add1;
+        r.v[i] = (r.v[i] ^ neg) - neg;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c = r.v[i] >> 30;
+        r.v[i] &= M30;
+        r.v[i + 1] += c;
+    }
+    const int32_t add2 = r.v[8] >> 31;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.v[i] += mod30<P>(i) & add2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c = r.v[i] >> 30;
+        r.v[i] &= M30;
+        r.v[i + 1] += c;
+    }
+}
+}  // namespace dsinv
+
+template <class P>
+HALO_HD void fp_inv(fp_t<P>& r, const fp_t<P>& a) {
+    using namespace dsinv;
+    s30 d, e, f, g;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        d.v[i] = 0;
+        e.v[i] = i == 0 ? 1 : 0;
+        f.v[i] = mod30<P>(i);
+    }
+    to30(g, a.v);
+    int32_t zeta = -1;
+#pragma unroll 1
+    for (int it = 0; it < 20; it++) {
+        trans t;
+        zeta = divsteps30(zeta, (uint32_t)f.v[0], (uint32_t)g.v[0], t);
+        update_de<P>(d, e, t);
+        update_fg(f, g, t);
+    }
+    // g = 0 and f = +-gcd = +-1 (or +-p when a = 0, where d = 0): the integer inverse is sign(f) * d
+    normalize<P>(d, f.v[8]);
+    fp_t<P> x, r3, r2;
+    from30(x.v, d);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r2.v[i] = P::r2(i);
+    fp_mul(r3, r2, r2);  // R^2 * R^2 / R = R^3
+    fp_mul(r, x, r3);    // (aR)^-1 * R^3 / R = a^-1 R
 }
 
 }  // namespace halo

@@ -455,13 +455,33 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
     vec_dot(ctx, c + m, z, m, scal + 2, scal);          // dot_l = <c_r, z_l>
     vec_dot(ctx, c, z + m, m, scal + 2, scal + 1);      // dot_r = <c_l, z_r>
     const uint64_t freeze_len = ctx->tune_ipa_freeze_len > 0 ? (uint64_t)ctx->tune_ipa_freeze_len : IPA_FREEZE_LEN;
-    if (!st->frozen && ((st->defer > 0 && st->round == 0) || st->cur <= freeze_len)) {  // freeze the generator vector
-        st->frozen = true;                                                                  // (see k_frozen_scalars)
-        st->deferred = st->cur > freeze_len;  // a head freeze is undone by k_fold_multi after `defer` rounds
-        st->M0 = (uint32_t)st->cur;
-        ctx->ipa_frozen.reserve((size_t)3 * st->M0 * sizeof(fr_t));
-        k_fill_one<<<(st->M0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ipa_frozen.as<fr_t>(), st->M0);
-        ctx->kernel_launches++;
+    if (!st->frozen) {  // between stages: decide how the coming rounds treat the generator vector (see k_frozen_scalars)
+        int D = 0;
+        bool over_gens = false;
+        if (st->cur > freeze_len) {
+            if (st->round == 0 && st->defer > 0) {
+                D = st->defer;  // head stage over GS itself
+                over_gens = true;
+            } else if (ctx->tune_ipa_defer2 > 0 && ctx->tune_ipa_defer != 0) {  // ("ipa_defer_rounds" = 0 switches every stage off)
+                int room = 0;  // rounds until the frozen-tail length is reached
+                while ((st->cur >> (room + 1)) >= freeze_len) room++;
+                D = room < ctx->tune_ipa_defer2 ? room : ctx->tune_ipa_defer2;
+                if (D > FOLD_MAX_DEFER) D = FOLD_MAX_DEFER;
+                if (D < 2) D = 0;  // a single round is the ordinary fold
+            }
+        }
+        if (D > 0 || st->cur <= freeze_len) {
+            st->frozen = true;
+            st->deferred = D > 0;  // a deferred stage is undone by k_fold_multi after D rounds; the tail freeze is final
+            st->stage_D = D;
+            st->stage_first = st->round;
+            st->stage_over_gens = over_gens;
+            st->M0 = (uint32_t)st->cur;
+            st->defer_xis.clear();
+            ctx->ipa_frozen.reserve((size_t)3 * st->M0 * sizeof(fr_t));
+            k_fill_one<<<(st->M0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ipa_frozen.as<fr_t>(), st->M0);
+            ctx->kernel_launches++;
+        }
     }
     MsmInput in[2];
     if (st->frozen) {
@@ -474,7 +494,7 @@ int halo_ipa_round_lr(halo_ipa* st, uint64_t L_jac[12], uint64_t R_jac[12]) {
         in[0].scalars = tL;
         in[1].bases = G;
         in[1].scalars = tR;
-        if (st->deferred && st->fixed_ok) {  // G is still GS[0..n): shared bucket set over the precomputed multiples
+        if (st->deferred && st->stage_over_gens && st->fixed_ok) {  // G is still GS[0..n): shared bucket set over the precomputed multiples
             for (int k = 0; k < 2; k++) {
                 in[k].bases = ctx->gens_pre.as<affine_t>();
                 in[k].fixed_stride = (uint32_t)ctx->pre_n;
@@ -547,9 +567,11 @@ int halo_ipa_round_fold(halo_ipa* st, const uint64_t xi[4], const uint64_t xi_in
     st->cur = m;
     st->round++;
     st->lr_done = false;
-    if (st->deferred && (int)st->round == st->defer && st->cur > 1) {
-        fold_multi(ctx, ctx->gens.as<affine_t>(), st->n, st->defer_xis.data(), st->defer);  // G^(defer) in one joint pass
+    if (st->deferred && (int)(st->round - st->stage_first) == st->stage_D && st->cur > 1) {
+        // the stage's rounds in one joint pass: G^(first + D) from G^(first) (ipa_G still holds it: nothing was folded)
+        fold_multi(ctx, ctx->ipa_G.as<affine_t>(), st->M0, st->defer_xis.data(), st->stage_D);
         st->frozen = st->deferred = false;
+        st->defer_xis.clear();
     }
     IPA_CATCH
 }

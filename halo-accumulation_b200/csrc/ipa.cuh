@@ -21,7 +21,13 @@ struct halo_ipa {
     uint32_t M0 = 0;
     // deferred head: the first `defer` rounds leave the generators untouched (L / R over GS itself with per-index
     // coefficients, fixed-base tables when present); k_fold_multi then materialises G^(defer) in one joint pass
+    // Later stages repeat the trick on the materialised vector (ctx->ipa_G, variable base): while the vector is longer than
+    // the frozen-tail length, the next `stage_D` rounds run as per-index-coefficient MSMs over it and ONE k_fold_multi takes
+    // it down 2^stage_D-fold (2^20: rounds 3-6 over G^(3), then G^(7) of 8192 elements, which the frozen tail keeps).
     int defer = 0;
+    int stage_D = 0;             // rounds of the current deferred stage
+    uint32_t stage_first = 0;    // its first round
+    bool stage_over_gens = false;  // head stage: the vector is still GS[0..n) (FIXED-base tables usable)
     bool deferred = false, fixed_ok = false;
     halo::affine_t hprime;  // affine H' on the host (the FIXED-base L / R add dot * H' there)
     std::vector<halo::fr_t> defer_xis;

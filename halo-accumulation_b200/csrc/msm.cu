@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(4 * RQ_MAX_T) k_reduce_slabs_quad(const xyzz_t
         const bool has = act && j + stride < T;
         const fq_t other = has ? cA[4 * (j + stride) + k] : zero;
         __syncthreads();
-        Suf = quad_add(Suf, other);
+        if (__any_sync(0xffffffffu, has)) Suf = quad_add(Suf, other);  // warps with nothing to add skip the call (warp uniform)
         if (act) cA[4 * j + k] = Suf;
         __syncthreads();
     }
@@ -726,7 +726,8 @@ __global__ void __launch_bounds__(4 * RQ_MAX_T) k_reduce_slabs_quad(const xyzz_t
         for (int stride = half; stride >= 1; stride >>= 1) {
             const bool on = act && jj < stride;
             const fq_t x = on ? c[4 * jj + k] : zero, y = on ? c[4 * (jj + stride) + k] : zero;
-            const fq_t r = quad_add(x, y);
+            fq_t r = zero;
+            if (__any_sync(0xffffffffu, on)) r = quad_add(x, y);
             __syncthreads();
             if (on) c[4 * jj + k] = r;
             __syncthreads();
@@ -754,7 +755,8 @@ __global__ void __launch_bounds__(4 * RQ_MAX_T) k_reduce_slabs_quad(const xyzz_t
         for (int stride = T >> 1; stride >= 1; stride >>= 1) {
             const bool on = act && j < stride;
             const fq_t x = on ? cA[4 * j + k] : zero, y = on ? cA[4 * (j + stride) + k] : zero;
-            const fq_t r = quad_add(x, y);
+            fq_t r = zero;
+            if (__any_sync(0xffffffffu, on)) r = quad_add(x, y);
             __syncthreads();
             if (on) cA[4 * j + k] = r;
             __syncthreads();
@@ -967,7 +969,11 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
         xyzz_t* slabA = ws.task_partial.as<xyzz_t>();
         xyzz_t* slabR = slabA + (size_t)nwin * plan.red_slabs;
         reduce(dim3(plan.red_slabs, nwin), plan.red_T, plan.red_log_s, buckets, nullptr, plan.M, slabA, slabR, nullptr, 1);
-        int T2 = plan.red_slabs < (uint32_t)maxT ? (int)plan.red_slabs : maxT;
+        // the second level is one CTA per window: with few windows its cost is the latency of its dependent chain, which is
+        // shortest when every scheduler of the SM runs one warp (32 quads); a full 128-quad CTA queues 4 warps per scheduler
+        // and measured 0.17 ms for 128 slabs (profiles/r02_reduce_launches.csv)
+        const int maxT2 = quad ? 32 : maxT;
+        int T2 = plan.red_slabs < (uint32_t)maxT2 ? (int)plan.red_slabs : maxT2;
         int log_s2 = 0;
         while (((uint32_t)T2 << log_s2) < plan.red_slabs) log_s2++;
         reduce(dim3(1, nwin), T2, log_s2, slabR, slabA, plan.red_slabs, d_out + 1, d_out + 2, d_out, 3);

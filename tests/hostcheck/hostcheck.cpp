@@ -18,6 +18,18 @@ void hc_fp_inv(int which, const uint32_t* a, uint32_t* r) {
     if (which) { fr_t x, z; memcpy(&x, a, 32); fp_inv(z, x); memcpy(r, &z, 32); }
     else { fq_t x, z; memcpy(&x, a, 32); fp_inv(z, x); memcpy(r, &z, 32); }
 }
+// count of inputs (n Montgomery residues) on which the division-step inversion (fp_inv) and the Fermat power (fp_inv_fermat)
+// disagree, or a * fp_inv(a) != 1
+uint64_t hc_fp_inv_cross(int which, const uint32_t* a, uint64_t n) {
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (which) { fr_t x, y, z, o, c; memcpy(&x, a + 8 * i, 32); fp_inv(y, x); fp_inv_fermat(z, x); fp_one(o); fp_mul(c, x, y);
+                     bad += !fp_eq(y, z) || (!fp_is_zero(x) && !fp_eq(c, o)) || (fp_is_zero(x) && !fp_is_zero(y)); }
+        else { fq_t x, y, z, o, c; memcpy(&x, a + 8 * i, 32); fp_inv(y, x); fp_inv_fermat(z, x); fp_one(o); fp_mul(c, x, y);
+               bad += !fp_eq(y, z) || (!fp_is_zero(x) && !fp_eq(c, o)) || (fp_is_zero(x) && !fp_is_zero(y)); }
+    }
+    return bad;
+}
 void hc_fp_canon(int which, int to, const uint32_t* a, uint32_t* r) {
     if (which) { fr_t x; if (to) { memcpy(&x, a, 32); fp_to_canon(r, x); } else { fp_from_canon(x, a); memcpy(r, &x, 32); } }
     else { fq_t x; if (to) { memcpy(&x, a, 32); fp_to_canon(r, x); } else { fp_from_canon(x, a); memcpy(r, &x, 32); } }

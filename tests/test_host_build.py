@@ -118,6 +118,29 @@ def test_shared_field_core_vs_python(hostcheck, oracle, tag):
 
 
 @pytest.mark.parametrize("tag", ["portable", "host64"])
+def test_division_step_inversion_vs_fermat(hostcheck, oracle, tag):
+    """fp_inv (Bernstein-Yang division steps on signed 30-bit limbs, csrc/fp.cuh) against the Fermat power it replaced and
+    against Python's pow(a, -1, p): edge values (0, 1, 2, p - 1, p - 2, powers of two around the limb boundaries, values with
+    long runs of zero / one bits) and 20 000 random residues per field."""
+    hc = hostcheck[tag]
+    hc.hc_fp_inv_cross.restype = C.c_uint64
+    rnd = random.Random(99)
+    for which, mod in ((0, PR.P), (1, PR.R)):
+        edge = [0, 1, 2, 3, mod - 1, mod - 2, (mod + 1) // 2, (1 << 256) % mod, (1 << 255) % mod, (1 << 254) - 1, 1 << 253]
+        edge += [1 << k for k in (29, 30, 31, 32, 59, 60, 61, 89, 90, 119, 120, 149, 150, 239, 240, 241, 252)]
+        edge += [(1 << k) - 1 for k in (30, 60, 90, 120, 150, 180, 210, 240, 254)] + [mod - (1 << k) for k in (30, 60, 120, 240)]
+        vals = edge + [rnd.randrange(mod) for _ in range(20000)]
+        A = np.array([oracle.int_to_limbs(v) for v in vals], dtype=np.uint64)
+        assert hc.hc_fp_inv_cross(which, _p32(A), C.c_uint64(len(vals))) == 0
+        r2 = pow(1 << 256, 2, mod)
+        for a in edge[1:] + vals[len(edge):len(edge) + 200]:
+            Aa = np.array(oracle.int_to_limbs(a), dtype=np.uint64)
+            r = np.zeros(4, dtype=np.uint64)
+            hc.hc_fp_inv(which, _p32(Aa), _p32(r))
+            assert oracle.limbs_to_int(r) == pow(a, -1, mod) * r2 % mod
+
+
+@pytest.mark.parametrize("tag", ["portable", "host64"])
 def test_shared_group_law_vs_oracle(hostcheck, oracle, tag):
     hc, O = hostcheck[tag], oracle
     GS = O.derive_points(2, 32)
