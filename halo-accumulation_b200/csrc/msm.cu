@@ -827,12 +827,16 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
     // pair-tree passes (msm_pairs.cu): worthwhile once the per-pass fixed costs (7 launches and one ~0.1 ms inversion
     // latency) are small against the additions saved; bucket segments are then padded to multiples of 2^P slots
     int P = 0;
-    if (ctx->tune_pair_passes >= 0)
+    if (ctx->tune_pair_passes >= 0) {
         P = ctx->tune_pair_passes;
-    else if (total_entries_max >= ((uint64_t)1 << 25) && total_entries_max >= (uint64_t)NB * 64)
-        P = 4;  // measured (profiles/r01_pair_tree_sweep.jsonl): 2^24 FIXED 36.6 -> 29.3 ms, 2^22 11.2 -> 8.6 ms
-    else if (total_entries_max >= ((uint64_t)1 << 23) && total_entries_max >= (uint64_t)NB * 32)
-        P = 2;  // 2^20 FIXED: 3.07 -> 2.69 ms
+    } else if (total_entries_max >= ((uint64_t)1 << 21)) {
+        // measured per size and mode (profiles/r02_pair_passes_sweep.jsonl; round 1: profiles/r01_pair_tree_sweep.jsonl): what
+        // decides is the mean bucket fill -- every pass halves it at 6.2 instead of 10 multiplications per addition but costs
+        // ~0.1 ms of hierarchy latency and pads every bucket to a multiple of 2^P slots.
+        //   FIXED 2^18 .. 2^24: fill 14 / 28 / 56 / 112 / 224 / 416 -> best P = 2 / 2 / 3 / 3 / 4 / 4;  variable 2^19 .. 2^22: 16 / 32 / 64 / 128 -> 2 / 2 / 3 / 4
+        const uint64_t fill = total_entries_max / NB;
+        P = fill < 12 ? 0 : fill < 48 ? 2 : fill < 120 ? 3 : 4;
+    }
     if (P > 8) P = 8;
     const uint32_t rmask = (1u << P) - 1u;
     uint64_t slots_max = total_entries_max + (uint64_t)rmask * NB;

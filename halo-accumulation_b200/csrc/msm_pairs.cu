@@ -29,7 +29,7 @@ namespace halo {
 
 constexpr int PT_K = 16;   // pairs per thread in k_pair_fwd / k_pair_bwd
 constexpr int PT_KU = 16;  // fan-in of the product hierarchy
-constexpr uint32_t PT_INV_MAX = 16384;  // k_inv is pure latency (0.12 ms) up to here; 65536 values take 0.27 ms
+constexpr uint32_t PT_INV_MAX = 65536;  // values inverted one per thread at the top of the hierarchy (division steps: 24 us of latency; was 16384 with the 0.105 ms Fermat chain)
 constexpr uint32_t PT_SENTINEL = 0xffffffffu;  // entry that stands for the point at infinity (padding)
 
 enum : int { PT_SKIP = 0, PT_ADD = 1, PT_DBL = 2 };
