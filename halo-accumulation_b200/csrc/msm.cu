@@ -273,8 +273,11 @@ __device__ __forceinline__ uint32_t acc_entry(const uint32_t* __restrict__ entri
 template <bool DIRECT>
 __device__ __forceinline__ affine_t acc_base(const affine_t* __restrict__ bases, uint32_t n, const affine_t* __restrict__ tail_bases,
                                              uint32_t ent) {
-    if (DIRECT) {
-        affine_t p = bases[ent];
+    if (DIRECT) {  // slot arrays are SoA: x[0 .. n) | y[0 .. n), n = capacity of the last pair-tree pass
+        const fq_t* xs = reinterpret_cast<const fq_t*>(bases);
+        affine_t p;
+        p.x = xs[ent];
+        p.y = xs[(size_t)n + ent];
         if (p.x.v[7] == 0xffffffffu) affine_set_inf(p);
         return p;
     }
@@ -900,7 +903,7 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
         k_shift_offsets<<<(NB + 1 + 255) / 256, 256, 0, st>>>(offsets, NB + 1, P, ws.cursor.as<uint32_t>());
         ctx->kernel_launches++;
         acc_offsets = ws.cursor.as<uint32_t>();
-        acc_n = 0;
+        acc_n = (uint32_t)(slots_max >> P);  // DIRECT mode: the y array starts this many elements behind the x array
         acc_entries_max = slots_max >> P;
     }
     // oversized-bucket threshold: 4x the mean fill, at least 1024 entries (uniform scalars never reach it)

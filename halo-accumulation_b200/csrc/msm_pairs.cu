@@ -131,9 +131,9 @@ __device__ __forceinline__ uint32_t pt_pair_index(uint32_t gwarp, int s, uint32_
 // ---- forward ---------------------------------------------------------------------------------------------------------
 template <bool PASS0>
 __global__ void __launch_bounds__(128) k_pair_fwd(const uint32_t* __restrict__ entries, const affine_t* __restrict__ bases, uint32_t n,
-                                                  const affine_t* __restrict__ tail_bases, const affine_t* __restrict__ in,
-                                                  const uint32_t* __restrict__ total_slots, int pass, fq_t* __restrict__ prefix,
-                                                  fq_t* __restrict__ totals) {
+                                                  const affine_t* __restrict__ tail_bases, const fq_t* __restrict__ in_x,
+                                                  const fq_t* __restrict__ in_y, const uint32_t* __restrict__ total_slots, int pass,
+                                                  fq_t* __restrict__ prefix, fq_t* __restrict__ totals) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gwarp = tid >> 5, lane = tid & 31u;
     const uint32_t Q = *total_slots >> (pass + 1);
@@ -160,13 +160,13 @@ __global__ void __launch_bounds__(128) k_pair_fwd(const uint32_t* __restrict__ e
                 by = b.y;
             } else {
                 if (!live) break;
-                ax = in[2 * (size_t)q].x;
-                bx = in[2 * (size_t)q + 1].x;
+                ax = in_x[2 * (size_t)q];  // the slot arrays are SoA: this pass reads x only, half the bytes of x | y records
+                bx = in_x[2 * (size_t)q + 1];
                 ainf = pt_x_is_inf(ax);
                 binf = pt_x_is_inf(bx);
                 if (!ainf && !binf && fp_eq(ax, bx)) {
-                    ay = in[2 * (size_t)q].y;
-                    by = in[2 * (size_t)q + 1].y;
+                    ay = in_y[2 * (size_t)q];
+                    by = in_y[2 * (size_t)q + 1];
                 } else {
                     fp_zero(ay);
                     fp_zero(by);
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128, HALO_PAIR_BWD0_BLOCKS) k_pair_bwd0(const 
                                                                           uint32_t n, const affine_t* __restrict__ tail_bases,
                                                                           const uint32_t* __restrict__ total_slots,
                                                                           const fq_t* __restrict__ prefix, const fq_t* __restrict__ tot_inv,
-                                                                          affine_t* __restrict__ out) {
+                                                                          fq_t* __restrict__ out_x, fq_t* __restrict__ out_y) {
     __shared__ BwdTile tiles[4][2];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gwarp = tid >> 5, lane = tid & 31u;
@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(128, HALO_PAIR_BWD0_BLOCKS) k_pair_bwd0(const 
             pt_take_staged(a, ainf, tile[s & 1], 0, e0.x, lane);
             pt_take_staged(b, binf, tile[s & 1], 1, e0.y, lane);
             pt_pair_finish(r, a, ainf, b, binf, invtot, prefix, q);
-            out[q] = r;
+            out_x[q] = r.x;
+            out_y[q] = r.y;
         }
         __syncwarp();  // every lane has read its row before the stage two steps on overwrites this buffer
         e0 = e1;
@@ -358,9 +359,9 @@ __global__ void __launch_bounds__(128, HALO_PAIR_BWD0_BLOCKS) k_pair_bwd0(const 
 template <bool PASS0>
 __global__ void __launch_bounds__(128, 7) k_pair_bwd(const uint32_t* __restrict__ entries, const affine_t* __restrict__ bases,
                                                      uint32_t n, const affine_t* __restrict__ tail_bases,
-                                                     const affine_t* __restrict__ in, const uint32_t* __restrict__ total_slots,
-                                                     int pass, const fq_t* __restrict__ prefix, const fq_t* __restrict__ tot_inv,
-                                                     affine_t* __restrict__ out) {
+                                                     const fq_t* __restrict__ in_x, const fq_t* __restrict__ in_y,
+                                                     const uint32_t* __restrict__ total_slots, int pass, const fq_t* __restrict__ prefix,
+                                                     const fq_t* __restrict__ tot_inv, fq_t* __restrict__ out_x, fq_t* __restrict__ out_y) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gwarp = tid >> 5, lane = tid & 31u;
     const uint32_t Q = *total_slots >> (pass + 1);
@@ -378,14 +379,17 @@ __global__ void __launch_bounds__(128, 7) k_pair_bwd(const uint32_t* __restrict_
             pt_gather(a, ainf, e.x, bases, n, tail_bases);
             pt_gather(b, binf, e.y, bases, n, tail_bases);
         } else {
-            a = in[2 * (size_t)q];
-            b = in[2 * (size_t)q + 1];
+            a.x = in_x[2 * (size_t)q];
+            b.x = in_x[2 * (size_t)q + 1];
+            a.y = in_y[2 * (size_t)q];
+            b.y = in_y[2 * (size_t)q + 1];
             ainf = pt_x_is_inf(a.x);
             binf = pt_x_is_inf(b.x);
         }
         affine_t r;
         pt_pair_finish(r, a, ainf, b, binf, invtot, prefix, q);
-        out[q] = r;
+        out_x[q] = r.x;
+        out_y[q] = r.y;
     }
 }
 
@@ -421,7 +425,10 @@ const affine_t* pair_tree_enqueue(halo_ctx* ctx, MsmWorkspace& ws, cudaStream_t 
     for (int j = 0; j < L; j++) lv_total += (size_t)sizes[j] * 2;  // values + prefixes per level
     ws.pt_levels.reserve(lv_total * sizeof(fq_t));
 
-    const affine_t* src = nullptr;
+    // Slot arrays are SoA: after pass p the Q_p = slots_max >> (p + 1) slots live as x[0 .. Q_p) | y[0 .. Q_p) in the pass's
+    // ping-pong buffer (the forward kernel of the next pass reads x only).
+    const fq_t* src_x = nullptr;
+    const fq_t* src_y = nullptr;
     const uint32_t nb = in.n;
     for (int p = 0; p < passes; p++) {
         const uint64_t Q = slots_max >> (p + 1);
@@ -434,29 +441,31 @@ const affine_t* pair_tree_enqueue(halo_ctx* ctx, MsmWorkspace& ws, cudaStream_t 
             pres[j] = lv + sizes[j];
             lv += (size_t)sizes[j] * 2;
         }
-        affine_t* dst = (p & 1) ? ws.pt_b.as<affine_t>() : ws.pt_a.as<affine_t>();
+        fq_t* dst_x = (p & 1) ? ws.pt_b.as<fq_t>() : ws.pt_a.as<fq_t>();
+        fq_t* dst_y = dst_x + Q;
         fq_t* prefix = ws.pt_prefix.as<fq_t>();
         if (p == 0)
-            k_pair_fwd<true><<<grids[0], 128, 0, st>>>(entries, in.bases, in.fixed_stride ? 0x7fffffffu : nb, in.tail_bases, nullptr,
+            k_pair_fwd<true><<<grids[0], 128, 0, st>>>(entries, in.bases, in.fixed_stride ? 0x7fffffffu : nb, in.tail_bases, nullptr, nullptr,
                                                        total_slots, p, prefix, vals[0]);
         else
-            k_pair_fwd<false><<<grids[0], 128, 0, st>>>(nullptr, nullptr, 0, nullptr, src, total_slots, p, prefix, vals[0]);
+            k_pair_fwd<false><<<grids[0], 128, 0, st>>>(nullptr, nullptr, 0, nullptr, src_x, src_y, total_slots, p, prefix, vals[0]);
         for (int j = 0; j + 1 < L; j++) k_prod_up<<<grids[j + 1], 128, 0, st>>>(vals[j], sizes[j], pres[j], vals[j + 1]);
         k_inv<<<ceil_div(sizes[L - 1], 128), 128, 0, st>>>(vals[L - 1], sizes[L - 1]);
         for (int j = L - 2; j >= 0; j--) k_prod_down<<<grids[j + 1], 128, 0, st>>>(vals[j], sizes[j], pres[j], vals[j + 1]);
         if (p == 0 && ctx->tune_pair_bwd_async)
             k_pair_bwd0<<<grids[0], 128, 0, st>>>(entries, in.bases, in.fixed_stride ? 0x7fffffffu : nb, in.tail_bases, total_slots, prefix,
-                                                  vals[0], dst);
+                                                  vals[0], dst_x, dst_y);
         else if (p == 0)
-            k_pair_bwd<true><<<grids[0], 128, 0, st>>>(entries, in.bases, in.fixed_stride ? 0x7fffffffu : nb, in.tail_bases, nullptr,
-                                                       total_slots, p, prefix, vals[0], dst);
+            k_pair_bwd<true><<<grids[0], 128, 0, st>>>(entries, in.bases, in.fixed_stride ? 0x7fffffffu : nb, in.tail_bases, nullptr, nullptr,
+                                                       total_slots, p, prefix, vals[0], dst_x, dst_y);
         else
-            k_pair_bwd<false><<<grids[0], 128, 0, st>>>(nullptr, nullptr, 0, nullptr, src, total_slots, p, prefix, vals[0], dst);
+            k_pair_bwd<false><<<grids[0], 128, 0, st>>>(nullptr, nullptr, 0, nullptr, src_x, src_y, total_slots, p, prefix, vals[0], dst_x, dst_y);
         ctx->kernel_launches += 2 + 2 * (uint64_t)(L - 1) + 1;
-        src = dst;
+        src_x = dst_x;
+        src_y = dst_y;
     }
     HALO_CUDA(cudaGetLastError());
-    return src;
+    return reinterpret_cast<const affine_t*>(src_x);  // x[0 .. Q) | y[0 .. Q) with Q = slots_max >> passes (DIRECT mode of k_accumulate)
 }
 
 // In-place inversion of n non-zero field elements through the same product hierarchy (3 multiplications per element
