@@ -379,6 +379,60 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_static(
     buckets[b] = acc;
 }
 
+// Four lanes per bucket (small MSMs).  With one lane per bucket a small MSM's accumulation lasts as long as its LONGEST
+// bucket: fills are Poisson, so at a mean of 8-16 entries some bucket has ~35 and the kernel takes 35 dependent mixed additions
+// (3.6 us each) while the average lane is done after 8 (ncu, 2^13 points: SMs active 56 % of the kernel, 18.5 of 32 lanes active
+// per instruction).  Here lane k of a quad adds the entries k, k + 4, .. of the bucket and the four partial sums are merged by
+// two shuffle steps (two full additions): chains of ~9 + 2 instead of ~35.  Used while four lanes per bucket fit about one wave
+// of the machine (<= 2^15 buckets, no pair-tree passes); oversized buckets go to the split kernels as before.
+__device__ __forceinline__ void xyzz_shfl_xor(xyzz_t& dst, const xyzz_t& src, int mask) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        dst.x.v[i] = __shfl_xor_sync(0xffffffffu, src.x.v[i], mask);
+        dst.y.v[i] = __shfl_xor_sync(0xffffffffu, src.y.v[i], mask);
+        dst.zz.v[i] = __shfl_xor_sync(0xffffffffu, src.zz.v[i], mask);
+        dst.zzz.v[i] = __shfl_xor_sync(0xffffffffu, src.zzz.v[i], mask);
+    }
+}
+__device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q);
+__global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_quad(const affine_t* __restrict__ bases, uint32_t n,
+                                                                              const affine_t* __restrict__ tail_bases,
+                                                                              const uint32_t* __restrict__ offsets,
+                                                                              const uint32_t* __restrict__ entries, uint32_t NB,
+                                                                              xyzz_t* __restrict__ buckets, uint32_t split_len) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = gt >> 2, k = gt & 3u;
+    uint32_t beg = 0, end = 0;
+    if (b < NB) {
+        beg = offsets[b];
+        end = offsets[b + 1];
+        if (end - beg > split_len) end = beg;  // oversized bucket: k_accumulate_split
+    }
+    xyzz_t acc;
+    xyzz_set_inf(acc);
+    // software pipeline as in k_accumulate_static, stride 4
+    uint32_t e = beg + k;
+    uint32_t ent1 = e < end ? entries[e] : 0, ent2 = e + 4 < end ? entries[e + 4] : 0;
+    affine_t p1;
+    affine_set_inf(p1);
+    if (e < end) p1 = acc_base<false>(bases, n, tail_bases, ent1);
+    for (; e < end; e += 4) {
+        const uint32_t ent0 = ent1;
+        const affine_t p0 = p1;
+        ent1 = ent2;
+        if (e + 8 < end) ent2 = entries[e + 8];
+        if (e + 4 < end) p1 = acc_base<false>(bases, n, tail_bases, ent1);
+        xyzz_madd(acc, p0, (ent0 >> 31) != 0);
+    }
+    // merge the quad: every lane of the warp takes part in the shuffles
+    xyzz_t other;
+    xyzz_shfl_xor(other, acc, 1);
+    xyzz_add_nl(acc, other);
+    xyzz_shfl_xor(other, acc, 2);
+    xyzz_add_nl(acc, other);
+    if (b < NB && k == 0 && !(offsets[b + 1] - offsets[b] > split_len)) buckets[b] = acc;
+}
+
 __device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q) { xyzz_add(acc, q); }
 __device__ __noinline__ void xyzz_dbl_nl(xyzz_t& acc) { xyzz_dbl(acc, acc); }
 
@@ -920,7 +974,13 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
     // thread-per-bucket is ~8 % faster when buckets are deep and evenly filled (variable base, large n); lane-level
     // claiming wins everywhere else (measured: profiles/r01_accumulate_static_vs_dynamic.txt)
     const bool deep = !P && !plan.fixed && (uint64_t)ntot * plan.W >= (uint64_t)NB * 256;
-    if (ctx->tune_acc_static == 1 || (ctx->tune_acc_static == 0 && deep)) {
+    // measured (profiles/r02_acc_quad_ab.jsonl): 2^8 .. 2^14 points (<= 24 576 buckets) 0.080 -> 0.041, 0.108 -> 0.055, 0.197 -> 0.165,
+    // 0.324 -> 0.229 ms; at 2^15 / 2^16 (82 k buckets: 4.3 waves of quads, two extra full additions per bucket) it loses
+    const bool quad_lanes = !P && ctx->tune_acc_quad != 0 && NB <= (1u << 15) && ctx->tune_acc_static == 0 && !deep;
+    if (quad_lanes) {
+        k_accumulate_quad<<<(unsigned)(((uint64_t)NB * 4 + 127) / 128), 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB,
+                                                                                  buckets, split_len);
+    } else if (ctx->tune_acc_static == 1 || (ctx->tune_acc_static == 0 && deep)) {
         if (P)
             k_accumulate_static<true><<<(NB + 127) / 128, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB,
                                                                        buckets, split_len);
@@ -1056,6 +1116,15 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, cons
         HALO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // later main-stream work (the fold) is ordered after lane 1
     }
     if (while_running) (*while_running)();  // host work that overlaps the kernels enqueued above
+    // A pair of very unequal MSMs on the two lanes (pcdl::check: <G, h> of 2^20 points beside the 2 lg n + 2 point MSM of the
+    // succinct check): the small one is done long before the large one, so its ~255 host doublings are finished while the
+    // large one still runs instead of after it.
+    bool early[MAXB] = {false, false, false, false};
+    if (two_lanes && count == 2 && !plans[1].fixed && (uint64_t)ins[1].n * 64 <= ins[0].n) {
+        HALO_CUDA(cudaEventSynchronize(ctx->ev_join));  // lane 1's partials are on the host
+        msm_finish_host(h_parts + 1 * SLOT, plans[1], outs[1]);
+        early[1] = true;
+    }
     if (any) HALO_CUDA(cudaStreamSynchronize(ctx->stream));
     if (any && ctx->profile) {
         float t[5];
@@ -1070,6 +1139,7 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, cons
     // the Horner combination of a variable-base MSM is ~255 host doublings (~0.1 ms): the two results of an IPA round
     // (L and R) are finished on two host threads
     auto finish = [&](int k) {
+        if (early[k]) return;
         if (ins[k].n + ins[k].n_tail == 0)
             xyzz_set_inf(outs[k]);
         else
