@@ -237,6 +237,7 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     if (!strcmp(key, "acc_static")) ctx->tune_acc_static = value;
     else if (!strcmp(key, "acc_blocks_per_sm")) ctx->tune_acc_blocks_per_sm = value;
     else if (!strcmp(key, "acc_quad")) ctx->tune_acc_quad = value;
+    else if (!strcmp(key, "acc_quad_max_buckets")) ctx->tune_acc_quad_max_buckets = value;
     else if (!strcmp(key, "pair_passes")) ctx->tune_pair_passes = value;
     else if (!strcmp(key, "split_blocking")) ctx->tune_split_blocking = value;
     else if (!strcmp(key, "split_first_16ths")) ctx->tune_split_first_16ths = value < 1 ? 1 : value > 15 ? 15 : value;

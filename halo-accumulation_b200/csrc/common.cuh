@@ -192,6 +192,7 @@ struct halo_ctx {
     int force_c = 0;
     int tune_acc_static = 0, tune_acc_blocks_per_sm = 0;
     int tune_acc_quad = 1;  // small MSMs: four lanes per bucket (k_accumulate_quad); 0: one lane per bucket
+    int tune_acc_quad_max_buckets = 1 << 15;
     bool force_two_lanes = false;  // run a pair of large MSMs (deferred IPA rounds) on the two lanes as well
     int tune_ipa_two_lanes = 1, tune_ipa_freeze_len = 0;
     int tune_ipa_frozen_c = 11;  // window of the frozen-tail MSMs (8192 points): round 1 measured 10 best with the one-lane single-slab reduction;

@@ -976,7 +976,7 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
     const bool deep = !P && !plan.fixed && (uint64_t)ntot * plan.W >= (uint64_t)NB * 256;
     // measured (profiles/r02_acc_quad_ab.jsonl): 2^8 .. 2^14 points (<= 24 576 buckets) 0.080 -> 0.041, 0.108 -> 0.055, 0.197 -> 0.165,
     // 0.324 -> 0.229 ms; at 2^15 / 2^16 (82 k buckets: 4.3 waves of quads, two extra full additions per bucket) it loses
-    const bool quad_lanes = !P && ctx->tune_acc_quad != 0 && NB <= (1u << 15) && ctx->tune_acc_static == 0 && !deep;
+    const bool quad_lanes = !P && ctx->tune_acc_quad != 0 && NB <= (uint32_t)ctx->tune_acc_quad_max_buckets && ctx->tune_acc_static == 0 && !deep;
     if (quad_lanes) {
         k_accumulate_quad<<<(unsigned)(((uint64_t)NB * 4 + 127) / 128), 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB,
                                                                                   buckets, split_len);

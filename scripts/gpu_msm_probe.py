@@ -10,6 +10,10 @@ def emit(**kw):
 lgs = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [16, 18, 20, 22, 24]
 cs_fixed = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 ctx = H.Context(0, 1 << max(lgs))
+import os
+for kv in os.environ.get('TUNE', '').split(','):
+    if kv:
+        k_, v_ = kv.split('='); ctx.set_tuning(k_, int(v_))
 ctx.set_profiling(True)
 for lg in lgs:
     n = 1 << lg
