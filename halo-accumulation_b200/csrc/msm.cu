@@ -85,7 +85,9 @@ static int ceil_lg(uint64_t n) {
 // total cost = W * (n mixed adds) + bucket reduction (~2.5 full adds per bucket).
 MsmPlan msm_make_plan(uint64_t n, int force_c) {
     const int lg = ceil_lg(n);
-    int c = lg <= 6 ? 4 : lg <= 8 ? 7 : lg <= 10 ? 8 : lg <= 14 ? 11 : lg <= 16 ? 13 : lg <= 17 ? 14 : 16;
+    // (third sweep, with four lanes per bucket below 2^15 buckets and the pair-pass policy by bucket fill:
+    // profiles/r02_msm_window_sweep_variable_v3.txt -- smaller windows pay once their buckets are full enough for tree passes)
+    int c = lg <= 6 ? 4 : lg <= 8 ? 7 : lg <= 10 ? 8 : lg <= 12 ? 11 : lg <= 15 ? 10 : lg <= 16 ? 11 : lg <= 19 ? 13 : 16;
     if (force_c) c = force_c;
     if (c < 4) c = 4;  // W = 255 / c + 1 <= MSM_MAX_WINDOWS
     if (c > 20) c = 20;
