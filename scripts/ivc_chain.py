@@ -32,13 +32,14 @@ def random_instance(draws):
     return acc.new_instance(Cm, d, z, v, pi)
 
 t_inst = t_prov = t_ver = 0.0
+inst_ms, prov_ms = [], []
 a, qss, accs = None, [], []
 for s in range(k):
     draws = draw_instance()
     h0, w, q, wb = rs(2), rs(1)[0], rs(n - 1), rs(1)[0]
-    t = time.perf_counter(); q_new = random_instance(draws); t_inst += time.perf_counter() - t
+    t = time.perf_counter(); q_new = random_instance(draws); t_inst += time.perf_counter() - t; inst_ms.append((time.perf_counter() - t) * 1e3)
     qs = [acc.to_instance(a), q_new] if a is not None else [q_new]
-    t = time.perf_counter(); a = acc.prover(ctx, d, qs, h0, w, q, wb); t_prov += time.perf_counter() - t
+    t = time.perf_counter(); a = acc.prover(ctx, d, qs, h0, w, q, wb); t_prov += time.perf_counter() - t; prov_ms.append((time.perf_counter() - t) * 1e3)
     qss.append(qs); accs.append(a)
 t = time.perf_counter()
 for qs, ac in zip(qss, accs):
@@ -56,7 +57,8 @@ oracle_verifier = {s: O.acc_verifier(d, [as_o(q, O.Instance) for q in qss[s]], a
 t = time.perf_counter(); oracle_decider = O.acc_decider(as_o(accs[-1], O.Accumulator), threads=T); t_odec = time.perf_counter() - t
 all_accept = all(rc == 0 for rc in oracle_verifier.values()) and oracle_decider == 0
 print(json.dumps({"config": f"ivc_chain_2^{lg}_k{k}", "setup_s": setup_s, "random_instance_ms": t_inst / k * 1e3, "prover_ms": t_prov / k * 1e3,
-                  "verifier_ms": t_ver / k * 1e3, "decider_ms": t_dec * 1e3, "fast_path_total_s": t_ver + t_dec,
+                  "random_instance_ms_median": float(np.median(inst_ms)), "prover_ms_median": float(np.median(prov_ms)),
+                  "random_instance_ms_first3": inst_ms[:3], "verifier_ms": t_ver / k * 1e3, "decider_ms": t_dec * 1e3, "fast_path_total_s": t_ver + t_dec,
                   "chain_total_s": t_inst + t_prov, "kernel_launches": ctx.kernel_launches(), "all_accept": all_accept,
                   "oracle": {"acc_verifier_rc_at_steps": {str(s): rc for s, rc in oracle_verifier.items()}, "acc_decider_rc": oracle_decider,
                              "acc_decider_cpu_ms": t_odec * 1e3, "threads": T}}))
