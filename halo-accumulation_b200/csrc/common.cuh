@@ -205,7 +205,8 @@ struct halo_ctx {
     int tune_split_blocking = 23;  // halo_msm_gens: two point slices through the pipeline slots for n >= 2^this (0: never)
     int tune_split_first_16ths = 5;  // size of the first slice in sixteenths of n: its H2D copy is exposed, the second slice's copy hides behind
                                      // the first slice's kernels (2^24: 8 -> 41.1 ms, 6 -> 38.4, 5 -> 38.2, 4 -> 39.7, 3 -> 41.0; scripts/gpu_split_probe.py)
-    int tune_pair_bwd_async = 0;  // pass 0 of the pair tree: 1 = cp.async-staged operands (k_pair_bwd0; measured +-1 %: profiles/r02_pair_bwd_async_ab.jsonl), 0 = per-lane gathers
+    int tune_pair_bwd_async = 1;  // pass 0 of the pair tree: 1 = cp.async-staged operands + prefix loaded a step ahead (k_pair_bwd0, 5 CTAs per SM:
+                                  // accumulation phase at 2^24 27.39 -> 26.75 ms; profiles/r02_pair_bwd_async_ab.jsonl), 0 = per-lane gathers
     int tune_reduce_quad = 1;   // 0: one-lane bucket reduction (k_reduce_slabs), for A/B measurements
     int tune_pair_passes = -1;  // -1: automatic; 0: XYZZ accumulation only; P > 0: force P pair-tree passes
     uint64_t kernel_launches = 0;

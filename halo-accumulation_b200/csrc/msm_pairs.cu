@@ -228,8 +228,9 @@ __global__ void __launch_bounds__(128) k_prod_down(fq_t* __restrict__ vals, uint
 // the 64 bases of step s - 1 are in flight, fetched cooperatively (4 adjacent lanes copy the four 16-byte chunks of one
 // base with ONE instruction -- the access pattern that reaches HBM's random-access rate, see pt_gather_pair_coop) straight
 // into the owner lane's row of the tile.  No registers hold data in flight (the register prefetch and the shuffle
-// transpose of round 1 both lost to register pressure), entries are loaded two steps ahead.  Two 4 KiB buffers per warp,
-// 32 KiB per CTA, 6 CTAs per SM.
+// transpose of round 1 both lost to register pressure), entries are loaded two steps ahead and the step's prefix one step
+// ahead (staging alone measured +-1 %: with the operands in shared memory every step still waited for that 32-byte load).
+// Two 4 KiB buffers per warp, 32 KiB per CTA; 5 CTAs per SM measured best (6: spills, 4: too few warps).
 struct BwdTile {
     uint4 v[2][32][4];  // [operand][owner lane][16-byte chunk]
 };
@@ -272,7 +273,7 @@ __device__ __forceinline__ void pt_take_staged(affine_t& p, bool& inf, const Bwd
 
 // The arithmetic of one pair, shared by both instantiations: 1/den from the thread's running inverse and prefix[q].
 __device__ __forceinline__ void pt_pair_finish(affine_t& r, const affine_t& a, bool ainf, const affine_t& b, bool binf, fq_t& invtot,
-                                               const fq_t* __restrict__ prefix, uint32_t q) {
+                                               const fq_t& pre) {
     fq_t den;
     const int mode = pt_classify(den, ainf, binf, a.x, b.x, a.y, b.y);
     if (mode == PT_SKIP) {
@@ -285,7 +286,7 @@ __device__ __forceinline__ void pt_pair_finish(affine_t& r, const affine_t& a, b
         else
             pt_set_inf(r);  // a = -b
     } else {
-        fq_t inv, pre = prefix[q], num, lam, t;
+        fq_t inv, num, lam, t;
         fp_mul(inv, invtot, pre);
         fp_mul(invtot, invtot, den);
         if (mode == PT_ADD) {
@@ -306,7 +307,7 @@ __device__ __forceinline__ void pt_pair_finish(affine_t& r, const affine_t& a, b
 }
 
 #ifndef HALO_PAIR_BWD0_BLOCKS
-#define HALO_PAIR_BWD0_BLOCKS 6
+#define HALO_PAIR_BWD0_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(128, HALO_PAIR_BWD0_BLOCKS) k_pair_bwd0(const uint32_t* __restrict__ entries, const affine_t* __restrict__ bases,
                                                                           uint32_t n, const affine_t* __restrict__ tail_bases,
@@ -328,9 +329,21 @@ __global__ void __launch_bounds__(128, HALO_PAIR_BWD0_BLOCKS) k_pair_bwd0(const 
     };
     uint2 e0 = load_entry(PT_K - 1), e1 = load_entry(PT_K - 2);
     pt_stage_pair_async(tile[(PT_K - 1) & 1], e0, bases, n, tail_bases, lane);
+    // the prefix of the step after this one is loaded a step ahead as well: with the operands staged, this 32-byte load was
+    // what every step still waited for
+    auto load_prefix = [&](int s) {
+        const uint32_t q = pt_pair_index(gwarp, s, lane);
+        fq_t v;
+        fp_zero(v);
+        if (q < Q) v = prefix[q];
+        return v;
+    };
+    fq_t pre0 = load_prefix(PT_K - 1);
 #pragma unroll 1
     for (int s = PT_K - 1; s >= 0; s--) {
         const uint2 e2 = s >= 2 ? load_entry(s - 2) : none;
+        fq_t pre1;
+        if (s >= 1) pre1 = load_prefix(s - 1); else fp_zero(pre1);
         if (s >= 1) {
             pt_stage_pair_async(tile[(s - 1) & 1], e1, bases, n, tail_bases, lane);
             cp_async_wait<1>();
@@ -344,13 +357,14 @@ __global__ void __launch_bounds__(128, HALO_PAIR_BWD0_BLOCKS) k_pair_bwd0(const 
             bool ainf, binf;
             pt_take_staged(a, ainf, tile[s & 1], 0, e0.x, lane);
             pt_take_staged(b, binf, tile[s & 1], 1, e0.y, lane);
-            pt_pair_finish(r, a, ainf, b, binf, invtot, prefix, q);
+            pt_pair_finish(r, a, ainf, b, binf, invtot, pre0);
             out_x[q] = r.x;
             out_y[q] = r.y;
         }
         __syncwarp();  // every lane has read its row before the stage two steps on overwrites this buffer
         e0 = e1;
         e1 = e2;
+        pre0 = pre1;
     }
 }
 
@@ -387,7 +401,8 @@ __global__ void __launch_bounds__(128, 7) k_pair_bwd(const uint32_t* __restrict_
             binf = pt_x_is_inf(b.x);
         }
         affine_t r;
-        pt_pair_finish(r, a, ainf, b, binf, invtot, prefix, q);
+        const fq_t pre = prefix[q];
+        pt_pair_finish(r, a, ainf, b, binf, invtot, pre);
         out_x[q] = r.x;
         out_y[q] = r.y;
     }
