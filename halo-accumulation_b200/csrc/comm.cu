@@ -114,6 +114,12 @@ struct halo_comm {
     DevBuf send, recv;     // [PART_SLOTS] and [size][PART_SLOTS] XYZZ slots (only the used prefix is gathered)
     xyzz_t* h_recv = nullptr;    // pinned, [size][PART_SLOTS]
     PartHeader* h_hdr = nullptr;  // pinned
+    // halo_comm_allgather_sum runs here, not on the context's stream: in the pipelined pattern (submit k + 1, collect k,
+    // combine k) the context's stream already holds the kernels of MSM k + 1, and a collective queued behind them would make
+    // every step wait for the next one
+    cudaStream_t side = nullptr;
+    DevBuf side_send, side_recv;
+    uint64_t* h_side = nullptr;  // pinned, [size][12]
 };
 
 namespace {
@@ -147,6 +153,12 @@ void comm_alloc(halo_comm* c) {
     c->recv.reserve((size_t)c->size * PART_SLOTS * sizeof(xyzz_t));
     HALO_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_recv), (size_t)c->size * PART_SLOTS * sizeof(xyzz_t)));
     HALO_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_hdr), sizeof(PartHeader)));
+    int prio_lo = 0, prio_hi = 0;
+    HALO_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    HALO_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));  // its one-CTA kernels go ahead of queued MSM CTAs
+    c->side_send.reserve(96);
+    c->side_recv.reserve((size_t)96 * c->size);
+    HALO_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_side), (size_t)96 * c->size));
 }
 
 // The plan every rank uses for an MSM over `n_global` points: FIXED-base when every rank holds tables built with the
@@ -270,10 +282,17 @@ void halo_comm_destroy(halo_comm* c) {
     if (c->ctx && c->ctx->stream) cudaStreamSynchronize(c->ctx->stream);
     NcclApi* api = nccl_api();
     if (c->comm && api) api->CommDestroy(c->comm);
+    if (c->side) {
+        cudaStreamSynchronize(c->side);
+        cudaStreamDestroy(c->side);
+    }
     c->send.release();
     c->recv.release();
+    c->side_send.release();
+    c->side_recv.release();
     if (c->h_recv) cudaFreeHost(c->h_recv);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    if (c->h_side) cudaFreeHost(c->h_side);
     delete c;
 }
 
@@ -347,12 +366,12 @@ int halo_comm_allgather_sum(halo_comm* c, const uint64_t point_jac[12], uint64_t
     NcclApi* api = nccl_api();
     if (!api) return comm_fail(ctx, HALO_ENCCL, nccl_load_error());
     COMM_TRY(ctx)
-    cudaStream_t st = ctx->stream;
-    HALO_CUDA(cudaMemcpyAsync(c->send.p, point_jac, 96, cudaMemcpyHostToDevice, st));
-    HALO_NCCL(api, AllGather(c->send.p, c->recv.p, 96, NCCL_UINT8, c->comm, st));
-    HALO_CUDA(cudaMemcpyAsync(c->h_recv, c->recv.p, (size_t)96 * c->size, cudaMemcpyDeviceToHost, st));
+    cudaStream_t st = c->side;
+    HALO_CUDA(cudaMemcpyAsync(c->side_send.p, point_jac, 96, cudaMemcpyHostToDevice, st));
+    HALO_NCCL(api, AllGather(c->side_send.p, c->side_recv.p, 96, NCCL_UINT8, c->comm, st));
+    HALO_CUDA(cudaMemcpyAsync(c->h_side, c->side_recv.p, (size_t)96 * c->size, cudaMemcpyDeviceToHost, st));
     HALO_CUDA(cudaStreamSynchronize(st));
-    int rc = halo_points_sum(reinterpret_cast<const uint64_t*>(c->h_recv), (uint64_t)c->size, out_jac);
+    int rc = halo_points_sum(c->h_side, (uint64_t)c->size, out_jac);
     if (rc) return rc;
     COMM_CATCH(ctx)
 }
