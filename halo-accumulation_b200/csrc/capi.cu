@@ -111,7 +111,7 @@ void h2d_copy(halo_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStrea
         if (errs[t] != cudaSuccess) throw CudaError{errs[t], "staged host-to-device copy", __FILE__, __LINE__};
 }
 
-static void async_init(halo_ctx* ctx) {
+void async_init(halo_ctx* ctx) {
     if (ctx->copy_stream) return;
     HALO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     int prio_lo = 0, prio_hi = 0;

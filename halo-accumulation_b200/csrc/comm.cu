@@ -176,37 +176,50 @@ MsmPlan comm_plan(const halo_comm* c, uint64_t n_global, bool fixed) {
 }
 
 // local MSM -> partials behind a header in `send` -> all-gather -> host: check headers, add the ranks' partials
-// component-wise in rank order, finish once.  d_scalars: this rank's slice, device resident.
-void sharded_msm(halo_comm* c, const fr_t* d_scalars, uint64_t off_local, uint64_t n_local, uint64_t n_global, xyzz_t& out) {
+// component-wise in rank order, finish once.  The local part may come as up to two point slices (`nsl`), each with its own
+// device scalars and an optional event that its host-to-device copy has landed: both run the same plan, so their partials
+// simply join the sum -- this is how the host-scalar call overlaps the copy of the second slice with the kernels of the first.
+struct LocalSlice {
+    const fr_t* d_scalars;
+    uint64_t off, n;
+    cudaEvent_t ready;  // may be null
+};
+void sharded_msm(halo_comm* c, const LocalSlice* sl, int nsl, uint64_t n_global, xyzz_t& out) {
     halo_ctx* ctx = c->ctx;
     NcclApi* api = nccl_api();
     const bool fixed = comm_use_fixed(c, n_global);
     MsmPlan plan = comm_plan(c, n_global, fixed);
     if (plan.red_quad != (ctx->tune_reduce_quad != 0)) plan_set_reduce(plan, ctx->tune_reduce_quad != 0);
     const int nwin = plan.fixed ? 1 : plan.W;
-    const int used = 1 + 3 * nwin;
+    if (1 + 3 * nwin * nsl > PART_SLOTS) throw NcclError{5, "too many windows for a sliced sharded MSM"};
+    const int used = 1 + 3 * nwin * nsl;
     xyzz_t* d_send = c->send.as<xyzz_t>();
     cudaStream_t st = ctx->stream;
     PartHeader& h = *c->h_hdr;
     memset(&h, 0, sizeof h);
     h.magic = PART_MAGIC;
     h.c = (uint32_t)plan.c, h.W = (uint32_t)plan.W, h.fixed = plan.fixed, h.red_slabs = plan.red_slabs;
-    h.red_T = (uint32_t)plan.red_T, h.red_log_s = (uint32_t)plan.red_log_s, h.n_local = (uint32_t)n_local;
+    h.red_T = (uint32_t)plan.red_T, h.red_log_s = (uint32_t)plan.red_log_s, h.n_local = (uint32_t)nsl;
     HALO_CUDA(cudaMemcpyAsync(d_send, &h, sizeof h, cudaMemcpyHostToDevice, st));
-    if (n_local) {
-        MsmInput in;
-        in.scalars = d_scalars;
-        in.n = (uint32_t)n_local;
-        if (fixed) {
-            in.bases = ctx->gens_pre.as<affine_t>();
-            in.fixed_stride = (uint32_t)ctx->pre_n;
-            in.fixed_first = (uint32_t)off_local;
+    for (int k = 0; k < nsl; k++) {
+        xyzz_t* d_parts = d_send + 1 + (size_t)3 * nwin * k;
+        if (sl[k].ready) HALO_CUDA(cudaStreamWaitEvent(st, sl[k].ready, 0));
+        if (sl[k].n) {
+            MsmInput in;
+            in.scalars = sl[k].d_scalars;
+            in.n = (uint32_t)sl[k].n;
+            if (fixed) {
+                in.bases = ctx->gens_pre.as<affine_t>();
+                in.fixed_stride = (uint32_t)ctx->pre_n;
+                in.fixed_first = (uint32_t)sl[k].off;
+            } else {
+                in.bases = ctx->gens.as<affine_t>() + sl[k].off;
+            }
+            MsmPlan pk = plan;  // (msm_enqueue settles the reduction geometry in its argument: identical for every slice)
+            msm_enqueue(ctx, in, pk, d_parts, 0, nullptr);
         } else {
-            in.bases = ctx->gens.as<affine_t>() + off_local;
+            HALO_CUDA(cudaMemsetAsync(d_parts, 0, (size_t)3 * nwin * sizeof(xyzz_t), st));  // zz = 0: infinity
         }
-        msm_enqueue(ctx, in, plan, d_send + 1, 0, nullptr);
-    } else {
-        HALO_CUDA(cudaMemsetAsync(d_send + 1, 0, (size_t)3 * nwin * sizeof(xyzz_t), st));  // zz = 0: infinity
     }
     const size_t bytes = (size_t)used * sizeof(xyzz_t);
     HALO_NCCL(api, AllGather(d_send, c->recv.p, bytes, NCCL_UINT8, c->comm, st));
@@ -220,11 +233,16 @@ void sharded_msm(halo_comm* c, const fr_t* d_scalars, uint64_t off_local, uint64
         PartHeader hr;
         memcpy(&hr, blk, sizeof hr);
         if (hr.magic != PART_MAGIC || hr.c != h.c || hr.W != h.W || hr.fixed != h.fixed || hr.red_slabs != h.red_slabs ||
-            hr.red_T != h.red_T || hr.red_log_s != h.red_log_s)
-            throw NcclError{5 /* ncclInvalidUsage */, "ranks disagree on the MSM plan (different n_global, tables or window on some rank)"};
-        for (int k = 0; k < 3 * nwin; k++) xyzz_add(sum[k], blk[1 + k]);
+            hr.red_T != h.red_T || hr.red_log_s != h.red_log_s || hr.n_local != h.n_local)
+            throw NcclError{5 /* ncclInvalidUsage */, "ranks disagree on the MSM plan (different n_global, tables, window or call on some rank)"};
+        for (int k = 0; k < nsl; k++)
+            for (int j = 0; j < 3 * nwin; j++) xyzz_add(sum[j], blk[1 + (size_t)3 * nwin * k + j]);
     }
     msm_finish_host(sum.data(), plan, out);
+}
+void sharded_msm(halo_comm* c, const fr_t* d_scalars, uint64_t off_local, uint64_t n_local, uint64_t n_global, xyzz_t& out) {
+    LocalSlice one{d_scalars, off_local, n_local, nullptr};
+    sharded_msm(c, &one, 1, n_global, out);
 }
 }  // namespace
 
@@ -348,10 +366,30 @@ int halo_msm_gens_sharded(halo_comm* c, const uint64_t* local_scalars, uint64_t 
     if (n_global < n_local) return comm_fail(ctx, HALO_EINVAL, "halo_msm_gens_sharded: n_global < n_local");
     COMM_TRY(ctx)
     ctx->stage_scalars.reserve((n_local ? n_local : 1) * sizeof(fr_t));
-    if (n_local)
-        h2d_copy(ctx, ctx->stage_scalars.p, local_scalars, n_local * sizeof(fr_t), ctx->stream);
     xyzz_t r;
-    sharded_msm(c, ctx->stage_scalars.as<fr_t>(), off_local, n_local, n_global, r);
+    // Large calls go as two point slices (5/16 and 11/16 of n_global / size, the split of the single-GPU blocking call): the copy
+    // of the second slice runs on the copy stream beside the kernels of the first.  The split point is a function of n_global
+    // and the communicator size only, so every rank makes the same number of slices whatever its own n_local.
+    const uint64_t slice = (n_global + c->size - 1) / c->size;
+    const bool fixed = comm_use_fixed(c, n_global);
+    const int nwin = fixed ? 1 : comm_plan(c, n_global, false).W;
+    if (ctx->tune_split_blocking > 0 && slice >= ((uint64_t)1 << ctx->tune_split_blocking) && 1 + 6 * nwin <= PART_SLOTS &&
+        !ctx->slots[0].active && !ctx->slots[1].active) {
+        async_init(ctx);
+        uint64_t h0 = slice / 16 * (uint64_t)ctx->tune_split_first_16ths;
+        if (h0 > n_local) h0 = n_local;
+        fr_t* d = ctx->stage_scalars.as<fr_t>();
+        cudaEvent_t ev0 = ctx->slots[0].copied, ev1 = ctx->slots[1].copied;
+        h2d_copy(ctx, d, local_scalars, h0 * sizeof(fr_t), ctx->copy_stream);
+        HALO_CUDA(cudaEventRecord(ev0, ctx->copy_stream));
+        h2d_copy(ctx, d + h0, local_scalars + 4 * h0, (n_local - h0) * sizeof(fr_t), ctx->copy_stream);
+        HALO_CUDA(cudaEventRecord(ev1, ctx->copy_stream));
+        LocalSlice sl[2] = {{d, off_local, h0, ev0}, {d + h0, off_local + h0, n_local - h0, ev1}};
+        sharded_msm(c, sl, 2, n_global, r);
+    } else {
+        if (n_local) h2d_copy(ctx, ctx->stage_scalars.p, local_scalars, n_local * sizeof(fr_t), ctx->stream);
+        sharded_msm(c, ctx->stage_scalars.as<fr_t>(), off_local, n_local, n_global, r);
+    }
     jac_t j;
     xyzz_to_jac(j, r);
     memcpy(out_jac, &j, 96);

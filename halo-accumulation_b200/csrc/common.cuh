@@ -136,6 +136,8 @@ namespace halo {
 // fraction of the PCIe rate; they are instead copied by a few host threads into a ring of pinned chunks, each chunk's DMA
 // enqueued as soon as it is filled.  Returns when the caller's buffer has been read completely (the DMAs may still run).
 void h2d_copy(halo_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st);
+// Creates the copy / sort streams and the two pipeline slots of the context on first use (capi.cu).
+void async_init(halo_ctx* ctx);
 }  // namespace halo
 
 // The opaque handle behind `halo_ctx*` (include/halo_b200.h).
