@@ -396,6 +396,13 @@ def test_open_and_full_check_2_20(ctx, oracle):
                 assert O.pt_eq(np.array(piv.Ls[i]), np.array(pi.Ls[i])) and O.pt_eq(np.array(piv.Rs[i]), np.array(pi.Rs[i])), i
             assert O.pt_eq(np.array(piv.U), np.array(pi.U)) and list(piv.c) == list(pi.c)
             pcdl.check(ctx, Cm, d, z, v, piv)
+            # and the HIDING opening: the deferred / FIXED-base proof above must equal, field by field, the proof of the
+            # round-by-round variable-base path on the same draws (two independent kernel paths; the oracle accepted it)
+            piwv = pcdl.open(ctx, p, Cw, d, z, w, q, wb)
+            for i in range(piw.lg_n):
+                assert O.pt_eq(np.array(piwv.Ls[i]), np.array(piw.Ls[i])) and O.pt_eq(np.array(piwv.Rs[i]), np.array(piw.Rs[i])), i
+            assert O.pt_eq(np.array(piwv.U), np.array(piw.U)) and list(piwv.c) == list(piw.c)
+            assert O.pt_eq(np.array(piwv.C_bar), np.array(piw.C_bar)) and list(piwv.w_prime) == list(piw.w_prime)
         finally:
             ctx.set_fixed_base(True)
     finally:
