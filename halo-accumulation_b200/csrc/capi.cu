@@ -196,7 +196,7 @@ void halo_ctx_destroy(halo_ctx* ctx) {
     MsmWorkspace& ws = *wsp;
     for (DevBuf* b : {&ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.buckets, &ws.wsums, &ws.scan_tmp,
                       &ws.task_bucket, &ws.task_partial, &ws.split_ctrl, &ws.split_tasks, &ws.split_buckets, &ws.split_partials,
-                      &ws.pt_a, &ws.pt_b, &ws.pt_prefix, &ws.pt_levels})
+                      &ws.pt_a, &ws.pt_b, &ws.pt_prefix, &ws.pt_levels, &ws.sort_tmp, &ws.sort_coarse, &ws.sort_fine})
         b->release();
     }
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -211,7 +211,7 @@ void halo_ctx_destroy(halo_ctx* ctx) {
         if (e) cudaEventDestroy(e);
     for (auto& s : ctx->slots) {
         s.scalars.release();
-        for (DevBuf* b : {&s.sort_ws.counts, &s.sort_ws.offsets, &s.sort_ws.entries, &s.sort_ws.scan_tmp}) b->release();
+        for (DevBuf* b : {&s.sort_ws.counts, &s.sort_ws.offsets, &s.sort_ws.entries, &s.sort_ws.scan_tmp, &s.sort_ws.sort_tmp, &s.sort_ws.sort_coarse, &s.sort_ws.sort_fine}) b->release();
         if (s.sorted) cudaEventDestroy(s.sorted);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
@@ -244,6 +244,8 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "sort_ahead")) ctx->tune_sort_ahead = value;
     else if (!strcmp(key, "stage_pageable")) ctx->tune_stage_pageable = value;
     else if (!strcmp(key, "reduce_quad")) ctx->tune_reduce_quad = value;
+    else if (!strcmp(key, "sort2")) ctx->tune_sort2 = value;
+    else if (!strcmp(key, "sort2_min_lg")) ctx->tune_sort2_min_lg = value;
     else if (!strcmp(key, "pair_bwd_async")) ctx->tune_pair_bwd_async = value;
     else if (!strcmp(key, "ipa_defer_rounds")) ctx->tune_ipa_defer = value;
     else if (!strcmp(key, "ipa_defer2_rounds")) ctx->tune_ipa_defer2 = value;

@@ -115,6 +115,7 @@ struct MsmWorkspace {
     DevBuf counts, offsets, cursor, entries, buckets, wsums, scan_tmp;
     DevBuf task_bucket, task_partial;  // slab partials of the bucket reduction
     DevBuf split_ctrl, split_tasks, split_buckets, split_partials;  // oversized-bucket splitting
+    DevBuf sort_tmp, sort_coarse, sort_fine;  // two-level counting sort: (fine bucket | entry) records grouped by coarse bin, per-CTA bin rows + directory, per-chunk bucket rows
     DevBuf pt_a, pt_b, pt_prefix, pt_levels;  // pair-tree passes (msm_pairs.cu): ping-pong slot arrays, prefixes, product hierarchy
 };
 
@@ -207,6 +208,9 @@ struct halo_ctx {
     int tune_split_blocking = 23;  // halo_msm_gens: two point slices through the pipeline slots for n >= 2^this (0: never)
     int tune_split_first_16ths = 5;  // size of the first slice in sixteenths of n: its H2D copy is exposed, the second slice's copy hides behind
                                      // the first slice's kernels (2^24: 8 -> 41.1 ms, 6 -> 38.4, 5 -> 38.2, 4 -> 39.7, 3 -> 41.0; scripts/gpu_split_probe.py)
+    bool sort2_attr = false;     // dynamic shared-memory opt-in of the staged sort kernels done on this context's device
+    int tune_sort2 = 1;          // two-level counting sort with staged, coalesced writes for inputs of >= 2^tune_sort2_min_lg entries
+    int tune_sort2_min_lg = 26;  // measured: 2^24 FIXED 6.15 -> 4.45 ms, 2^23 2.76 -> 2.31, 2^22 1.26 -> 1.29 (profiles/r02_sort2_v3_ab.jsonl)
     int tune_pair_bwd_async = 1;  // pass 0 of the pair tree: 1 = cp.async-staged operands + prefix loaded a step ahead (k_pair_bwd0, 5 CTAs per SM:
                                   // accumulation phase at 2^24 27.39 -> 26.75 ms; profiles/r02_pair_bwd_async_ab.jsonl), 0 = per-lane gathers
     int tune_reduce_quad = 1;   // 0: one-lane bucket reduction (k_reduce_slabs), for A/B measurements

@@ -259,6 +259,340 @@ static void exclusive_scan(const uint32_t* counts, uint32_t* offsets, uint32_t n
 }
 
 // ------------------------------------------------------------------------------------------------
+// 1-3 (large MSMs): two-level counting sort with shared-memory atomics and STAGED, COALESCED writes.  The one-pass sort above
+// pays two L2 atomics per entry (a RED for the histogram, an atomic with return for the write cursor) plus a random 4-byte
+// store: 6.1 ms of a 34 ms MSM at 2^24.  What bounds it is not the atomics but the number of scattered store transactions
+// (~45-50 G/s to HBM-backed lines whatever their size; ~94 G/s inside an L2-resident region): two earlier versions of this
+// sort that only moved the atomics into shared memory measured 8.6 and 9.5 ms (profiles/r02_sort2_v1_ab.jsonl, _v2_).  So
+// here every record leaves a CTA as part of a run.  Buckets are grouped into NC coarse bins of NF = 1024 consecutive buckets;
+//   A   k_sort_coarse_count    every CTA counts the entries of ITS tiles (tile = 1024 scalars, CTA c owns tiles c, c + grid, ..)
+//                              per coarse bin in shared memory and writes the row cta_hist[cta][bin]
+//   S1  k_sort_coarse_scan     per bin: total, offset, chunk directory (chunks of 8192 records), and the row turned into the
+//                              CTA's first slot inside the bin (no global atomic anywhere: every slot is known in advance)
+//   B   k_sort_coarse_scatter  the same tiles again: count, scan, place the tile's records into shared memory IN BIN ORDER,
+//                              write them out so that consecutive threads write consecutive (fine bucket | entry) records of
+//                              a bin's run (26 records = 208 bytes per bin and tile at 2^24)
+//   C   k_sort_fine_count      per chunk: histogram over the bin's 1024 fine buckets -> row fine[chunk][bucket]
+//   S2a k_sort_fine_total      per bucket: sum over its bin's chunks -> the global bucket counts (the array the one-pass sort
+//                              produces; scan, rounding to 2^P slots and padding are shared with it)
+//   S3  k_sort_fine_base       per bucket: rows turned into each chunk's first slot inside the bucket
+//   D   k_sort_fine_scatter    per chunk: records placed into shared memory IN BUCKET ORDER and written out in that order (the
+//                              ~8 entries a bucket gets from a chunk leave as one or two transactions, inside the bin's own
+//                              L2-resident region)
+// Chunks make C / D insensitive to skew (all scalars equal puts every entry into a handful of bins: such a bin is cut into
+// many chunks whose shared-memory atomics serialise, nothing worse).  Output (counts, offsets, entries, pad slots) is what
+// the downstream kernels expect from the one-pass sort, up to the order inside a bucket, which no consumer depends on.
+// Measured at 2^24 FIXED: 0.46 (A) + 0.03 + 1.56 (B) + 0.48 (C) + 0.1 + 1.65 (D) = 4.45 ms against 6.15; used from 2^26 entries.
+// ------------------------------------------------------------------------------------------------
+constexpr int S2_THREADS = 512;
+constexpr int S2_MAX_W = 20;        // windows per scalar (c >= 13)
+constexpr uint32_t S2_NF_LOG = 10;  // fine buckets per coarse bin
+constexpr uint32_t S2_NF = 1u << S2_NF_LOG;
+constexpr uint32_t S2_MAX_NC = 2048;
+constexpr uint32_t S2_CHUNK = 8192;  // entries per chunk
+constexpr uint32_t S2_MAX_CTAS = 592;
+constexpr int S2_SPT = 2;                                // scalars per thread and tile (coarse passes)
+constexpr uint32_t S2_TILE = S2_THREADS * S2_SPT;        // scalars per tile: CTA c owns the tiles c, c + grid, ..
+constexpr int S2_BIN_SHIFT = 42;                         // staged record: entry (32) | fine bucket (10) | coarse bin (12)
+constexpr uint64_t S2_REC_MASK = ((uint64_t)1 << S2_BIN_SHIFT) - 1;
+
+// Calls f(bucket, entry) for every non-zero digit of scalar i (the digit rule of k_digits).  Bits are picked straight out of
+// the canonical limbs (no 256-bit shift per window).
+template <class F>
+__device__ __forceinline__ void s2_for_digits(const fr_t& s, uint32_t i, const MsmWidths& widths, int W, uint32_t M, uint32_t fixed_stride,
+                                              uint32_t fixed_first, F&& f) {
+    uint32_t k[9];
+    fp_to_canon(k, s);
+    k[8] = 0;
+    uint32_t carry = 0, off = 0;
+    for (int w = 0; w < W; w++) {
+        const uint32_t c = widths.w[w];
+        const uint32_t lo = off >> 5, sh = off & 31u;
+        const uint32_t bits = __funnelshift_r(k[lo], k[lo + 1], sh);  // k[lo] >> sh | k[lo + 1] << (32 - sh)
+        uint32_t d = (bits & ((1u << c) - 1u)) + carry;
+        off += c;
+        carry = 0;
+        uint32_t neg = 0;
+        if (d > (1u << (c - 1))) {
+            d = (1u << c) - d;
+            neg = 1;
+            carry = 1;
+        }
+        if (d != 0) {
+            const uint32_t b = fixed_stride ? (d - 1) : (uint32_t)w * M + (d - 1);
+            const uint32_t idx = fixed_stride ? (uint32_t)w * fixed_stride + fixed_first + i : i;
+            f(b, idx | (neg << 31));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(S2_THREADS) k_sort_coarse_count(const fr_t* __restrict__ scalars, uint32_t n,
+                                                                  const fr_t* __restrict__ tail_scalars, uint32_t n_tail,
+                                                                  const MsmWidths widths, int W, uint32_t M, uint32_t fixed_stride,
+                                                                  uint32_t fixed_first, uint32_t NC, uint32_t* __restrict__ cta_hist) {
+    __shared__ uint32_t hist[S2_MAX_NC];
+    for (uint32_t t = threadIdx.x; t < NC; t += blockDim.x) hist[t] = 0;
+    __syncthreads();
+    const uint32_t ntot = n + n_tail, ntiles = (ntot + S2_TILE - 1) / S2_TILE;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+#pragma unroll
+        for (int r = 0; r < S2_SPT; r++) {
+            const uint32_t i = tile * S2_TILE + (uint32_t)r * S2_THREADS + threadIdx.x;
+            if (i < ntot) {
+                const fr_t s = i < n ? scalars[i] : tail_scalars[i - n];
+                s2_for_digits(s, i, widths, W, M, fixed_stride, fixed_first, [&](uint32_t b, uint32_t) { atomicAdd(&hist[b >> S2_NF_LOG], 1u); });
+            }
+        }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < NC; t += blockDim.x) cta_hist[(size_t)blockIdx.x * NC + t] = hist[t];
+}
+
+// one CTA of 1024 threads, up to 2 bins per thread
+__global__ void __launch_bounds__(1024) k_sort_coarse_scan(uint32_t* __restrict__ cta_hist, uint32_t nctas, uint32_t NC,
+                                                           uint32_t* __restrict__ coarse_off, uint32_t* __restrict__ chunk_pre) {
+    __shared__ uint32_t sh_tot;
+    uint32_t tot[2] = {0, 0};
+    for (int r = 0; r < 2; r++) {
+        const uint32_t t = threadIdx.x * 2 + r;
+        if (t < NC) {
+            uint32_t acc = 0;
+#pragma unroll 8
+            for (uint32_t c = 0; c < nctas; c++) acc += cta_hist[(size_t)c * NC + t];
+            tot[r] = acc;
+        }
+    }
+    uint32_t total, ctotal;
+    const uint32_t ch0 = (tot[0] + S2_CHUNK - 1) / S2_CHUNK, ch1 = (tot[1] + S2_CHUNK - 1) / S2_CHUNK;
+    uint32_t ex = block_exclusive_scan(tot[0] + tot[1], &total);
+    __syncthreads();
+    uint32_t cex = block_exclusive_scan(ch0 + ch1, &ctotal);
+    __syncthreads();
+    (void)sh_tot;
+    for (int r = 0; r < 2; r++) {
+        const uint32_t t = threadIdx.x * 2 + r;
+        if (t < NC) {
+            const uint32_t off = ex + (r ? tot[0] : 0), coff = cex + (r ? ch0 : 0);
+            coarse_off[t] = off;
+            chunk_pre[t] = coff;
+            uint32_t base = off;
+            for (uint32_t c = 0; c < nctas; c += 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = c + j < nctas ? cta_hist[(size_t)(c + j) * NC + t] : 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (c + j < nctas) {
+                        cta_hist[(size_t)(c + j) * NC + t] = base;
+                        base += v[j];
+                    }
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        coarse_off[NC] = total;
+        chunk_pre[NC] = ctotal;
+    }
+}
+
+// exclusive scan of v[0 .. len) (len <= 4 * blockDim) into out[0 .. len], out[len] = total; every thread of the CTA calls it
+__device__ __forceinline__ void s2_block_scan(const uint32_t* __restrict__ v, uint32_t len, uint32_t* __restrict__ out) {
+    const uint32_t per = (len + blockDim.x - 1) / blockDim.x;  // <= 4
+    const uint32_t b0 = threadIdx.x * per;
+    uint32_t loc[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        loc[j] = ((uint32_t)j < per && b0 + j < len) ? v[b0 + j] : 0;
+        sum += loc[j];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(sum, &total);
+    __syncthreads();  // (block_exclusive_scan's own scratch may be reused by the next call)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if ((uint32_t)j < per && b0 + j < len) {
+            out[b0 + j] = ex;
+            ex += loc[j];
+        }
+    if (threadIdx.x == 0) out[len] = total;
+}
+
+// B: the CTA's tiles again.  Per tile: count per bin, scan, place every record into a shared-memory staging area IN BIN ORDER,
+// then write the staged records out so that consecutive threads write consecutive addresses of a bin's run (26 records =
+// 208 bytes per bin and tile at 2^24): what limits a scatter on this part is the number of store transactions, ~45 G/s,
+// whatever their size, so a record must not be its own transaction.  Dynamic shared memory: gcur[NC] | hist[NC] | toff[NC + 1]
+// | stage[S2_TILE * W] (8 bytes each).
+__global__ void __launch_bounds__(S2_THREADS) k_sort_coarse_scatter(const fr_t* __restrict__ scalars, uint32_t n,
+                                                                    const fr_t* __restrict__ tail_scalars, uint32_t n_tail,
+                                                                    const MsmWidths widths, int W, uint32_t M, uint32_t fixed_stride,
+                                                                    uint32_t fixed_first, uint32_t NC, const uint32_t* __restrict__ cta_base,
+                                                                    uint64_t* __restrict__ tmp) {
+    extern __shared__ __align__(16) unsigned char s2_smem[];
+    uint32_t* gcur = reinterpret_cast<uint32_t*>(s2_smem);
+    uint32_t* hist = gcur + NC;
+    uint32_t* toff = hist + NC;
+    uint64_t* stage = reinterpret_cast<uint64_t*>(s2_smem + (((size_t)(3 * NC + 1) * 4 + 15) & ~(size_t)15));
+    for (uint32_t t = threadIdx.x; t < NC; t += blockDim.x) gcur[t] = cta_base[(size_t)blockIdx.x * NC + t];
+    const uint32_t ntot = n + n_tail, ntiles = (ntot + S2_TILE - 1) / S2_TILE;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (uint32_t t = threadIdx.x; t < NC; t += blockDim.x) hist[t] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < S2_SPT; r++) {
+            const uint32_t i = tile * S2_TILE + (uint32_t)r * S2_THREADS + threadIdx.x;
+            if (i < ntot) {
+                const fr_t s = i < n ? scalars[i] : tail_scalars[i - n];
+                s2_for_digits(s, i, widths, W, M, fixed_stride, fixed_first, [&](uint32_t b, uint32_t) { atomicAdd(&hist[b >> S2_NF_LOG], 1u); });
+            }
+        }
+        __syncthreads();
+        s2_block_scan(hist, NC, toff);
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < NC; t += blockDim.x) hist[t] = 0;  // now the placement cursor inside the tile
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < S2_SPT; r++) {
+            const uint32_t i = tile * S2_TILE + (uint32_t)r * S2_THREADS + threadIdx.x;
+            if (i < ntot) {
+                const fr_t s = i < n ? scalars[i] : tail_scalars[i - n];
+                s2_for_digits(s, i, widths, W, M, fixed_stride, fixed_first, [&](uint32_t b, uint32_t ent) {
+                    const uint32_t bin = b >> S2_NF_LOG;
+                    const uint32_t pos = toff[bin] + atomicAdd(&hist[bin], 1u);
+                    stage[pos] = ((uint64_t)bin << S2_BIN_SHIFT) | ((uint64_t)(b & (S2_NF - 1u)) << 32) | ent;
+                });
+            }
+        }
+        __syncthreads();
+        const uint32_t total = toff[NC];
+        for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
+            const uint64_t rec = stage[t];
+            const uint32_t bin = (uint32_t)(rec >> S2_BIN_SHIFT);
+            tmp[gcur[bin] + (t - toff[bin])] = rec & S2_REC_MASK;
+        }
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < NC; t += blockDim.x) gcur[t] += hist[t];
+        __syncthreads();
+    }
+}
+
+// chunk -> (bin, entry range): binary search in the chunk directory
+__device__ __forceinline__ void s2_chunk_range(uint32_t chunk, const uint32_t* __restrict__ chunk_pre, const uint32_t* __restrict__ coarse_off,
+                                               uint32_t NC, uint32_t& bin, uint32_t& lo, uint32_t& hi) {
+    uint32_t a = 0, b = NC;  // largest bin with chunk_pre[bin] <= chunk
+    while (b - a > 1) {
+        const uint32_t m = (a + b) >> 1;
+        if (chunk_pre[m] <= chunk) a = m; else b = m;
+    }
+    bin = a;
+    lo = coarse_off[a] + (chunk - chunk_pre[a]) * S2_CHUNK;
+    const uint32_t end = coarse_off[a + 1];
+    hi = lo + S2_CHUNK < end ? lo + S2_CHUNK : end;
+}
+
+__global__ void __launch_bounds__(S2_THREADS) k_sort_fine_count(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ chunk_pre,
+                                                                const uint32_t* __restrict__ coarse_off, uint32_t NC,
+                                                                uint32_t* __restrict__ fine) {
+    __shared__ uint32_t hist[S2_NF];
+    __shared__ uint32_t sh[3];
+    const uint32_t nchunks = chunk_pre[NC];
+    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        if (threadIdx.x == 0) s2_chunk_range(chunk, chunk_pre, coarse_off, NC, sh[0], sh[1], sh[2]);
+        for (uint32_t t = threadIdx.x; t < S2_NF; t += blockDim.x) hist[t] = 0;
+        __syncthreads();
+        const uint32_t lo = sh[1], hi = sh[2];
+        for (uint32_t q = lo + threadIdx.x; q < hi; q += blockDim.x) atomicAdd(&hist[(uint32_t)(tmp[q] >> 32)], 1u);
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < S2_NF; t += blockDim.x) fine[(size_t)chunk * S2_NF + t] = hist[t];
+        __syncthreads();
+    }
+}
+// per bucket: total over the chunks of its bin
+__global__ void __launch_bounds__(256) k_sort_fine_total(const uint32_t* __restrict__ fine, const uint32_t* __restrict__ chunk_pre, uint32_t NB,
+                                                         uint32_t* __restrict__ counts) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    const uint32_t bin = b >> S2_NF_LOG, f = b & (S2_NF - 1u);
+    uint32_t acc = 0;
+    for (uint32_t c = chunk_pre[bin], c1 = chunk_pre[bin + 1]; c < c1; c++) acc += fine[(size_t)c * S2_NF + f];
+    counts[b] = acc;
+}
+// per bucket: fine[chunk][bucket] <- first slot of the chunk's entries inside the bucket.  Loads go in batches of 8 ahead of
+// the stores (read and written array are the same, so the compiler would otherwise serialise one global round trip per chunk).
+__global__ void __launch_bounds__(256) k_sort_fine_base(uint32_t* __restrict__ fine, const uint32_t* __restrict__ chunk_pre, uint32_t NB,
+                                                        const uint32_t* __restrict__ offsets) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    const uint32_t bin = b >> S2_NF_LOG, f = b & (S2_NF - 1u);
+    uint32_t base = offsets[b];
+    const uint32_t c1 = chunk_pre[bin + 1];
+    for (uint32_t c = chunk_pre[bin]; c < c1; c += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = c + j < c1 ? fine[(size_t)(c + j) * S2_NF + f] : 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (c + j < c1) {
+                fine[(size_t)(c + j) * S2_NF + f] = base;
+                base += v[j];
+            }
+    }
+}
+
+// D: per chunk the records are placed into shared memory IN BUCKET ORDER and written out in that order, so the (on average 8)
+// entries a bucket receives from a chunk leave as one or two transactions instead of eight.
+__global__ void __launch_bounds__(S2_THREADS) k_sort_fine_scatter(const uint64_t* __restrict__ tmp, const uint32_t* __restrict__ chunk_pre,
+                                                                  const uint32_t* __restrict__ coarse_off, uint32_t NC,
+                                                                  const uint32_t* __restrict__ fine, uint32_t* __restrict__ entries) {
+    extern __shared__ __align__(16) unsigned char s2_smem[];  // stage[S2_CHUNK] (8 B) | hist[NF] | coff[NF + 1] | base[NF]
+    uint64_t* stage = reinterpret_cast<uint64_t*>(s2_smem);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(stage + S2_CHUNK);
+    uint32_t* coff = hist + S2_NF;
+    uint32_t* base = coff + S2_NF + 1;
+    __shared__ uint32_t sh[3];
+    constexpr int PER = S2_CHUNK / S2_THREADS;  // 16
+    const uint32_t nchunks = chunk_pre[NC];
+    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        if (threadIdx.x == 0) s2_chunk_range(chunk, chunk_pre, coarse_off, NC, sh[0], sh[1], sh[2]);
+        for (uint32_t t = threadIdx.x; t < S2_NF; t += blockDim.x) {
+            hist[t] = 0;
+            base[t] = fine[(size_t)chunk * S2_NF + t];
+        }
+        __syncthreads();
+        const uint32_t lo = sh[1], hi = sh[2];
+        uint64_t v[PER];
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const uint32_t q = lo + (uint32_t)j * S2_THREADS + threadIdx.x;
+            v[j] = 0;
+            if (q < hi) {
+                v[j] = tmp[q];
+                atomicAdd(&hist[(uint32_t)(v[j] >> 32)], 1u);
+            }
+        }
+        __syncthreads();
+        s2_block_scan(hist, S2_NF, coff);
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < S2_NF; t += blockDim.x) hist[t] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const uint32_t q = lo + (uint32_t)j * S2_THREADS + threadIdx.x;
+            if (q < hi) {
+                const uint32_t f = (uint32_t)(v[j] >> 32);
+                stage[coff[f] + atomicAdd(&hist[f], 1u)] = v[j];
+            }
+        }
+        __syncthreads();
+        const uint32_t total = hi - lo;
+        for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
+            const uint64_t rec = stage[t];
+            const uint32_t f = (uint32_t)(rec >> 32);
+            entries[base[f] + (t - coff[f])] = (uint32_t)rec;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 4. bucket accumulation: one thread per bucket, accumulator in registers
 // ------------------------------------------------------------------------------------------------
 // Lanes do not own a fixed bucket: a lane that has drained its bucket stores it and claims the next unprocessed one
@@ -924,10 +1258,60 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
     HALO_CUDA(cudaMemsetAsync(counts, 0, (size_t)(NB + 1) * 4, sst));
     const int TPB = 256;
     uint32_t grid = (ntot + TPB - 1) / TPB;
+    uint32_t cap = 0;
     if (ahead && ahead->ctas_per_sm > 0) {
-        const uint32_t cap = (uint32_t)ctx->sm_count * (uint32_t)ahead->ctas_per_sm;
+        cap = (uint32_t)ctx->sm_count * (uint32_t)ahead->ctas_per_sm;
         if (grid > cap) grid = cap;
     }
+    // two-level sort (shared-memory atomics) for large inputs whose geometry fits; else the one-pass counting sort
+    const uint32_t NC = (NB + S2_NF - 1) / S2_NF;
+    const bool sort2 = ctx->tune_sort2 != 0 && total_entries_max >= ((uint64_t)1 << ctx->tune_sort2_min_lg) && plan.W <= S2_MAX_W &&
+                       plan.M >= S2_NF && NC <= S2_MAX_NC;
+    if (sort2) {
+        const uint32_t max_chunks = (uint32_t)(total_entries_max / S2_CHUNK) + NC + 1;
+        uint32_t g1 = (ntot + S2_TILE - 1) / S2_TILE, g2 = max_chunks;
+        const uint32_t full1 = (uint32_t)ctx->sm_count * 2u, full2 = (uint32_t)ctx->sm_count * 4u;  // persistent grids
+        if (g1 > full1) g1 = full1;
+        if (g1 > S2_MAX_CTAS) g1 = S2_MAX_CTAS;
+        if (g2 > full2) g2 = full2;
+        if (cap) {
+            if (g1 > cap) g1 = cap;
+            if (g2 > cap) g2 = cap;
+        }
+        sws.sort_tmp.reserve((size_t)total_entries_max * 8);
+        sws.sort_fine.reserve((size_t)max_chunks * S2_NF * 4);
+        sws.sort_coarse.reserve(((size_t)S2_MAX_CTAS * S2_MAX_NC + 2 * (S2_MAX_NC + 1)) * 4);
+        uint32_t* cta_hist = sws.sort_coarse.as<uint32_t>();
+        uint32_t* coarse_off = cta_hist + (size_t)S2_MAX_CTAS * S2_MAX_NC;
+        uint32_t* chunk_pre = coarse_off + (S2_MAX_NC + 1);
+        uint64_t* tmp = sws.sort_tmp.as<uint64_t>();
+        uint32_t* fine = sws.sort_fine.as<uint32_t>();
+        k_sort_coarse_count<<<g1, S2_THREADS, 0, sst>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
+                                                         in.fixed_first, NC, cta_hist);
+        k_sort_coarse_scan<<<1, 1024, 0, sst>>>(cta_hist, g1, NC, coarse_off, chunk_pre);
+        const size_t smem_b = (((size_t)(3 * NC + 1) * 4 + 15) & ~(size_t)15) + (size_t)S2_TILE * plan.W * 8;
+        const size_t smem_d = (size_t)S2_CHUNK * 8 + (size_t)(3 * S2_NF + 1) * 4;
+        if (!ctx->sort2_attr) {  // per device: opt in to more than 48 KiB of dynamic shared memory
+            HALO_CUDA(cudaFuncSetAttribute(k_sort_coarse_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            HALO_CUDA(cudaFuncSetAttribute(k_sort_fine_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            ctx->sort2_attr = true;
+        }
+        k_sort_coarse_scatter<<<g1, S2_THREADS, smem_b, sst>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
+                                                                in.fixed_first, NC, cta_hist, tmp);
+        mark(1);
+        k_sort_fine_count<<<g2, S2_THREADS, 0, sst>>>(tmp, chunk_pre, coarse_off, NC, fine);
+        k_sort_fine_total<<<(NB + 255) / 256, 256, 0, sst>>>(fine, chunk_pre, NB, counts);
+        exclusive_scan(counts, offsets, NB, rmask, sws.scan_tmp.as<uint32_t>(), sst, &ctx->kernel_launches);
+        if (P) {
+            k_fill_pads<<<(NB + 255) / 256, 256, 0, sst>>>(counts, offsets, NB, entries);
+            ctx->kernel_launches++;
+        }
+        HALO_CUDA(cudaMemsetAsync(counts + NB, 0, 4, sst));  // the claim counter of k_accumulate
+        k_sort_fine_base<<<(NB + 255) / 256, 256, 0, sst>>>(fine, chunk_pre, NB, offsets);
+        mark(2);
+        k_sort_fine_scatter<<<g2, S2_THREADS, smem_d, sst>>>(tmp, chunk_pre, coarse_off, NC, fine, entries);
+        ctx->kernel_launches += 7;
+    } else {
     k_digits<false><<<grid, TPB, 0, sst>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
                                            in.fixed_first, counts, nullptr);
     mark(1);
@@ -942,6 +1326,8 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
     mark(2);
     k_digits<true><<<grid, TPB, 0, sst>>>(in.scalars, n, in.tail_scalars, in.n_tail, plan.widths, plan.W, plan.M, fstride,
                                           in.fixed_first, counts, entries);
+    ctx->kernel_launches += 2;
+    }
     if (ahead) {
         HALO_CUDA(cudaEventRecord(ahead->sorted, sst));
         HALO_CUDA(cudaStreamWaitEvent(st, ahead->sorted, 0));
@@ -1049,7 +1435,7 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
         ctx->kernel_launches += 2;
     }
     mark(5);
-    ctx->kernel_launches += 3;
+    ctx->kernel_launches += 1;  // the accumulation kernel (the sort counted its own above)
     HALO_CUDA(cudaGetLastError());
 }
 
