@@ -269,6 +269,56 @@ def test_msm_oversized_buckets(ctx, oracle, fixed):
         ctx.derive_generators(1 << 16)
 
 
+@pytest.mark.parametrize("fixed,c", [(False, 13), (False, 16), (True, 16), (True, 19)])
+def test_msm_two_level_sort(ctx, oracle, fixed, c):
+    """The staged two-level counting sort (k_sort_*, automatic from 2^26 entries) forced at 2^16 points: uniform, ragged and
+    degenerate scalar distributions (every entry in a few coarse bins: the chunk directory must cope), zero scalars, with and
+    without pair-tree passes (bucket segments padded to 2^P slots), pipelined calls (the throttled sort-ahead grid)."""
+    O = oracle
+    n = 1 << 16
+    ctx.derive_generators(n)
+    try:
+        if fixed:
+            ctx.precompute_generators(c)
+        else:
+            ctx.set_msm_window(c)
+        ctx.set_fixed_base(fixed)
+        ctx.set_tuning("sort2_min_lg", 8)
+        gs = ctx.get_generators(0, n)
+        big = O.random_scalars(1, 5)[0]
+        zeros = O.random_scalars(n, 9)
+        zeros[::3] = 0
+        cases = {
+            "uniform": O.random_scalars(n, 8),
+            "ragged": O.random_scalars(n - 4321, 10),
+            "with_zeros": zeros,
+            "all_equal": np.tile(big, (n, 1)),
+            "small": O.to_mont([i % 7 for i in range(n)]),
+            "half_uniform_half_equal": np.concatenate([O.random_scalars(n // 2, 7), np.tile(big, (n // 2, 1))]),
+        }
+        for P in (0, 3):
+            ctx.set_tuning("pair_passes", P)
+            for name, sc in cases.items():
+                sc = np.ascontiguousarray(sc, dtype=np.uint64)
+                exp = O.msm_affine(gs[:sc.shape[0]], sc, threads=8)
+                assert O.pt_eq(ctx.msm_gens(sc), exp), (name, P)
+        ctx.set_tuning("pair_passes", -1)
+        sc = cases["uniform"]
+        exp = O.msm_affine(gs, sc, threads=8)
+        t0 = ctx.msm_gens_submit(sc)
+        t1 = ctx.msm_gens_submit(sc)
+        assert O.pt_eq(ctx.msm_gens_collect(t0), exp) and O.pt_eq(ctx.msm_gens_collect(t1), exp)
+        ctx.set_tuning("sort2", 0)  # and the one-pass sort on the same input
+        assert O.pt_eq(ctx.msm_gens(sc), exp)
+    finally:
+        ctx.set_tuning("sort2", 1)
+        ctx.set_tuning("sort2_min_lg", 26)
+        ctx.set_tuning("pair_passes", -1)
+        ctx.set_msm_window(0)
+        ctx.set_fixed_base(True)
+        ctx.derive_generators(1 << 16)
+
+
 def test_msm_pipelined_submit_collect(ctx, oracle):
     """halo_msm_gens_submit / _collect: two MSMs in flight give the same points as the blocking call and the oracle."""
     O = oracle
