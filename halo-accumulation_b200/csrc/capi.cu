@@ -13,7 +13,6 @@
 using namespace halo;
 
 namespace halo {
-
 // Registry behind DevBuf's canaries: one process-wide list, guarded by a mutex (a context is single-threaded like the
 // reference, but several contexts may live on several host threads).
 std::vector<DevBuf*>& devbuf_registry() {

@@ -50,7 +50,7 @@ void plan_set_reduce(MsmPlan& p, bool quad) {
     // shorter dependent chain but issues ~40 % more instructions per addition: it wins while the reduction is latency
     // bound (<= 3 * 2^17 buckets in all), the one-lane kernel wins beyond (2^22 variable base: 0.69 against 0.83 ms).
     const uint32_t nwin = p.fixed ? 1u : (uint32_t)p.W;
-    quad = quad && (uint64_t)nwin * p.M <= 393216u;
+    quad = quad && (uint64_t)nwin * p.M <= (p.fixed ? 524288u : 393216u);  // (one bucket set of 2^19: 0.80 -> 0.67 ms)
     p.red_quad = quad;
     if (!quad) {
         p.red_T = p.M < 256u ? (int)p.M : 256;
