@@ -431,6 +431,31 @@ def test_open_deferred_head_rounds(env, n, defer):
         ctx.set_tuning("ipa_defer_rounds", -1)
 
 
+@pytest.mark.parametrize("lg,defer2,freeze", [(16, 4, 0), (15, 2, 0), (14, 3, 2048), (12, 4, 256)])
+def test_open_second_deferred_stage(env, lg, defer2, freeze):
+    """Later deferred stages over the materialised vector ("ipa_defer2_rounds"; off by default because it measured slower at
+    2^20, profiles/r02_ipa_stage2_probe.txt): the next rounds run as per-index-coefficient MSMs over the current generator
+    vector and ONE k_fold_multi takes it down 2^D-fold.  Same L, R, U, c as the oracle's round-by-round fold."""
+    ctx, O, pcdl = env["ctx"], env["O"], env["pcdl"]
+    n = 1 << lg
+    d = n - 1
+    p = O.random_scalars(n - 11, 6000 + lg)
+    z = O.random_scalars(1, 61)[0]
+    w, wb = O.random_scalars(2, 62)
+    q = O.random_scalars(p.shape[0] - 1, 63)
+    ctx.set_tuning("ipa_defer2_rounds", defer2)
+    if freeze:
+        ctx.set_tuning("ipa_freeze_len", freeze)
+    try:
+        Cm = pcdl.commit(ctx, p, d)
+        _same_proof(O, pcdl.open(ctx, p, Cm, d, z), O.pcdl_open(p, Cm, d, z, threads=8))
+        Cw = pcdl.commit(ctx, p, d, w)
+        _same_proof(O, pcdl.open(ctx, p, Cw, d, z, w, q, wb), O.pcdl_open(p, Cw, d, z, w, q, wb, threads=8))
+    finally:
+        ctx.set_tuning("ipa_defer2_rounds", 0)
+        ctx.set_tuning("ipa_freeze_len", 0)
+
+
 def test_open_deferred_head_fixed_base_2_17(ctx, oracle):
     """The automatic policy: with FIXED-base tables covering the opening, three rounds are deferred and their L / R take
     the shared-bucket-set path (dot * H' added on the host).  n = 2^17 is the smallest size it triggers at; the oracle
