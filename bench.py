@@ -64,10 +64,12 @@ def make_config(log_n, world):
             "l2": "inputs_exceed_l2 (>= 1.5 GiB streamed per step)"}
 
 
-def bench_scalars(n, rank):
-    from oracle import oracle as O  # only the seeded generator of the test inputs (numpy), no arithmetic
-
-    return O.random_scalars(n, SCALAR_SEED + rank)
+def bench_scalars(n, seed_offset):
+    """Seeded synthetic scalars as Montgomery limbs: any 4-limb value below 2^254 < r is the Montgomery form of some scalar."""
+    rng = np.random.Generator(np.random.PCG64(SCALAR_SEED + seed_offset))
+    a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 62) - 1)
+    return a
 
 
 class ClockSampler(threading.Thread):

@@ -98,7 +98,7 @@ struct NcclError {
 
 // Every rank must run the SAME plan for the component-wise sum to be valid; the plan signature travels with the partials.
 struct alignas(16) PartHeader {
-    uint32_t magic, c, W, fixed, red_slabs, red_T, red_log_s, n_local;
+    uint32_t magic, c, W, fixed, red_slabs, red_T, red_log_s, n_sets;  // n_sets: point slices (partial sets) in the block
     uint32_t pad[24];
 };
 static_assert(sizeof(PartHeader) == sizeof(xyzz_t), "header occupies one XYZZ slot");
@@ -199,7 +199,7 @@ void sharded_msm(halo_comm* c, const LocalSlice* sl, int nsl, uint64_t n_global,
     memset(&h, 0, sizeof h);
     h.magic = PART_MAGIC;
     h.c = (uint32_t)plan.c, h.W = (uint32_t)plan.W, h.fixed = plan.fixed, h.red_slabs = plan.red_slabs;
-    h.red_T = (uint32_t)plan.red_T, h.red_log_s = (uint32_t)plan.red_log_s, h.n_local = (uint32_t)nsl;
+    h.red_T = (uint32_t)plan.red_T, h.red_log_s = (uint32_t)plan.red_log_s, h.n_sets = (uint32_t)nsl;
     HALO_CUDA(cudaMemcpyAsync(d_send, &h, sizeof h, cudaMemcpyHostToDevice, st));
     for (int k = 0; k < nsl; k++) {
         xyzz_t* d_parts = d_send + 1 + (size_t)3 * nwin * k;
@@ -233,7 +233,7 @@ void sharded_msm(halo_comm* c, const LocalSlice* sl, int nsl, uint64_t n_global,
         PartHeader hr;
         memcpy(&hr, blk, sizeof hr);
         if (hr.magic != PART_MAGIC || hr.c != h.c || hr.W != h.W || hr.fixed != h.fixed || hr.red_slabs != h.red_slabs ||
-            hr.red_T != h.red_T || hr.red_log_s != h.red_log_s || hr.n_local != h.n_local)
+            hr.red_T != h.red_T || hr.red_log_s != h.red_log_s || hr.n_sets != h.n_sets)
             throw NcclError{5 /* ncclInvalidUsage */, "ranks disagree on the MSM plan (different n_global, tables, window or call on some rank)"};
         for (int k = 0; k < nsl; k++)
             for (int j = 0; j < 3 * nwin; j++) xyzz_add(sum[j], blk[1 + (size_t)3 * nwin * k + j]);
