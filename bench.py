@@ -73,37 +73,78 @@ def bench_scalars(n, seed_offset):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons of one GPU during the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clock, power and clock-event reasons of one GPU during a timed region (B200_PROFILING.md recipe): in-process
+    NVML every 10 ms when the bindings load (a 0.6 s timed region gets ~60 samples), else `nvidia-smi` every 200 ms."""
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.uuid, self.rows, self.stop_flag = index, uuid, [], threading.Event()
+        self.source = "nvidia-smi"
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    def _nvml_handle(self):
+        import pynvml as nv
+
+        nv.nvmlInit()
+        if self.uuid:
+            try:
+                return nv, nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
+            except Exception:
+                pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = self.index
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            phys = int(vis.split(",")[self.index])
+        return nv, nv.nvmlDeviceGetHandleByIndex(phys)
+
+    def _run_nvml(self):
+        nv, h = self._nvml_handle()
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)  # any failure lands in the fallback before the first row
+        self.source = "nvml"
+        while not self.stop_flag.is_set():
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                  [name for name, bit in names if mask & bit]))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
+
+    def _run_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                r = [c.strip() for c in out.split(",")]
+                if len(r) >= 7 and r[0].isdigit():
+                    why = [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7])
+                           if v.lower().startswith("active")]
+                    self.rows.append((int(r[0]), int(r[1]) if r[1].isdigit() else 0, float(r[2]) if r[2].replace(".", "").isdigit() else 0.0, why))
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self.source = "nvidia-smi"
+            self._run_smi()
+
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        rows = list(self.rows)
+        sm = sorted(r[0] for r in rows)
+        pw = sorted(r[2] for r in rows)
+        reasons = sorted({w for r in rows for w in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_mhz_min": sm[0] if sm else None,
+                "sm_max_mhz": max((r[1] for r in rows), default=None), "power_w_median": pw[len(pw) // 2] if pw else None,
+                "power_w_max": pw[-1] if pw else None, "reasons": reasons, "samples": len(rows), "source": self.source}
 
 
 def host_threads():
@@ -239,7 +280,8 @@ def run_ours(args):
 
     run_pipelined(max(args.warmup, 2), lambda: ctx.msm_gens_submit_resident(d_scalars.data_ptr(), n))
     barrier()
-    sampler = ClockSampler(local)
+    dev_uuid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
+    sampler = ClockSampler(local, dev_uuid)
     sampler.start()
     l0 = ctx.kernel_launches()
     ctx.timer_start()
@@ -275,9 +317,12 @@ def run_ours(args):
     # ---- per-phase profile of the FIXED-base path (dominant phase: bucket accumulation), CUDA events on the library's stream ----
     ctx.set_profiling(True)
     acc_ms = []
+    phase_sampler = ClockSampler(local, dev_uuid)
+    phase_sampler.start()
     for _ in range(max(3, min(args.steps, 5))):
         ctx.msm_gens_resident(d_scalars.data_ptr(), n)
         acc_ms.append(ctx.last_msm_timings())
+    phase_clocks = phase_sampler.summary()
     ctx.set_profiling(False)
     phases = {k: float(np.mean([t[k] for t in acc_ms])) for k in acc_ms[0]}
 
@@ -325,7 +370,20 @@ def run_ours(args):
     sms = torch.cuda.get_device_properties(local).multi_processor_count
     blocks, threads, iters = sms * 8, 256, 4096
     imad_ms = min(ctx.test_imad_throughput(0, blocks, threads, iters) for _ in range(3))
-    imad_peak = blocks * threads * iters * 16 / imad_ms / 1e9  # T IMAD32/s: dependent-multiplicand mad.lo.u32 chains
+    imad_peak = blocks * threads * iters * 16 / imad_ms / 1e9  # T IMAD32/s: dependent-multiplicand mad.lo.u32 chains (1 ms burst)
+    # the same microbenchmark back to back for ~2 s: the integer pipe's rate at the clocks the power cap allows under
+    # sustained load (MEASURED_PEAKS.json makes the same burst / sustained distinction for bf16)
+    imad_sust, imad_sust_clocks = None, None
+    if rank == 0 or world > 1:
+        it8 = iters * 8
+        smp = ClockSampler(local, dev_uuid)
+        smp.start()
+        t_end, runs = time.perf_counter() + 2.0, []
+        while time.perf_counter() < t_end:
+            runs.append(ctx.test_imad_throughput(0, blocks, threads, it8))
+        imad_sust_clocks = smp.summary()
+        tail = sorted(runs[len(runs) // 2:])
+        imad_sust = blocks * threads * it8 * 16 / tail[len(tail) // 2] / 1e9
 
     def whole_msm_frac(points, ms, gpus=1):
         return (points * 160 + 14.68e6) * IMAD_PER_MODMUL / (ms * 1e-3) / 1e12 / (imad_peak * gpus)
@@ -382,7 +440,11 @@ def run_ours(args):
                          "hbm_gbs_phase": (traffic / (phases["accumulate"] * 1e-3) / 1e9) if traffic else None,
                          "peak_source": "measured in this run (libhalo_b200 mad.lo.u32 microbenchmark, 16 independent chains per thread, all SMs); MEASURED_PEAKS.json has no integer-pipe figure. IMAD.WIDE / IMAD.HI issue at half this rate (profiles/r01_imad_pipe_rates.jsonl)",
                          "algorithmic": f"{n} pts x {CANON_W} windows x 10 modmul x {IMAD_PER_MODMUL} IMAD32 per launch (SURVEY 8d canonical accounting, c = 16)",
-                         "launch_ms": phases["accumulate"], "phases_ms": phases,
+                         "launch_ms": phases["accumulate"], "phases_ms": phases, "clocks_phase": phase_clocks,
+                         "peak_sustained": imad_sust, "frac_of_sustained_peak": (achieved / imad_sust) if imad_sust else None,
+                         "peak_sustained_note": "the same IMAD microbenchmark back to back for 2 s (median of the second half): `peak` is a 1 ms burst at boost clocks, "
+                                                "the phase is timed inside back-to-back MSMs under the board's power cap; `frac` stays against the burst figure",
+                         "clocks_peak_sustained": imad_sust_clocks,
                          "whole_msm_frac": whole_msm_frac(n, ms_step),
                          "executed": {"note": "what the kernels issue: 13 windows (c = 20), 15/16 of the additions affine in the pair tree (6.2 modmul each: 5M + 1S + shared inversion), the rest XYZZ (10)",
                                       "modmul_per_point": 13 * (15 / 16 * 6.2 + 1 / 16 * 10),
