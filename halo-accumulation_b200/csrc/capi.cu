@@ -67,14 +67,15 @@ void h2d_copy(halo_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStrea
         HALO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         return;
     }
-    constexpr int T = halo_ctx::STAGE_THREADS, S = halo_ctx::STAGE_SLOTS;
+    constexpr int TMAX = halo_ctx::STAGE_THREADS, S = halo_ctx::STAGE_SLOTS;
+    const int T = ctx->tune_stage_threads < 1 ? 1 : ctx->tune_stage_threads > TMAX ? TMAX : ctx->tune_stage_threads;
     for (int i = 0; i < T * S; i++)
         if (!ctx->stage_pinned[i]) {
             HALO_CUDA(cudaMallocHost(&ctx->stage_pinned[i], CH));
             HALO_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
         }
     const size_t nchunks = (bytes + CH - 1) / CH;
-    cudaError_t errs[T];
+    cudaError_t errs[TMAX];
     auto work = [&](int t) {
         errs[t] = cudaSetDevice(ctx->device);
         size_t use = 0;
@@ -89,8 +90,9 @@ void h2d_copy(halo_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStrea
         }
     };
     // the ring may still be draining from the previous staged copy (a different stream): wait before refilling it
-    for (int i = 0; i < T * S; i++) HALO_CUDA(cudaEventSynchronize(ctx->stage_ev[i]));
-    std::thread th[T];
+    for (int i = 0; i < TMAX * S; i++)
+        if (ctx->stage_ev[i]) HALO_CUDA(cudaEventSynchronize(ctx->stage_ev[i]));
+    std::thread th[TMAX];
     int spawned = 0;
     for (int t = 1; t < T; t++) {
         try {
@@ -166,6 +168,13 @@ int halo_ctx_create(int device, uint64_t max_n, halo_ctx** out) {
         HALO_CUDA(cudaSetDevice(device));
         HALO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         HALO_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+        {  // staging threads for pageable host buffers: the host's hardware threads shared among the visible GPUs, 4 .. 8
+            int ndev = 1;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+            const int hw = (int)std::thread::hardware_concurrency();
+            const int t = hw / ndev;
+            ctx->tune_stage_threads = t < 4 ? 4 : t > halo_ctx::STAGE_THREADS ? halo_ctx::STAGE_THREADS : t;
+        }
         HALO_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
         HALO_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         HALO_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -240,8 +249,10 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "pair_passes")) ctx->tune_pair_passes = value;
     else if (!strcmp(key, "split_blocking")) ctx->tune_split_blocking = value;
     else if (!strcmp(key, "split_first_16ths")) ctx->tune_split_first_16ths = value < 1 ? 1 : value > 15 ? 15 : value;
+    else if (!strcmp(key, "split_second_16ths")) ctx->tune_split_second_16ths = value < 0 ? 0 : value > 14 ? 14 : value;
     else if (!strcmp(key, "sort_ahead")) ctx->tune_sort_ahead = value;
     else if (!strcmp(key, "stage_pageable")) ctx->tune_stage_pageable = value;
+    else if (!strcmp(key, "stage_threads")) ctx->tune_stage_threads = value;
     else if (!strcmp(key, "reduce_quad")) ctx->tune_reduce_quad = value;
     else if (!strcmp(key, "sort2")) ctx->tune_sort2 = value;
     else if (!strcmp(key, "sort2_min_lg")) ctx->tune_sort2_min_lg = value;
@@ -574,27 +585,40 @@ int halo_msm_gens_resident(halo_ctx* ctx, const void* d_scalars, uint64_t off, u
 int halo_msm_gens(halo_ctx* ctx, const uint64_t* scalars, uint64_t off, uint64_t n, uint64_t out_jac[12]) {
     if (!ctx || !out_jac || (!scalars && n)) return HALO_EINVAL;
     if (off + n > ctx->n_gens) return fail(ctx, HALO_ESTATE, "halo_msm_gens: range exceeds resident generators");
-    // Large calls are split into two point slices that go through the two pipeline slots: the host-to-device copy of the
-    // second slice overlaps the kernels of the first (2^24 scalars from pinned memory: 45.4 ms unsplit, 41.1 ms with two
-    // halves, 38.2 ms with 5/16 + 11/16); the two partial sums are added on the host.
+    // Large calls are split into point slices that go through the two pipeline slots: the host-to-device copies of the later
+    // slices overlap the kernels of the earlier ones (2^24 scalars from pinned memory, round 1: 45.4 ms unsplit, 41.1 ms with
+    // two halves, 38.2 ms with 5/16 + 11/16; round 2: 37.0 ms with 5/16 + 11/16, 36.05 ms with 2/16 + 5/16 + 9/16; from
+    // pageable memory 41.9 -> 39.8 ms); the partial sums are added on the host.
     if (ctx->tune_split_blocking > 0 && n >= ((uint64_t)1 << ctx->tune_split_blocking) && !ctx->slots[0].active && !ctx->slots[1].active) {
-        const uint64_t h = n / 16 * (uint64_t)ctx->tune_split_first_16ths;  // the first slice's copy is the exposed one
-        int t0, t1;
-        uint64_t p0[12], p1[12];
-        int rc = halo_msm_gens_submit(ctx, scalars, off, h, &t0);
-        if (rc) return rc;
-        rc = halo_msm_gens_submit(ctx, scalars + 4 * h, off + h, n - h, &t1);
-        if (rc) {
-            halo_msm_gens_collect(ctx, t0, p0);
-            return rc;
+        // slices in sixteenths of n: the first slice's copy is the exposed one; with a second cut the third slice is submitted
+        // into the first slice's slot as soon as that one is collected (two slots in flight at any time)
+        const int a = ctx->tune_split_first_16ths, b = ctx->tune_split_second_16ths;
+        uint64_t cut[4] = {0, n / 16 * (uint64_t)a, 0, n};
+        int ns = 2;
+        if (b > 0 && a + b < 16) {
+            cut[2] = n / 16 * (uint64_t)(a + b);
+            ns = 3;
+        } else {
+            cut[2] = n;
         }
-        rc = halo_msm_gens_collect(ctx, t0, p0);
-        int rc1 = halo_msm_gens_collect(ctx, t1, p1);
-        if (rc || rc1) return rc ? rc : rc1;
-        uint64_t both[24];
-        memcpy(both, p0, 96);
-        memcpy(both + 12, p1, 96);
-        return halo_points_sum(both, 2, out_jac);
+        int tk[3];
+        uint64_t parts[36];
+        int rc = 0, submitted = 0, collected = 0;
+        for (int i = 0; i < ns && !rc; i++) {
+            if (i == 2) {
+                rc = halo_msm_gens_collect(ctx, tk[0], parts);
+                collected = 1;
+                if (rc) break;
+            }
+            rc = halo_msm_gens_submit(ctx, scalars + 4 * cut[i], off + cut[i], cut[i + 1] - cut[i], &tk[i]);
+            if (!rc) submitted = i + 1;
+        }
+        for (int i = collected; i < submitted; i++) {  // on failure this drains what is in flight; the first error is the one returned
+            const int rci = halo_msm_gens_collect(ctx, tk[i], parts + 12 * i);
+            if (!rc) rc = rci;
+        }
+        if (rc) return rc;
+        return halo_points_sum(parts, (uint64_t)ns, out_jac);
     }
     HALO_TRY(ctx)
     ctx->stage_scalars.reserve((n ? n : 1) * sizeof(fr_t));

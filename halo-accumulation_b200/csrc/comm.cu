@@ -120,6 +120,7 @@ struct halo_comm {
     cudaStream_t side = nullptr;
     DevBuf side_send, side_recv;
     uint64_t* h_side = nullptr;  // pinned, [size][12]
+    cudaEvent_t copied[3] = {};  // host-to-device copies of the point slices of a host-scalar call
 };
 
 namespace {
@@ -176,9 +177,9 @@ MsmPlan comm_plan(const halo_comm* c, uint64_t n_global, bool fixed) {
 }
 
 // local MSM -> partials behind a header in `send` -> all-gather -> host: check headers, add the ranks' partials
-// component-wise in rank order, finish once.  The local part may come as up to two point slices (`nsl`), each with its own
+// component-wise in rank order, finish once.  The local part may come as up to three point slices (`nsl`), each with its own
 // device scalars and an optional event that its host-to-device copy has landed: both run the same plan, so their partials
-// simply join the sum -- this is how the host-scalar call overlaps the copy of the second slice with the kernels of the first.
+// simply join the sum -- this is how the host-scalar call overlaps the copies of the later slices with the kernels of the earlier ones.
 struct LocalSlice {
     const fr_t* d_scalars;
     uint64_t off, n;
@@ -311,6 +312,8 @@ void halo_comm_destroy(halo_comm* c) {
     if (c->h_recv) cudaFreeHost(c->h_recv);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     if (c->h_side) cudaFreeHost(c->h_side);
+    for (cudaEvent_t e : c->copied)
+        if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -367,25 +370,31 @@ int halo_msm_gens_sharded(halo_comm* c, const uint64_t* local_scalars, uint64_t 
     COMM_TRY(ctx)
     ctx->stage_scalars.reserve((n_local ? n_local : 1) * sizeof(fr_t));
     xyzz_t r;
-    // Large calls go as two point slices (5/16 and 11/16 of n_global / size, the split of the single-GPU blocking call): the copy
-    // of the second slice runs on the copy stream beside the kernels of the first.  The split point is a function of n_global
-    // and the communicator size only, so every rank makes the same number of slices whatever its own n_local.
+    // Large calls go as two or three point slices (the cuts of the single-GPU blocking call, in sixteenths of n_global / size):
+    // the copies of the later slices run on the copy stream beside the kernels of the earlier ones.  The cuts are a function of
+    // n_global and the communicator size only, so every rank makes the same number of slices whatever its own n_local.
     const uint64_t slice = (n_global + c->size - 1) / c->size;
     const bool fixed = comm_use_fixed(c, n_global);
     const int nwin = fixed ? 1 : comm_plan(c, n_global, false).W;
-    if (ctx->tune_split_blocking > 0 && slice >= ((uint64_t)1 << ctx->tune_split_blocking) && 1 + 6 * nwin <= PART_SLOTS &&
+    const int a16 = ctx->tune_split_first_16ths, b16 = ctx->tune_split_second_16ths;
+    const int nsl = (b16 > 0 && a16 + b16 < 16 && 1 + 9 * nwin <= PART_SLOTS) ? 3 : 2;
+    if (ctx->tune_split_blocking > 0 && slice >= ((uint64_t)1 << ctx->tune_split_blocking) && 1 + 3 * nsl * nwin <= PART_SLOTS &&
         !ctx->slots[0].active && !ctx->slots[1].active) {
         async_init(ctx);
-        uint64_t h0 = slice / 16 * (uint64_t)ctx->tune_split_first_16ths;
-        if (h0 > n_local) h0 = n_local;
+        uint64_t cut[4] = {0, slice / 16 * (uint64_t)a16, nsl == 3 ? slice / 16 * (uint64_t)(a16 + b16) : n_local, n_local};
+        for (int k = 1; k < 3; k++)
+            if (cut[k] > n_local) cut[k] = n_local;
+        if (nsl == 2) cut[2] = n_local;
         fr_t* d = ctx->stage_scalars.as<fr_t>();
-        cudaEvent_t ev0 = ctx->slots[0].copied, ev1 = ctx->slots[1].copied;
-        h2d_copy(ctx, d, local_scalars, h0 * sizeof(fr_t), ctx->copy_stream);
-        HALO_CUDA(cudaEventRecord(ev0, ctx->copy_stream));
-        h2d_copy(ctx, d + h0, local_scalars + 4 * h0, (n_local - h0) * sizeof(fr_t), ctx->copy_stream);
-        HALO_CUDA(cudaEventRecord(ev1, ctx->copy_stream));
-        LocalSlice sl[2] = {{d, off_local, h0, ev0}, {d + h0, off_local + h0, n_local - h0, ev1}};
-        sharded_msm(c, sl, 2, n_global, r);
+        LocalSlice sl[3];
+        for (int k = 0; k < nsl; k++) {
+            if (!c->copied[k]) HALO_CUDA(cudaEventCreateWithFlags(&c->copied[k], cudaEventDisableTiming));
+            const uint64_t lo = cut[k], hi = k + 1 == nsl ? n_local : cut[k + 1];
+            h2d_copy(ctx, d + lo, local_scalars + 4 * lo, (hi - lo) * sizeof(fr_t), ctx->copy_stream);
+            HALO_CUDA(cudaEventRecord(c->copied[k], ctx->copy_stream));
+            sl[k] = LocalSlice{d + lo, off_local + lo, hi - lo, c->copied[k]};
+        }
+        sharded_msm(c, sl, nsl, n_global, r);
     } else {
         if (n_local) h2d_copy(ctx, ctx->stage_scalars.p, local_scalars, n_local * sizeof(fr_t), ctx->stream);
         sharded_msm(c, ctx->stage_scalars.as<fr_t>(), off_local, n_local, n_global, r);

@@ -185,11 +185,12 @@ struct halo_ctx {
     cudaStream_t copy_stream = nullptr, sort_stream = nullptr;  // sort_stream: highest priority
     int next_slot = 0;
     // staging ring for host-to-device copies out of PAGEABLE caller memory (h2d_copy, capi.cu)
-    static constexpr int STAGE_THREADS = 4, STAGE_SLOTS = 2;
+    static constexpr int STAGE_THREADS = 8, STAGE_SLOTS = 2;  // upper bound of threads; tune_stage_threads of them work
     static constexpr size_t STAGE_CHUNK = 8u << 20;
     void* stage_pinned[STAGE_THREADS * STAGE_SLOTS] = {};
     cudaEvent_t stage_ev[STAGE_THREADS * STAGE_SLOTS] = {};
     int tune_stage_pageable = 1;  // 0: hand pageable pointers to cudaMemcpyAsync as they are
+    int tune_stage_threads = 4;   // host threads that copy pageable chunks into the pinned ring (1 .. STAGE_THREADS)
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     int force_c = 0;
@@ -206,7 +207,8 @@ struct halo_ctx {
                                 // (rounds 3-6 as one stage: 4 x 2.1 ms L / R + 5.3 ms latency-bound fold of 8192 outputs against 4.9 + 6.2 ms; profiles/r02_ipa_stage2_probe.txt)
     int tune_sort_ahead = 1;  // pipelined submit: CTAs per SM of the counting sort running beside the previous MSM (0: off)
     int tune_split_blocking = 23;  // halo_msm_gens: two point slices through the pipeline slots for n >= 2^this (0: never)
-    int tune_split_first_16ths = 5;  // size of the first slice in sixteenths of n: its H2D copy is exposed, the second slice's copy hides behind
+    int tune_split_second_16ths = 5;  // > 0: three slices (first, second, rest); the third copy starts when the first slice is collected
+    int tune_split_first_16ths = 2;  // size of the first slice in sixteenths of n: its H2D copy is exposed, the second slice's copy hides behind
                                      // the first slice's kernels (2^24: 8 -> 41.1 ms, 6 -> 38.4, 5 -> 38.2, 4 -> 39.7, 3 -> 41.0; scripts/gpu_split_probe.py)
     bool sort2_attr = false;     // dynamic shared-memory opt-in of the staged sort kernels done on this context's device
     int tune_sort2 = 1;          // two-level counting sort with staged, coalesced writes for inputs of >= 2^tune_sort2_min_lg entries

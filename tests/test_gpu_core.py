@@ -343,17 +343,21 @@ def test_msm_pipelined_submit_collect(ctx, oracle):
     ta = ctx.msm_gens_submit_resident(d0.data_ptr(), n)
     tb = ctx.msm_gens_submit_resident(d1.data_ptr(), n)
     assert O.pt_eq(ctx.msm_gens_collect(ta), exp[0]) and O.pt_eq(ctx.msm_gens_collect(tb), exp[1])
-    # the blocking call splits large inputs over the two pipeline slots (copy of the second half overlaps the kernels of
-    # the first); forced here at a small size, odd length
+    # the blocking call splits large inputs into two or three point slices over the two pipeline slots (the copies of the
+    # later slices overlap the kernels of the earlier ones); forced here at a small size, odd length
     ctx.set_tuning("split_blocking", 10)
     try:
-        for first in (5, 1, 8, 15):  # size of the first slice in sixteenths (5 is the default)
+        exp_off = O.msm_affine(gs[3:n], scs[1][:n - 3], threads=8)
+        # sizes of the first and second slice in sixteenths (2 + 5 + the rest is the default; second = 0: two slices)
+        for first, second in ((2, 5), (5, 0), (1, 0), (8, 0), (15, 0), (1, 1), (7, 8), (1, 14), (15, 5)):
             ctx.set_tuning("split_first_16ths", first)
-            assert O.pt_eq(ctx.msm_gens(scs[0]), exp[0])
-            assert O.pt_eq(ctx.msm_gens(scs[1][:n - 3], off=3), O.msm_affine(gs[3:n], scs[1][:n - 3], threads=8))
+            ctx.set_tuning("split_second_16ths", second)
+            assert O.pt_eq(ctx.msm_gens(scs[0]), exp[0]), (first, second)
+            assert O.pt_eq(ctx.msm_gens(scs[1][:n - 3], off=3), exp_off), (first, second)
     finally:
         ctx.set_tuning("split_blocking", 23)
-        ctx.set_tuning("split_first_16ths", 5)
+        ctx.set_tuning("split_first_16ths", 2)
+        ctx.set_tuning("split_second_16ths", 5)
     # a third submit without collecting is refused, not queued silently
     import halo_accumulation_b200 as H
     t0, t1 = ctx.msm_gens_submit(scs[0]), ctx.msm_gens_submit(scs[1])

@@ -76,13 +76,17 @@ def test_rank_form_two_threads_matches_oracle(halo, oracle):
                 torch.cuda.synchronize(r)
                 res[(r, "res")] = comm.msm_gens_sharded_resident(d.data_ptr(), count, n_total)
                 res[(r, "gather")] = comm.allgather_sum(ctx.msm_gens(loc))
-                # the host-scalar call as two pipelined point slices (automatic from 2^23 points per rank; forced here), FIXED
-                # and variable base
+                # the host-scalar call as three (default) or two pipelined point slices (automatic from 2^23 points per rank;
+                # forced here), FIXED and variable base
                 ctx.set_tuning("split_blocking", 12)
                 res[(r, "split_fix")] = comm.msm_gens_sharded(loc, n_total)
                 ctx.set_fixed_base(False)
                 res[(r, "split_var")] = comm.msm_gens_sharded(loc, n_total)
+                ctx.set_tuning("split_second_16ths", 0)
+                res[(r, "split2_var")] = comm.msm_gens_sharded(loc, n_total)
                 ctx.set_fixed_base(True)
+                res[(r, "split2_fix")] = comm.msm_gens_sharded(loc, n_total)
+                ctx.set_tuning("split_second_16ths", 5)
                 ctx.set_tuning("split_blocking", 23)
                 # a short MSM that lives entirely on rank 0's slice: rank 1 contributes nothing
                 k = 1000
@@ -98,7 +102,7 @@ def test_rank_form_two_threads_matches_oracle(halo, oracle):
     [t.join() for t in th]
     assert not errs, errs
     for r in range(g):
-        for k in ("var", "fix", "res", "gather", "split_fix", "split_var"):
+        for k in ("var", "fix", "res", "gather", "split_fix", "split_var", "split2_var", "split2_fix"):
             assert O.pt_eq(res[(r, k)], exp), (r, k)
         assert O.pt_eq(res[(r, "short")], O.msm_derived_by_dlog(0, sc[:1000], threads=4)), r
 
