@@ -76,7 +76,7 @@ def hostcheck():
     device runs; and the 64-bit host path used by the transcript glue)."""
     d = os.path.join(ROOT, "tests", "hostcheck")
     libs = {}
-    for tag, flags in (("portable", ["-DHALO_FP_FORCE_PORTABLE"]), ("host64", [])):
+    for tag, flags in (("portable", ["-DHALO_FP_FORCE_PORTABLE"]), ("host64", []), ("host64_c", ["-DHALO_FP_NO_X64_ASM"])):
         so = os.path.join(d, f"libhostcheck_{tag}{'' if CURVE == 'pallas' else '_vesta'}.so")
         flags = flags + (["-DHALO_CURVE_VESTA"] if CURVE == "vesta" else [])
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", *flags, "-o", so,
@@ -89,7 +89,7 @@ def _p32(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint32))
 
 
-@pytest.mark.parametrize("tag", ["portable", "host64"])
+@pytest.mark.parametrize("tag", ["portable", "host64", "host64_c"])
 def test_shared_field_core_vs_python(hostcheck, oracle, tag):
     hc = hostcheck[tag]
     rnd = random.Random(3)
@@ -138,6 +138,30 @@ def test_division_step_inversion_vs_fermat(hostcheck, oracle, tag):
             r = np.zeros(4, dtype=np.uint64)
             hc.hc_fp_inv(which, _p32(Aa), _p32(r))
             assert oracle.limbs_to_int(r) == pow(a, -1, mod) * r2 % mod
+
+
+def test_host_field_implementations_agree(hostcheck, oracle):
+    """The host field core exists three times: MULX / ADC chains in x86-64 inline assembly (what the library's host glue runs on
+    a CPU with BMI2: Horner finish of every variable-base MSM, the verifier's scalar multiplications), the 64-bit C versions
+    (other CPUs) and the portable 32-bit-limb multiplication (the device algorithm).  All must agree bit for bit -- 40 000
+    random operand pairs per field, the edge values crossed with each other, results aliasing an operand, squares."""
+    rnd = random.Random(2024)
+    for tag in ("host64", "host64_c"):
+        hc = hostcheck[tag]
+        hc.hc_fp_impl_cross.restype = C.c_uint64
+        for which, mod in ((0, PR.P), (1, PR.R)):
+            edge = [0, 1, 2, mod - 1, mod - 2, (mod + 1) // 2, mod >> 1, (1 << 256) % mod, (1 << 255) % mod, (1 << 254) - 1, 1 << 253,
+                    (1 << 64) - 1, 1 << 64, (1 << 128) - 1, 1 << 128, (1 << 192) - 1, 1 << 192, mod - (1 << 64), mod - (1 << 128),
+                    mod - (1 << 192), (1 << 254) % mod, 0xFFFFFFFF, 1 << 32]
+            pairs = [(a, b) for a in edge for b in edge] + [(rnd.randrange(mod), rnd.randrange(mod)) for _ in range(40000)]
+            A = np.array([oracle.int_to_limbs(a) for a, _ in pairs], dtype=np.uint64)
+            B = np.array([oracle.int_to_limbs(b) for _, b in pairs], dtype=np.uint64)
+            assert hc.hc_fp_impl_cross(which, _p32(A), _p32(B), C.c_uint64(len(pairs))) == 0, (tag, which)
+    # this suite must have exercised the assembly path where the CPU offers it (x86-64 with BMI2), and never in the C build
+    assert hostcheck["host64_c"].hc_fp_uses_x64_asm() == 0
+    import platform
+    if platform.machine() == "x86_64" and "bmi2" in open("/proc/cpuinfo").read():
+        assert hostcheck["host64"].hc_fp_uses_x64_asm() == 2
 
 
 @pytest.mark.parametrize("tag", ["portable", "host64"])
