@@ -180,7 +180,7 @@ def run_reference(args):
     ok = bool(O.pt_eq(res, O.msm_derived_by_dlog(0, scalars, threads=threads)))
     val = n / dt
     sample = (f"one MSM of 2^{args.log_n} points per step = the full per-GPU workload, {args.steps} timed steps after "
-              f"{min(args.warmup, 1)} warm-up; windows x point chunks over {threads} host threads"
+              f"{min(args.warmup, 1)} warm-up; field core in MULX / ADC assembly, windows x point chunks over {threads} host threads"
               + (f"; with {world} GPUs the other arm runs {world} such slices at once, this arm times one slice" if world > 1 else ""))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -359,7 +359,7 @@ def run_ours(args):
         oracle_match["pippenger_same_size"] = bool(O.pt_eq(res, exp))
         cpu = {"value": n / dt, "unit": UNIT, "cores": threads_cpu, "kind": "port",
                "sample": f"1 MSM of 2^{args.log_n} points = the full workload, same bases and scalars as the GPU arm ({dt:.1f} s); "
-                         f"arkworks-shaped Pippenger restated in C, windows x point chunks over {threads_cpu} threads"}
+                         f"arkworks-shaped Pippenger restated in C (field core in MULX / ADC assembly), windows x point chunks over {threads_cpu} threads"}
     ok_all = all(oracle_match.values())
     if world > 1:
         t = torch.tensor([1.0 if ok_all else 0.0], device=dev, dtype=torch.float64)

@@ -239,14 +239,14 @@ inline void add_x64(uint32_t r32[8], const uint32_t a32[8], const uint32_t b32[8
     const u64m* a = reinterpret_cast<const u64m*>(a32);
     const u64m* b = reinterpret_cast<const u64m*>(b32);
     uint64_t s0, s1, s2, s3, d0, d1, d2, d3, l;
-    __asm__("movq %[a0], %[s0]\n\t"
-            "movq %[a1], %[s1]\n\t"
-            "movq %[a2], %[s2]\n\t"
-            "movq %[a3], %[s3]\n\t"
-            "addq %[b0], %[s0]\n\t"
-            "adcq %[b1], %[s1]\n\t"
-            "adcq %[b2], %[s2]\n\t"
-            "adcq %[b3], %[s3]\n\t"  // a, b < p < 2^255: no carry out
+    __asm__("movq (%[ap]), %[s0]\n\t"
+            "movq 8(%[ap]), %[s1]\n\t"
+            "movq 16(%[ap]), %[s2]\n\t"
+            "movq 24(%[ap]), %[s3]\n\t"
+            "addq (%[bp]), %[s0]\n\t"
+            "adcq 8(%[bp]), %[s1]\n\t"
+            "adcq 16(%[bp]), %[s2]\n\t"
+            "adcq 24(%[bp]), %[s3]\n\t"  // a, b < p < 2^255: no carry out
             "movabsq $0x4000000000000000, %[l]\n\t"
             "movq %[s0], %[d0]\n\t"
             "movq %[s1], %[d1]\n\t"
@@ -262,8 +262,8 @@ inline void add_x64(uint32_t r32[8], const uint32_t a32[8], const uint32_t b32[8
             "cmovcq %[s3], %[d3]\n\t"
             : [s0] "=&r"(s0), [s1] "=&r"(s1), [s2] "=&r"(s2), [s3] "=&r"(s3), [d0] "=&r"(d0), [d1] "=&r"(d1), [d2] "=&r"(d2),
               [d3] "=&r"(d3), [l] "=&r"(l)
-            : [a0] "m"(a[0]), [a1] "m"(a[1]), [a2] "m"(a[2]), [a3] "m"(a[3]), [b0] "m"(b[0]), [b1] "m"(b[1]), [b2] "m"(b[2]),
-              [b3] "m"(b[3]), [kp0] "m"(K[0]), [kp1] "m"(K[1])
+            : [ap] "r"(a), [bp] "r"(b), "m"(*reinterpret_cast<const u64m(*)[4]>(a)), "m"(*reinterpret_cast<const u64m(*)[4]>(b)),
+              [kp0] "m"(K[0]), [kp1] "m"(K[1])
             : "cc");
     u64m* r = reinterpret_cast<u64m*>(r32);
     r[0] = d0, r[1] = d1, r[2] = d2, r[3] = d3;
@@ -274,14 +274,14 @@ inline void sub_x64(uint32_t r32[8], const uint32_t a32[8], const uint32_t b32[8
     const u64m* a = reinterpret_cast<const u64m*>(a32);
     const u64m* b = reinterpret_cast<const u64m*>(b32);
     uint64_t d0, d1, d2, d3, m, q0, q1, q3;
-    __asm__("movq %[a0], %[d0]\n\t"
-            "movq %[a1], %[d1]\n\t"
-            "movq %[a2], %[d2]\n\t"
-            "movq %[a3], %[d3]\n\t"
-            "subq %[b0], %[d0]\n\t"
-            "sbbq %[b1], %[d1]\n\t"
-            "sbbq %[b2], %[d2]\n\t"
-            "sbbq %[b3], %[d3]\n\t"
+    __asm__("movq (%[ap]), %[d0]\n\t"
+            "movq 8(%[ap]), %[d1]\n\t"
+            "movq 16(%[ap]), %[d2]\n\t"
+            "movq 24(%[ap]), %[d3]\n\t"
+            "subq (%[bp]), %[d0]\n\t"
+            "sbbq 8(%[bp]), %[d1]\n\t"
+            "sbbq 16(%[bp]), %[d2]\n\t"
+            "sbbq 24(%[bp]), %[d3]\n\t"
             "sbbq %[m], %[m]\n\t"  // all ones if a < b: add p back
             "movq %[kp0], %[q0]\n\t"
             "movq %[kp1], %[q1]\n\t"
@@ -295,8 +295,8 @@ inline void sub_x64(uint32_t r32[8], const uint32_t a32[8], const uint32_t b32[8
             "adcq %[q3], %[d3]\n\t"
             : [d0] "=&r"(d0), [d1] "=&r"(d1), [d2] "=&r"(d2), [d3] "=&r"(d3), [m] "=&r"(m), [q0] "=&r"(q0), [q1] "=&r"(q1),
               [q3] "=&r"(q3)
-            : [a0] "m"(a[0]), [a1] "m"(a[1]), [a2] "m"(a[2]), [a3] "m"(a[3]), [b0] "m"(b[0]), [b1] "m"(b[1]), [b2] "m"(b[2]),
-              [b3] "m"(b[3]), [kp0] "m"(K[0]), [kp1] "m"(K[1])
+            : [ap] "r"(a), [bp] "r"(b), "m"(*reinterpret_cast<const u64m(*)[4]>(a)), "m"(*reinterpret_cast<const u64m(*)[4]>(b)),
+              [kp0] "m"(K[0]), [kp1] "m"(K[1])
             : "cc");
     u64m* r = reinterpret_cast<u64m*>(r32);
     r[0] = d0, r[1] = d1, r[2] = d2, r[3] = d3;
@@ -501,14 +501,14 @@ inline bool cpu_has_bmi2() {
 inline const bool g_has_bmi2 = cpu_has_bmi2();  // (read as false before its initialiser has run: the portable path is taken)
 }  // namespace host64
 #define HALO_X64_ROW(bi, T0, T1, T2, T3, T4) /* T4 is zero on entry: the high half of the last product lands in it directly */ \
-    "movq %[" bi "], %%rdx\n\t"               \
-    "mulx %[a0], %[l], %[h0]\n\t"             \
+    "movq " bi "(%[bp]), %%rdx\n\t"               \
+    "mulx (%[ap]), %[l], %[h0]\n\t"             \
     "addq %[l], %[" T0 "]\n\t"                \
-    "mulx %[a1], %[l], %[h1]\n\t"             \
+    "mulx 8(%[ap]), %[l], %[h1]\n\t"             \
     "adcq %[l], %[" T1 "]\n\t"                \
-    "mulx %[a2], %[l], %[h2]\n\t"             \
+    "mulx 16(%[ap]), %[l], %[h2]\n\t"             \
     "adcq %[l], %[" T2 "]\n\t"                \
-    "mulx %[a3], %[l], %[" T4 "]\n\t"         \
+    "mulx 24(%[ap]), %[l], %[" T4 "]\n\t"         \
     "adcq %[l], %[" T3 "]\n\t"                \
     "adcq $0, %[" T4 "]\n\t"                  \
     "addq %[h0], %[" T1 "]\n\t"               \
@@ -542,10 +542,10 @@ inline void fp_mul_x64(uint32_t r32[8], const uint32_t a32[8], const uint32_t b3
             "xorl %k[t1], %k[t1]\n\t"
             "xorl %k[t2], %k[t2]\n\t"
             "xorl %k[t3], %k[t3]\n\t"  //
-            HALO_X64_ROW("b0", "t0", "t1", "t2", "t3", "t4") HALO_X64_RED("t0", "t1", "t2", "t3", "t4")  //
-            HALO_X64_ROW("b1", "t1", "t2", "t3", "t4", "t0") HALO_X64_RED("t1", "t2", "t3", "t4", "t0")  //
-            HALO_X64_ROW("b2", "t2", "t3", "t4", "t0", "t1") HALO_X64_RED("t2", "t3", "t4", "t0", "t1")  //
-            HALO_X64_ROW("b3", "t3", "t4", "t0", "t1", "t2") HALO_X64_RED("t3", "t4", "t0", "t1", "t2")
+            HALO_X64_ROW("0", "t0", "t1", "t2", "t3", "t4") HALO_X64_RED("t0", "t1", "t2", "t3", "t4")  //
+            HALO_X64_ROW("8", "t1", "t2", "t3", "t4", "t0") HALO_X64_RED("t1", "t2", "t3", "t4", "t0")  //
+            HALO_X64_ROW("16", "t2", "t3", "t4", "t0", "t1") HALO_X64_RED("t2", "t3", "t4", "t0", "t1")  //
+            HALO_X64_ROW("24", "t3", "t4", "t0", "t1", "t2") HALO_X64_RED("t3", "t4", "t0", "t1", "t2")
             // the value is (t4, t0, t1, t2) < 2p: subtract p once if that does not borrow
             "movq %[t4], %[h0]\n\t"
             "movq %[t0], %[h1]\n\t"
@@ -562,8 +562,8 @@ inline void fp_mul_x64(uint32_t r32[8], const uint32_t a32[8], const uint32_t b3
             "cmovcq %[t2], %[l]\n\t"
             : [t0] "=&r"(t0), [t1] "=&r"(t1), [t2] "=&r"(t2), [t3] "=&r"(t3), [t4] "=&r"(t4), [l] "=&r"(l), [h0] "=&r"(h0),
               [h1] "=&r"(h1), [h2] "=&r"(h2)
-            : [a0] "m"(a[0]), [a1] "m"(a[1]), [a2] "m"(a[2]), [a3] "m"(a[3]), [b0] "m"(b[0]), [b1] "m"(b[1]), [b2] "m"(b[2]),
-              [b3] "m"(b[3]), [kp0] "m"(K[0]), [kp1] "m"(K[1]), [kinv] "m"(K[2])
+            : [ap] "r"(a), [bp] "r"(b), "m"(*reinterpret_cast<const host64::u64a(*)[4]>(a)),
+              "m"(*reinterpret_cast<const host64::u64a(*)[4]>(b)), [kp0] "m"(K[0]), [kp1] "m"(K[1]), [kinv] "m"(K[2])
             : "rdx", "cc");
     host64::u64a* r = reinterpret_cast<host64::u64a*>(r32);
     r[0] = h0, r[1] = h1, r[2] = h2, r[3] = l;

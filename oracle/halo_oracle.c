@@ -143,6 +143,24 @@ int orc_num_threads(void) {
 /* exported field helpers                                                                      */
 /* ------------------------------------------------------------------------------------------ */
 void orc_fp_mul(int w, const u64 a[4], const u64 b[4], u64 r[4]) { if (w) fr_mul(r, a, b); else fq_mul(r, a, b); }
+/* count of pairs on which the assembly multiplication / addition / subtraction and their C definitions (fp_tmpl.h) disagree,
+ * or a result is not reduced */
+u64 orc_fp_mul_cross(int w, const u64 *a, const u64 *b, u64 n) {
+    u64 bad = 0;
+    for (u64 i = 0; i < n; i++) {
+        u64 x[4], y[4];
+        if (w) {
+            fr_mul(x, a + 4 * i, b + 4 * i); fr_mul_c(y, a + 4 * i, b + 4 * i); bad += !fr_eq(x, y) || fr_geq_p(x);
+            fr_add(x, a + 4 * i, b + 4 * i); fr_add_c(y, a + 4 * i, b + 4 * i); bad += !fr_eq(x, y) || fr_geq_p(x);
+            fr_sub(x, a + 4 * i, b + 4 * i); fr_sub_c(y, a + 4 * i, b + 4 * i); bad += !fr_eq(x, y) || fr_geq_p(x);
+        } else {
+            fq_mul(x, a + 4 * i, b + 4 * i); fq_mul_c(y, a + 4 * i, b + 4 * i); bad += !fq_eq(x, y) || fq_geq_p(x);
+            fq_add(x, a + 4 * i, b + 4 * i); fq_add_c(y, a + 4 * i, b + 4 * i); bad += !fq_eq(x, y) || fq_geq_p(x);
+            fq_sub(x, a + 4 * i, b + 4 * i); fq_sub_c(y, a + 4 * i, b + 4 * i); bad += !fq_eq(x, y) || fq_geq_p(x);
+        }
+    }
+    return bad;
+}
 void orc_fp_add(int w, const u64 a[4], const u64 b[4], u64 r[4]) { if (w) fr_add(r, a, b); else fq_add(r, a, b); }
 void orc_fp_sub(int w, const u64 a[4], const u64 b[4], u64 r[4]) { if (w) fr_sub(r, a, b); else fq_sub(r, a, b); }
 void orc_fp_inv(int w, const u64 a[4], u64 r[4]) { if (w) fr_inv(r, a); else fq_inv(r, a); }

@@ -83,6 +83,7 @@ void orc_sha3_256(const uint8_t *msg, uint64_t len, uint8_t out[32]);
 
 /* ---- field arithmetic (which: 0 = Fq base field, 1 = Fr scalar field) ---- */
 void orc_fp_mul(int which, const uint64_t a[4], const uint64_t b[4], uint64_t r[4]);
+uint64_t orc_fp_mul_cross(int which, const uint64_t *a, const uint64_t *b, uint64_t n); /* asm vs C definition, count of mismatches */
 void orc_fp_add(int which, const uint64_t a[4], const uint64_t b[4], uint64_t r[4]);
 void orc_fp_sub(int which, const uint64_t a[4], const uint64_t b[4], uint64_t r[4]);
 void orc_fp_inv(int which, const uint64_t a[4], uint64_t r[4]);

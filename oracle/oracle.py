@@ -141,6 +141,14 @@ def fp_mul(a, b, which):
     return r
 
 
+def fp_mul_cross(a, b, which):
+    """Mismatches between the assembly multiplication / addition / subtraction and their C definitions over pairs of residues."""
+    a, b = np.ascontiguousarray(a, dtype=np.uint64), np.ascontiguousarray(b, dtype=np.uint64)
+    f = lib().orc_fp_mul_cross
+    f.restype = C.c_uint64
+    return int(f(which, _p(a), _p(b), C.c_uint64(a.shape[0])))
+
+
 def fp_inv(a, which):
     a = _arr(a)
     r = np.zeros(4, dtype=np.uint64)
