@@ -183,7 +183,8 @@ MsmPlan comm_plan(const halo_comm* c, uint64_t n_global, bool fixed) {
 struct LocalSlice {
     const fr_t* d_scalars;
     uint64_t off, n;
-    cudaEvent_t ready;  // may be null
+    cudaEvent_t ready;      // may be null
+    const uint64_t* h_src;  // host scalars still to be copied to d_scalars on the copy stream (then `ready` is recorded), or null
 };
 void sharded_msm(halo_comm* c, const LocalSlice* sl, int nsl, uint64_t n_global, xyzz_t& out) {
     halo_ctx* ctx = c->ctx;
@@ -204,6 +205,12 @@ void sharded_msm(halo_comm* c, const LocalSlice* sl, int nsl, uint64_t n_global,
     HALO_CUDA(cudaMemcpyAsync(d_send, &h, sizeof h, cudaMemcpyHostToDevice, st));
     for (int k = 0; k < nsl; k++) {
         xyzz_t* d_parts = d_send + 1 + (size_t)3 * nwin * k;
+        if (sl[k].h_src) {
+            // the copy is issued here, slice by slice: staging a PAGEABLE slice blocks this thread, and the kernels of the
+            // slices already enqueued run meanwhile
+            h2d_copy(ctx, const_cast<fr_t*>(sl[k].d_scalars), sl[k].h_src, sl[k].n * sizeof(fr_t), ctx->copy_stream);
+            HALO_CUDA(cudaEventRecord(sl[k].ready, ctx->copy_stream));
+        }
         if (sl[k].ready) HALO_CUDA(cudaStreamWaitEvent(st, sl[k].ready, 0));
         if (sl[k].n) {
             MsmInput in;
@@ -242,7 +249,7 @@ void sharded_msm(halo_comm* c, const LocalSlice* sl, int nsl, uint64_t n_global,
     msm_finish_host(sum.data(), plan, out);
 }
 void sharded_msm(halo_comm* c, const fr_t* d_scalars, uint64_t off_local, uint64_t n_local, uint64_t n_global, xyzz_t& out) {
-    LocalSlice one{d_scalars, off_local, n_local, nullptr};
+    LocalSlice one{d_scalars, off_local, n_local, nullptr, nullptr};
     sharded_msm(c, &one, 1, n_global, out);
 }
 }  // namespace
@@ -390,9 +397,7 @@ int halo_msm_gens_sharded(halo_comm* c, const uint64_t* local_scalars, uint64_t 
         for (int k = 0; k < nsl; k++) {
             if (!c->copied[k]) HALO_CUDA(cudaEventCreateWithFlags(&c->copied[k], cudaEventDisableTiming));
             const uint64_t lo = cut[k], hi = k + 1 == nsl ? n_local : cut[k + 1];
-            h2d_copy(ctx, d + lo, local_scalars + 4 * lo, (hi - lo) * sizeof(fr_t), ctx->copy_stream);
-            HALO_CUDA(cudaEventRecord(c->copied[k], ctx->copy_stream));
-            sl[k] = LocalSlice{d + lo, off_local + lo, hi - lo, c->copied[k]};
+            sl[k] = LocalSlice{d + lo, off_local + lo, hi - lo, c->copied[k], local_scalars + 4 * lo};
         }
         sharded_msm(c, sl, nsl, n_global, r);
     } else {
