@@ -246,6 +246,8 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "acc_blocks_per_sm")) ctx->tune_acc_blocks_per_sm = value;
     else if (!strcmp(key, "acc_quad")) ctx->tune_acc_quad = value;
     else if (!strcmp(key, "acc_quad_max_buckets")) ctx->tune_acc_quad_max_buckets = value;
+    else if (!strcmp(key, "acc_quad_lanes")) ctx->tune_acc_quad_lanes = value;
+    else if (!strcmp(key, "acc_quad_blocks")) ctx->tune_acc_quad_blocks = value;
     else if (!strcmp(key, "pair_passes")) ctx->tune_pair_passes = value;
     else if (!strcmp(key, "split_blocking")) ctx->tune_split_blocking = value;
     else if (!strcmp(key, "split_first_16ths")) ctx->tune_split_first_16ths = value < 1 ? 1 : value > 15 ? 15 : value;

@@ -190,6 +190,7 @@ struct halo_ctx {
     void* stage_pinned[STAGE_THREADS * STAGE_SLOTS] = {};
     cudaEvent_t stage_ev[STAGE_THREADS * STAGE_SLOTS] = {};
     int tune_stage_pageable = 1;  // 0: hand pageable pointers to cudaMemcpyAsync as they are
+    int tune_acc_quad_lanes = 0, tune_acc_quad_blocks = 0;  // k_accumulate_quad: lanes per bucket (2 / 4) and CTAs per SM (4 / 6); 0 = policy
     int tune_stage_threads = 4;   // host threads that copy pageable chunks into the pinned ring (1 .. STAGE_THREADS)
     void* pinned = nullptr;
     size_t pinned_cap = 0;

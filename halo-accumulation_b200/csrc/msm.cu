@@ -731,13 +731,17 @@ __device__ __forceinline__ void xyzz_shfl_xor(xyzz_t& dst, const xyzz_t& src, in
     }
 }
 __device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q);
-__global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_quad(const affine_t* __restrict__ bases, uint32_t n,
-                                                                              const affine_t* __restrict__ tail_bases,
-                                                                              const uint32_t* __restrict__ offsets,
-                                                                              const uint32_t* __restrict__ entries, uint32_t NB,
-                                                                              xyzz_t* __restrict__ buckets, uint32_t split_len) {
+// L = 4 or 2 lanes per bucket; MINB CTAs of 128 threads per SM (4: 128 registers; 6: 80 registers -- enough resident lanes to
+// run 2^16 points' 24 576 buckets x 4 lanes in ONE wave instead of 1.3, measured slower: see the launch site)
+template <int L, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_accumulate_quad(const affine_t* __restrict__ bases, uint32_t n,
+                                                               const affine_t* __restrict__ tail_bases,
+                                                               const uint32_t* __restrict__ offsets,
+                                                               const uint32_t* __restrict__ entries, uint32_t NB,
+                                                               xyzz_t* __restrict__ buckets, uint32_t split_len) {
+    static_assert(L == 2 || L == 4, "lanes per bucket");
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t b = gt >> 2, k = gt & 3u;
+    const uint32_t b = gt / L, k = gt % L;
     uint32_t beg = 0, end = 0;
     if (b < NB) {
         beg = offsets[b];
@@ -746,26 +750,28 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_quad(co
     }
     xyzz_t acc;
     xyzz_set_inf(acc);
-    // software pipeline as in k_accumulate_static, stride 4
+    // software pipeline as in k_accumulate_static, stride L
     uint32_t e = beg + k;
-    uint32_t ent1 = e < end ? entries[e] : 0, ent2 = e + 4 < end ? entries[e + 4] : 0;
+    uint32_t ent1 = e < end ? entries[e] : 0, ent2 = e + L < end ? entries[e + L] : 0;
     affine_t p1;
     affine_set_inf(p1);
     if (e < end) p1 = acc_base<false>(bases, n, tail_bases, ent1);
-    for (; e < end; e += 4) {
+    for (; e < end; e += L) {
         const uint32_t ent0 = ent1;
         const affine_t p0 = p1;
         ent1 = ent2;
-        if (e + 8 < end) ent2 = entries[e + 8];
-        if (e + 4 < end) p1 = acc_base<false>(bases, n, tail_bases, ent1);
+        if (e + 2 * L < end) ent2 = entries[e + 2 * L];
+        if (e + L < end) p1 = acc_base<false>(bases, n, tail_bases, ent1);
         xyzz_madd(acc, p0, (ent0 >> 31) != 0);
     }
-    // merge the quad: every lane of the warp takes part in the shuffles
+    // merge the lanes of a bucket: every lane of the warp takes part in the shuffles
     xyzz_t other;
     xyzz_shfl_xor(other, acc, 1);
     xyzz_add_nl(acc, other);
-    xyzz_shfl_xor(other, acc, 2);
-    xyzz_add_nl(acc, other);
+    if (L == 4) {
+        xyzz_shfl_xor(other, acc, 2);
+        xyzz_add_nl(acc, other);
+    }
     if (b < NB && k == 0 && !(offsets[b + 1] - offsets[b] > split_len)) buckets[b] = acc;
 }
 
@@ -1366,8 +1372,20 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
     // 0.324 -> 0.229 ms; at 2^15 / 2^16 (82 k buckets: 4.3 waves of quads, two extra full additions per bucket) it loses
     const bool quad_lanes = !P && ctx->tune_acc_quad != 0 && NB <= (uint32_t)ctx->tune_acc_quad_max_buckets && ctx->tune_acc_static == 0 && !deep;
     if (quad_lanes) {
-        k_accumulate_quad<<<(unsigned)(((uint64_t)NB * 4 + 127) / 128), 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB,
-                                                                                  buckets, split_len);
+        // lanes per bucket and CTAs per SM (tunables acc_quad_lanes / acc_quad_blocks; 0 = the policy below)
+        int lanes = ctx->tune_acc_quad_lanes, minb = ctx->tune_acc_quad_blocks;
+        // measured (profiles/r02_acc_quad_lanes_blocks_ab.jsonl, 2^12 .. 2^16 points): 6 CTAs per SM (80 registers, one wave at
+        // 2^16 instead of 1.3) is 4-9 % slower than 4 CTAs (128 registers) at every size, 2 lanes 9-25 % slower than 4: the
+        // kernel is bound by issue slots and by the deepest lane of each warp, not by the partial second wave
+        if (lanes != 2 && lanes != 4) lanes = 4;
+        if (minb != 4 && minb != 6) minb = 4;
+        const unsigned qgrid = (unsigned)(((uint64_t)NB * lanes + 127) / 128);
+#define HALO_ACCQ(LL, MB) k_accumulate_quad<LL, MB><<<qgrid, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB, buckets, split_len)
+        if (lanes == 4 && minb == 4) HALO_ACCQ(4, 4);
+        else if (lanes == 4) HALO_ACCQ(4, 6);
+        else if (minb == 4) HALO_ACCQ(2, 4);
+        else HALO_ACCQ(2, 6);
+#undef HALO_ACCQ
     } else if (ctx->tune_acc_static == 1 || (ctx->tune_acc_static == 0 && deep)) {
         if (P)
             k_accumulate_static<true><<<(NB + 127) / 128, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB,
