@@ -269,6 +269,38 @@ def test_msm_oversized_buckets(ctx, oracle, fixed):
         ctx.derive_generators(1 << 16)
 
 
+def test_msm_from_pageable_host_memory_staged(halo, oracle):
+    """Host scalars in PAGEABLE memory (a numpy array, a Rust Vec<Fr>) of 32 MiB or more are staged by the library through a ring
+    of pinned 8 MiB chunks filled by 1..8 host threads (h2d_copy, csrc/capi.cu): odd lengths (last chunk partial, chunk count
+    not a multiple of the thread count), every thread count, staging off, the pipelined and the blocking three-slice path.
+    All results against the oracle (discrete-log property of the derived generators)."""
+    O = oracle
+    n = (1 << 20) + (1 << 18) + 12345  # 40.4 MiB of scalars: 6 chunks, the last one partial
+    ctx = halo.Context(0, 1 << 21)
+    ctx.derive_generators(n)
+    sc = O.random_scalars(n, 31)
+    exp = O.msm_derived_by_dlog(0, sc, threads=8)
+    exp_off = O.msm_derived_by_dlog(7, sc[: n - 7], threads=8)
+    try:
+        for threads in (1, 2, 3, 5, 8, 99):
+            ctx.set_tuning("stage_threads", threads)
+            assert O.pt_eq(ctx.msm_gens(sc), exp), threads
+        assert O.pt_eq(ctx.msm_gens(sc[: n - 7], off=7), exp_off)
+        ctx.set_tuning("stage_pageable", 0)  # the driver's own bounce buffer
+        assert O.pt_eq(ctx.msm_gens(sc), exp)
+        ctx.set_tuning("stage_pageable", 1)
+        ctx.set_tuning("stage_threads", 4)
+        # two staged submits in flight, then the blocking call as three slices (forced at this size: the slices fall below the
+        # staging threshold; staged slices are what tests/test_gpu_configs.py runs at 2^24)
+        t0, t1 = ctx.msm_gens_submit(sc), ctx.msm_gens_submit(sc[: n - 7], off=7)
+        assert O.pt_eq(ctx.msm_gens_collect(t0), exp) and O.pt_eq(ctx.msm_gens_collect(t1), exp_off)
+        ctx.set_tuning("split_blocking", 20)
+        assert O.pt_eq(ctx.msm_gens(sc), exp)
+        assert halo.check_canaries()[0] == 0
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("fixed,c", [(False, 13), (False, 16), (True, 16), (True, 19)])
 def test_msm_two_level_sort(ctx, oracle, fixed, c):
     """The staged two-level counting sort (k_sort_*, automatic from 2^26 entries) forced at 2^16 points: uniform, ragged and
