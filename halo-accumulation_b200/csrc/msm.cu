@@ -350,7 +350,6 @@ __global__ void __launch_bounds__(S2_THREADS) k_sort_coarse_count(const fr_t* __
 // one CTA of 1024 threads, up to 2 bins per thread
 __global__ void __launch_bounds__(1024) k_sort_coarse_scan(uint32_t* __restrict__ cta_hist, uint32_t nctas, uint32_t NC,
                                                            uint32_t* __restrict__ coarse_off, uint32_t* __restrict__ chunk_pre) {
-    __shared__ uint32_t sh_tot;
     uint32_t tot[2] = {0, 0};
     for (int r = 0; r < 2; r++) {
         const uint32_t t = threadIdx.x * 2 + r;
@@ -367,7 +366,6 @@ __global__ void __launch_bounds__(1024) k_sort_coarse_scan(uint32_t* __restrict_
     __syncthreads();
     uint32_t cex = block_exclusive_scan(ch0 + ch1, &ctotal);
     __syncthreads();
-    (void)sh_tot;
     for (int r = 0; r < 2; r++) {
         const uint32_t t = threadIdx.x * 2 + r;
         if (t < NC) {
