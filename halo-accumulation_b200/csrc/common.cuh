@@ -200,9 +200,10 @@ struct halo_ctx {
     int tune_acc_quad_max_buckets = 1 << 15;
     bool force_two_lanes = false;  // run a pair of large MSMs (deferred IPA rounds) on the two lanes as well
     int tune_ipa_two_lanes = 1, tune_ipa_freeze_len = 0;
-    int tune_ipa_frozen_c = 10;  // window of the frozen-tail MSMs (8192 points): round 1 measured 10 best with the one-lane single-slab reduction;
-                                 // with the two-level quad reduction 11 was (8192-point MSM 0.46 / 0.38 / 0.41 ms at c = 10 / 11 / 12), and with
-                                 // four lanes per bucket 10 is again (0.32 / 0.35 ms at c = 10 / 11)
+    int tune_ipa_frozen_c = 9;   // window of the frozen-tail MSMs (8192 points): round 1 measured 10 best with the one-lane single-slab reduction;
+                                 // with the two-level quad reduction 11 was (8192-point MSM 0.46 / 0.38 / 0.41 ms at c = 10 / 11 / 12), with
+                                 // four lanes per bucket 10 again (0.32 / 0.35 ms at c = 10 / 11), and once the host's Horner finish halved
+                                 // (assembly field core) 9: open at 2^20 46.0 -> 45.6 ms in three alternating runs
     int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
     int tune_ipa_defer2 = 0;    // later deferred stages over the materialised vector, at most this many rounds each; 0 = off: measured slower at 2^20
                                 // (rounds 3-6 as one stage: 4 x 2.1 ms L / R + 5.3 ms latency-bound fold of 8192 outputs against 4.9 + 6.2 ms; profiles/r02_ipa_stage2_probe.txt)
