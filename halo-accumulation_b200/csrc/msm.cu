@@ -24,6 +24,11 @@
 
 namespace halo {
 
+// This file is compiled twice (see msm_small.cu): the normal translation unit holds everything except the two kernels whose
+// lanes are few and out of step (k_accumulate_quad, k_reduce_slabs_quad); those live in the second unit, where the field
+// multiplication is an out-of-line call (HALO_FP_MUL_CALL).
+#ifndef HALO_MSM_SMALL_TU
+
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
@@ -597,6 +602,7 @@ __global__ void __launch_bounds__(S2_THREADS) k_sort_fine_scatter(const uint64_t
 // (one warp-aggregated atomicAdd per claim round), so every lane of a warp stays busy until the work runs out.  With
 // a static thread-per-bucket mapping the warp waits for its fullest bucket: bucket loads are Poisson, which costs
 // 10 % at 416 entries per bucket and 21 % at 96 (c = 22).
+#endif  // HALO_MSM_SMALL_TU
 // Entry / base fetch of the accumulation kernels.  Indirect: entries[e] = (index | sign << 31) into bases (or the tail).
 // DIRECT (after the pair-tree passes, msm_pairs.cu): slot e itself holds an affine partial sum, infinity is marked by
 // x = 2^256 - 1 and is mapped to the (0, 0) encoding xyzz_madd skips.
@@ -619,6 +625,7 @@ __device__ __forceinline__ affine_t acc_base(const affine_t* __restrict__ bases,
     return idx < n ? bases[idx] : tail_bases[idx - n];
 }
 
+#ifndef HALO_MSM_SMALL_TU
 #ifndef HALO_ACC_MIN_BLOCKS
 #define HALO_ACC_MIN_BLOCKS 4
 #endif
@@ -713,6 +720,8 @@ __global__ void __launch_bounds__(128, HALO_ACC_MIN_BLOCKS) k_accumulate_static(
     buckets[b] = acc;
 }
 
+#endif  // HALO_MSM_SMALL_TU
+
 // Four lanes per bucket (small MSMs).  With one lane per bucket a small MSM's accumulation lasts as long as its LONGEST
 // bucket: fills are Poisson, so at a mean of 8-16 entries some bucket has ~35 and the kernel takes 35 dependent mixed additions
 // (3.6 us each) while the average lane is done after 8 (ncu, 2^13 points: SMs active 56 % of the kernel, 18.5 of 32 lanes active
@@ -728,7 +737,8 @@ __device__ __forceinline__ void xyzz_shfl_xor(xyzz_t& dst, const xyzz_t& src, in
         dst.zzz.v[i] = __shfl_xor_sync(0xffffffffu, src.zzz.v[i], mask);
     }
 }
-__device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q);
+static __device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q);
+#ifdef HALO_MSM_SMALL_TU
 // L = 4 or 2 lanes per bucket; MINB CTAs of 128 threads per SM (4: 128 registers; 6: 80 registers -- enough resident lanes to
 // run 2^16 points' 24 576 buckets x 4 lanes in ONE wave instead of 1.3, measured slower: see the launch site)
 template <int L, int MINB>
@@ -773,9 +783,11 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate_quad(const affine_t* _
     if (b < NB && k == 0 && !(offsets[b + 1] - offsets[b] > split_len)) buckets[b] = acc;
 }
 
-__device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q) { xyzz_add(acc, q); }
-__device__ __noinline__ void xyzz_dbl_nl(xyzz_t& acc) { xyzz_dbl(acc, acc); }
+#endif  // HALO_MSM_SMALL_TU
+static __device__ __noinline__ void xyzz_add_nl(xyzz_t& acc, const xyzz_t& q) { xyzz_add(acc, q); }
+static __device__ __noinline__ void xyzz_dbl_nl(xyzz_t& acc) { xyzz_dbl(acc, acc); }
 
+#ifndef HALO_MSM_SMALL_TU
 // ------------------------------------------------------------------------------------------------
 // 4b. oversized buckets.  Uniform scalars fill buckets evenly, but legal inputs can pile everything into a few buckets
 //     (all scalars equal, tiny scalars, a constant polynomial): one lane would then add millions of points serially.
@@ -976,6 +988,10 @@ __global__ void __launch_bounds__(REDUCE_THREADS) k_reduce_slabs(const xyzz_t* _
     }
 }
 
+#endif  // HALO_MSM_SMALL_TU
+
+constexpr int RQ_MAX_T = 128;  // logical threads (quads) per CTA of k_reduce_slabs_quad: 512 physical threads
+#ifdef HALO_MSM_SMALL_TU
 // ------------------------------------------------------------------------------------------------
 // 5b. the same reduction with QUAD-COOPERATIVE point additions (the default; "reduce_quad" = 0 selects the kernel above).
 //     The reduction is a chain of ~30-70 dependent point additions per CTA with almost nothing to run beside it: its cost
@@ -1012,7 +1028,7 @@ __device__ __forceinline__ fq_t fq_sel(bool c, const fq_t& a, const fq_t& b) {
 __device__ __forceinline__ fq_t xyzz_coord(const xyzz_t& p, unsigned k) {
     return k == 0 ? p.x : k == 1 ? p.y : k == 2 ? p.zz : p.zzz;
 }
-__device__ __noinline__ fq_t quad_add(fq_t acc, fq_t q) {
+static __device__ __noinline__ fq_t quad_add(fq_t acc, fq_t q) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, k = lane & 3u, qb = lane & ~3u;
     // infinity <=> ZZ == 0: the flag lives on lane 2 of the quad
@@ -1073,7 +1089,6 @@ __device__ __noinline__ fq_t quad_add(fq_t acc, fq_t q) {
     return res;
 }
 
-constexpr int RQ_MAX_T = 128;  // logical threads (quads) per CTA: 512 physical threads
 // Same contract as k_reduce_slabs; blockDim.x = max(32, 4 * T), logical thread j = threadIdx.x / 4.
 __global__ void __launch_bounds__(4 * RQ_MAX_T) k_reduce_slabs_quad(const xyzz_t* __restrict__ in, const xyzz_t* __restrict__ extra,
                                                                     size_t in_stride, int T, int log_s, xyzz_t* __restrict__ outA,
@@ -1163,6 +1178,24 @@ __global__ void __launch_bounds__(4 * RQ_MAX_T) k_reduce_slabs_quad(const xyzz_t
     }
 }
 
+// Launchers of this unit's kernels (declared in msm.cuh, called by msm_enqueue in the normal unit).
+void launch_accumulate_quad(cudaStream_t st, int lanes, int minb, const affine_t* bases, uint32_t n, const affine_t* tail_bases,
+                            const uint32_t* offsets, const uint32_t* entries, uint32_t NB, xyzz_t* buckets, uint32_t split_len) {
+    const unsigned qgrid = (unsigned)(((uint64_t)NB * lanes + 127) / 128);
+#define HALO_ACCQ(LL, MB) k_accumulate_quad<LL, MB><<<qgrid, 128, 0, st>>>(bases, n, tail_bases, offsets, entries, NB, buckets, split_len)
+    if (lanes == 4 && minb == 4) HALO_ACCQ(4, 4);
+    else if (lanes == 4) HALO_ACCQ(4, 6);
+    else if (minb == 4) HALO_ACCQ(2, 4);
+    else HALO_ACCQ(2, 6);
+#undef HALO_ACCQ
+}
+void launch_reduce_slabs_quad(cudaStream_t st, dim3 grid, int T, int log_s, const xyzz_t* in, const xyzz_t* extra, size_t in_stride,
+                              xyzz_t* outA, xyzz_t* outR, xyzz_t* outE, int out_stride) {
+    k_reduce_slabs_quad<<<grid, 4 * T < 32 ? 32 : 4 * T, 0, st>>>(in, extra, in_stride, T, log_s, outA, outR, outE, out_stride);
+}
+#endif  // HALO_MSM_SMALL_TU
+
+#ifndef HALO_MSM_SMALL_TU
 // ------------------------------------------------------------------------------------------------
 // fixed-base tables: table[w * n + i] = 2^(off_w) * G_i (affine), w = 0 .. W-1, off_w = sum of the lower window widths
 // ------------------------------------------------------------------------------------------------
@@ -1377,13 +1410,7 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
         // kernel is bound by issue slots and by the deepest lane of each warp, not by the partial second wave
         if (lanes != 2 && lanes != 4) lanes = 4;
         if (minb != 4 && minb != 6) minb = 4;
-        const unsigned qgrid = (unsigned)(((uint64_t)NB * lanes + 127) / 128);
-#define HALO_ACCQ(LL, MB) k_accumulate_quad<LL, MB><<<qgrid, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB, buckets, split_len)
-        if (lanes == 4 && minb == 4) HALO_ACCQ(4, 4);
-        else if (lanes == 4) HALO_ACCQ(4, 6);
-        else if (minb == 4) HALO_ACCQ(2, 4);
-        else HALO_ACCQ(2, 6);
-#undef HALO_ACCQ
+        launch_accumulate_quad(st, lanes, minb, acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB, buckets, split_len);
     } else if (ctx->tune_acc_static == 1 || (ctx->tune_acc_static == 0 && deep)) {
         if (P)
             k_accumulate_static<true><<<(NB + 127) / 128, 128, 0, st>>>(acc_bases, acc_n, in.tail_bases, acc_offsets, entries, NB,
@@ -1428,7 +1455,7 @@ void msm_enqueue(halo_ctx* ctx, const MsmInput& in, MsmPlan& plan, xyzz_t* d_out
     auto reduce = [&](dim3 grid, int T, int log_s, const xyzz_t* src, const xyzz_t* extra, size_t stride, xyzz_t* oA, xyzz_t* oR, xyzz_t* oE,
                       int ostride) {
         if (quad)
-            k_reduce_slabs_quad<<<grid, 4 * T < 32 ? 32 : 4 * T, 0, st>>>(src, extra, stride, T, log_s, oA, oR, oE, ostride);
+            launch_reduce_slabs_quad(st, grid, T, log_s, src, extra, stride, oA, oR, oE, ostride);
         else
             k_reduce_slabs<<<grid, T, 0, st>>>(src, extra, stride, T, log_s, oA, oR, oE, ostride);
     };
@@ -1598,4 +1625,5 @@ void msm_gens_device(halo_ctx* ctx, const fr_t* d_scalars, uint64_t first, uint6
     msm_batch(ctx, &in, 1, &out);
 }
 
+#endif  // HALO_MSM_SMALL_TU
 }  // namespace halo

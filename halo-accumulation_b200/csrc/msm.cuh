@@ -43,4 +43,10 @@ void msm_batch(halo_ctx* ctx, const MsmInput* ins, int count, xyzz_t* outs, cons
 void msm_finish_host(const xyzz_t* wsums, const MsmPlan& plan, xyzz_t& out);
 // Full MSM with device-resident inputs; synchronises the context stream and returns the point on the host.
 void msm_device(halo_ctx* ctx, const affine_t* d_bases, const fr_t* d_scalars, uint64_t n, xyzz_t& out);
+// Kernels of the second translation unit of msm.cu (msm_small.cu: out-of-line field multiplication): four (or two) lanes per
+// bucket for the accumulation of small MSMs, and the quad-cooperative bucket reduction.
+void launch_accumulate_quad(cudaStream_t st, int lanes, int minb, const affine_t* bases, uint32_t n, const affine_t* tail_bases,
+                            const uint32_t* offsets, const uint32_t* entries, uint32_t NB, xyzz_t* buckets, uint32_t split_len);
+void launch_reduce_slabs_quad(cudaStream_t st, dim3 grid, int T, int log_s, const xyzz_t* in, const xyzz_t* extra, size_t in_stride,
+                              xyzz_t* outA, xyzz_t* outR, xyzz_t* outE, int out_stride);
 }  // namespace halo
