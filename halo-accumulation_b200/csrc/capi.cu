@@ -260,6 +260,7 @@ int halo_set_tuning(halo_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "sort2_min_lg")) ctx->tune_sort2_min_lg = value;
     else if (!strcmp(key, "pair_bwd_async")) ctx->tune_pair_bwd_async = value;
     else if (!strcmp(key, "ipa_defer_rounds")) ctx->tune_ipa_defer = value;
+    else if (!strcmp(key, "ipa_fold_call_min_lg")) ctx->tune_fold_call_min_lg = value;
     else if (!strcmp(key, "ipa_defer2_rounds")) ctx->tune_ipa_defer2 = value;
     else if (!strcmp(key, "ipa_two_lanes")) ctx->tune_ipa_two_lanes = value;
     else if (!strcmp(key, "ipa_freeze_len")) ctx->tune_ipa_freeze_len = value;

@@ -204,6 +204,7 @@ struct halo_ctx {
                                  // with the two-level quad reduction 11 was (8192-point MSM 0.46 / 0.38 / 0.41 ms at c = 10 / 11 / 12), with
                                  // four lanes per bucket 10 again (0.32 / 0.35 ms at c = 10 / 11), and once the host's Horner finish halved
                                  // (assembly field core) 9: open at 2^20 46.0 -> 45.6 ms in three alternating runs
+    int tune_fold_call_min_lg = 17;  // generator folds of >= 2^this outputs use the copy of k_fold_multi with the multiplication out of line (-1: never)
     int tune_ipa_defer = -1;    // -1: automatic (3 rounds when the FIXED-base tables cover the opening); 0: off; D: force
     int tune_ipa_defer2 = 0;    // later deferred stages over the materialised vector, at most this many rounds each; 0 = off: measured slower at 2^20
                                 // (rounds 3-6 as one stage: 4 x 2.1 ms L / R + 5.3 ms latency-bound fold of 8192 outputs against 4.9 + 6.2 ms; profiles/r02_ipa_stage2_probe.txt)

@@ -23,13 +23,17 @@ using namespace halo;
 
 namespace halo {
 
+// This file is compiled twice (see ipa_fold.cu): the second unit holds only k_fold_multi, under the name k_fold_multi_call and
+// with the field multiplication as an out-of-line call, for folds with many outputs.
+#ifndef HALO_FOLD_MIN_BLOCKS
+#define HALO_FOLD_MIN_BLOCKS 3  // 4 CTAs per SM (128 registers) spills and measures 10 % slower
+#endif
+#ifndef HALO_IPA_FOLD_TU
+
 #ifndef HALO_IPA_FREEZE_LEN
 #define HALO_IPA_FREEZE_LEN 8192
 #endif
 constexpr uint64_t IPA_FREEZE_LEN = HALO_IPA_FREEZE_LEN;
-#ifndef HALO_FOLD_MIN_BLOCKS
-#define HALO_FOLD_MIN_BLOCKS 3  // 168 registers; 4 CTAs per SM (128 registers) spills and measures 10 % slower
-#endif
 
 // ---- GLV: xi * P = k1 * P + k2 * phi(P), phi(x, y) = (beta x, y) = lambda * P, |k1|, |k2| < 2^129 ------------------
 // Pallas has j-invariant 0, so Fq contains a primitive cube root of unity beta and Fr the matching lambda
@@ -81,12 +85,15 @@ constexpr int FOLD_MAX_OPS = 3072;
 // reads it with uniform addresses (one L1 broadcast per operation, negligible beside the ~10 multiplications that follow).
 static_assert(FOLD_MAX_OPS == sizeof(halo::FoldOpsHost::code), "halo_ctx::fold_ops capacity");
 
+#endif  // HALO_IPA_FOLD_TU
+
 __device__ __forceinline__ uint64_t fold_term_offset(uint64_t n, int D, int t) {
     uint64_t off = 0;
     for (int k = 0; k < D; k++)
         if ((t >> k) & 1) off += n >> (k + 1);
     return off;
 }
+#ifndef HALO_IPA_FOLD_TU
 // Per term t >= 1 and output j: beta x (so phi(P) = (beta x, y)) and the denominator x - beta x of P - phi(P); the joint
 // sparse form below adds P, phi(P), P + phi(P) = (-(x + beta x), -y) [= -phi^2(P), free] or P - phi(P) [one affine
 // addition per term, inversions shared by batch_invert].
@@ -134,7 +141,12 @@ __global__ void __launch_bounds__(128) k_fold_prep2(const affine_t* __restrict__
     diff[(uint64_t)(t - 1) * m + j] = out;
 }
 
+#endif  // HALO_IPA_FOLD_TU
+
 // op code: 0xff = double; else (t - 1) | kind << 4 | sign << 7 with kind 0: P_t, 1: phi(P_t), 2: P_t + phi(P_t), 3: P_t - phi(P_t)
+#ifdef HALO_IPA_FOLD_TU
+#define k_fold_multi k_fold_multi_call
+#endif
 __global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_multi(const affine_t* __restrict__ G0, uint64_t n, int D,
                                                                          const fq_t* __restrict__ bx,
                                                                          const affine_t* __restrict__ diff,
@@ -184,6 +196,15 @@ __global__ void __launch_bounds__(128, HALO_FOLD_MIN_BLOCKS) k_fold_multi(const 
         fp_mul(d, acc.zz, acc.zzz);
     den[j] = d;
 }
+
+#ifdef HALO_IPA_FOLD_TU
+#undef k_fold_multi
+void launch_fold_multi_call(cudaStream_t st, unsigned grid, const affine_t* G0, uint64_t n, int D, const fq_t* bx, const affine_t* diff,
+                            const uint8_t* ops, int n_ops, xyzz_t* sums, fq_t* den) {
+    k_fold_multi_call<<<grid, 128, 0, st>>>(G0, n, D, bx, diff, ops, n_ops, sums, den);
+}
+}  // namespace halo
+#else  // the rest of the file belongs to the normal unit
 
 // ---- frozen tail: once the vectors are short the generators stop being folded -------------------------------------
 // Folding m elements costs one ~2300-modmul serial chain per element no matter how small m is (about a millisecond of
@@ -278,9 +299,17 @@ static void fold_multi(halo_ctx* ctx, const affine_t* src, uint64_t n, const fr_
     k_fold_prep1<<<pgrid, 128, 0, ctx->stream>>>(G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_den2.as<fq_t>());
     batch_invert(ctx, ctx->stream, ctx->ipa_den2.as<fq_t>(), (uint32_t)((T - 1) * m), ctx->ipa_inv_scratch);
     k_fold_prep2<<<pgrid, 128, 0, ctx->stream>>>(G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_den2.as<fq_t>(), ctx->ipa_diff.as<affine_t>());
-    k_fold_multi<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_diff.as<affine_t>(),
-                                                                       ctx->ipa_ops.as<uint8_t>(), no,
-                                                                       ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>());
+    // Many outputs: the copy of the kernel with the multiplication out of line (ipa_fold.cu).  The loop body inlines a doubling
+    // and a mixed addition behind four kinds of operand selection, ~75 KiB of code that every warp walks at its own pace; out of
+    // line the 2^17-output joint fold of an opening at 2^20 takes 12.7 instead of 15.0 ms, while folds of <= 2^15 outputs
+    // (latency bound, a warp or two per SM) are 5-10 % faster inlined (profiles/r02_fold_multi_call_ab.txt).
+    if (ctx->tune_fold_call_min_lg >= 0 && m >= ((uint64_t)1 << ctx->tune_fold_call_min_lg))
+        launch_fold_multi_call(ctx->stream, (unsigned)((m + 127) / 128), G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_diff.as<affine_t>(),
+                               ctx->ipa_ops.as<uint8_t>(), no, ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>());
+    else
+        k_fold_multi<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(G0, n, D, ctx->ipa_bx.as<fq_t>(), ctx->ipa_diff.as<affine_t>(),
+                                                                           ctx->ipa_ops.as<uint8_t>(), no,
+                                                                           ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>());
     batch_invert(ctx, ctx->stream, ctx->ipa_den.as<fq_t>(), (uint32_t)m, ctx->ipa_inv_scratch);
     k_fold_finish<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(ctx->ipa_sums.as<xyzz_t>(), ctx->ipa_den.as<fq_t>(), m,
                                                                         ctx->ipa_G.as<affine_t>());
@@ -601,3 +630,4 @@ int halo_ipa_finish(halo_ipa* st, uint64_t U_jac[12], uint64_t c_out[4]) {
 }
 
 }  // extern "C"
+#endif  // HALO_IPA_FOLD_TU

@@ -32,3 +32,9 @@ struct halo_ipa {
     halo::affine_t hprime;  // affine H' on the host (the FIXED-base L / R add dot * H' there)
     std::vector<halo::fr_t> defer_xis;
 };
+
+namespace halo {
+// k_fold_multi of the second translation unit (ipa_fold.cu: field multiplication out of line), for folds with many outputs.
+void launch_fold_multi_call(cudaStream_t st, unsigned grid, const affine_t* G0, uint64_t n, int D, const fq_t* bx, const affine_t* diff,
+                            const uint8_t* ops, int n_ops, xyzz_t* sums, fq_t* den);
+}  // namespace halo

@@ -456,6 +456,30 @@ def test_open_second_deferred_stage(env, lg, defer2, freeze):
         ctx.set_tuning("ipa_freeze_len", 0)
 
 
+@pytest.mark.parametrize("lg,defer", [(13, 0), (14, 2), (15, 3)])
+def test_open_fold_kernel_with_out_of_line_multiplication(env, lg, defer):
+    """k_fold_multi exists twice: inlined multiplication (few outputs) and, in a second translation unit, the multiplication as
+    an out-of-line call (from 2^17 outputs: the joint fold of an opening at 2^20).  Forced here for every fold of small openings
+    ("ipa_fold_call_min_lg" = 0), single-round folds and deferred head rounds: same L, R, U, c as the oracle, and as the inlined
+    kernel ("ipa_fold_call_min_lg" = -1)."""
+    ctx, O, pcdl = env["ctx"], env["O"], env["pcdl"]
+    n = 1 << lg
+    d = n - 1
+    p = O.random_scalars(n - 3, 7000 + lg)
+    z = O.random_scalars(1, 71)[0]
+    exp = None
+    try:
+        ctx.set_tuning("ipa_defer_rounds", defer)
+        Cm = pcdl.commit(ctx, p, d)
+        exp = O.pcdl_open(p, Cm, d, z, threads=8)
+        for min_lg in (0, -1):
+            ctx.set_tuning("ipa_fold_call_min_lg", min_lg)
+            _same_proof(O, pcdl.open(ctx, p, Cm, d, z), exp)
+    finally:
+        ctx.set_tuning("ipa_fold_call_min_lg", 17)
+        ctx.set_tuning("ipa_defer_rounds", -1)
+
+
 def test_open_deferred_head_fixed_base_2_17(ctx, oracle):
     """The automatic policy: with FIXED-base tables covering the opening, three rounds are deferred and their L / R take
     the shared-bucket-set path (dot * H' added on the host).  n = 2^17 is the smallest size it triggers at; the oracle
