@@ -19,7 +19,11 @@ KERNELS = {
     "k_pair_bwd<stream>": "_ZN4halo10k_pair_bwdILb0EEE",
     "k_pair_fwd<PASS0>": "_ZN4halo10k_pair_fwdILb1EEE",
     "k_accumulate<indirect>": "_ZN4halo12k_accumulateILb0EEE",
-    "k_fold_multi": "_ZN4halo12k_fold_multiE",
+    "k_pair_bwd0 (pass 0, cp.async staging)": "_ZN4halo11k_pair_bwd0E",
+    "k_fold_multi (multiplication inlined: folds of < 2^17 outputs)": "_ZN4halo12k_fold_multiE",
+    "k_fold_multi_call (multiplication out of line, ipa_fold.cu: folds of >= 2^17 outputs)": "_ZN4halo17k_fold_multi_callE",
+    "k_accumulate_quad<4, 4> (msm_small.cu: multiplication out of line)": "_ZN4halo17k_accumulate_quadILi4ELi4EEE",
+    "k_reduce_slabs_quad (msm_small.cu: multiplication out of line)": "_ZN4halo19k_reduce_slabs_quadE",
     "k_reduce_slabs": "_ZN4halo14k_reduce_slabsE",
 }
 
