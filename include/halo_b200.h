@@ -59,8 +59,16 @@ const char *halo_curve_name(void);
 uint64_t halo_kernel_launches(halo_ctx *ctx);
 /* Tuning / diagnostics: force the Pippenger window width (0 = automatic). */
 int halo_set_msm_window(halo_ctx *ctx, int c);
-/* Measurement knobs (no effect on results): "acc_static" 1 / 2 = force thread-per-bucket / lane-level bucket claiming (0 = automatic)
- * in the accumulation kernel; "acc_blocks_per_sm" = CTAs per SM of the persistent accumulation grid (0 = default). */
+/* Measurement knobs (no effect on results; every value is exercised against the oracle in tests/).  Keys:
+ *   accumulation   "acc_static" 1 / 2 = force thread-per-bucket / lane-level bucket claiming (0 = automatic), "acc_blocks_per_sm",
+ *                  "acc_quad" (four lanes per bucket for small MSMs), "acc_quad_max_buckets", "acc_quad_lanes" (2 / 4), "acc_quad_blocks"
+ *                  (4 / 6 CTAs per SM), "pair_passes" (-1 = policy by bucket fill), "pair_bwd_async", "reduce_quad"
+ *   counting sort  "sort_ahead" (CTAs per SM of the sort of the next pipelined call), "sort2", "sort2_min_lg" (two-level staged sort)
+ *   host buffers   "split_blocking" (lg of the size from which the blocking call runs as point slices), "split_first_16ths",
+ *                  "split_second_16ths" (0 = two slices), "stage_pageable", "stage_threads" (1 .. 8)
+ *   opening        "ipa_defer_rounds" (-1 = automatic), "ipa_defer2_rounds", "ipa_two_lanes", "ipa_freeze_len", "ipa_frozen_c",
+ *                  "ipa_fold_call_min_lg" (folds of >= 2^v outputs use the kernel copy with the multiplication out of line)
+ * Unknown keys return HALO_EINVAL. */
 int halo_set_tuning(halo_ctx *ctx, const char *key, int value);
 /* Enable per-phase CUDA-event timing of the MSM; read back with halo_last_msm_timings (ms):
  * [digits, scan, scatter, accumulate, bucket_reduce, total]. */
